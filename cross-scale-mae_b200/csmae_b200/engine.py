@@ -1,0 +1,408 @@
+"""Executor of the Cross-Scale MAE hot path: one forward and one hand-written backward over the
+C-ABI kernels (include/csmae_b200.h), with torch supplying only device memory and streams.
+
+Dataflow restated from the reference (paths relative to the upstream repo):
+  models_mae/MAE_ViT_Baseline.py:243-320   forward_encoder / forward_decoder / forward
+  models_mae/MAE_ViT_MsLd.py:37-77         two scales, loss_orig + loss_crop
+  models_mae/MAE_ViT_MsLdCeCd.py:27-84     + predictor cross-decoder loss + NT-Xent
+Both scales run as ONE batched pass of 2N images (nothing in a Block mixes samples):
+images [0, N) are scale 1 ("orig"), [N, 2N) scale 2 ("crop").
+
+Precision policy (independent of the ambient autocast state, SURVEY.md 0.8 / 8a'): fp32 master
+weights and residual stream, bf16 tensor-core operands with fp32 accumulation, Linear outputs rounded
+to bf16 where the reference's autocast graph rounds them, LayerNorm / softmax / losses in fp32.
+
+Memory: activations needed by the backward live in a per-model workspace that is reused every step
+(the backward of step i always precedes the forward of step i+1).  A generation counter makes a
+stale backward fail loudly instead of reading overwritten activations.
+"""
+import torch
+
+from . import _native as nat
+from ._native import EPI_BF16, EPI_DGELU, EPI_F32, EPI_GELU, EPI_RESID, call
+
+LN_EPS = 1e-6          # MAE_ViT_Baseline.py:43-45
+BN_EPS = 1e-5          # nn.BatchNorm1d default (MLP.py:7)
+BN_MOMENTUM = 0.1
+NTXENT_TAU = 0.5       # MAE_ViT_MsLdCeCd.py:62
+NTXENT_EPS = 1e-8      # util/contrast_loss.py:51
+
+_GEMM_WEIGHT_SUFFIXES = ("qkv.weight", "proj.weight", "fc1.weight", "fc2.weight")
+
+
+class HotPathEngine:
+    def __init__(self, model, use_cd=False, use_ce=False):
+        self.model = model
+        self.use_cd = use_cd
+        self.use_ce = use_ce
+        self.generation = 0
+        self._bufs = {}
+        self._state = None          # what the last forward saved for the backward
+        self._w16 = None            # flat bf16 shadow of every GEMM weight
+        self._w16_views = {}
+        self._w16_key = None
+        self._w16_versions = None
+        self._cast_table = None
+        self._names = None
+        self._coefs = None
+        self._coefs_key = None
+        self._last_out = None
+
+    # ------------------------------------------------------------------ parameters
+    def param_names(self):
+        """Trainable parameters the hot path differentiates, in named_parameters() order.
+        encoder_norm.* is registered but never used (reference: MAE_ViT_Baseline.py:264)."""
+        if self._names is None:
+            names = []
+            for n, p in self.model.named_parameters():
+                if not p.requires_grad or n.startswith("encoder_norm."):
+                    continue
+                if n.startswith("predictor.") and not self.use_cd:
+                    continue
+                names.append(n)
+            self._names = names
+        return self._names
+
+    def _is_gemm_weight(self, name, p):
+        return p.dim() >= 2 and name.endswith(".weight") and "norm" not in name and not name.startswith("predictor.1")
+
+    def _refresh_weights(self, params):
+        """bf16 shadow copies of the GEMM weights, refreshed with one multi-tensor cast kernel when any
+        master weight changed (optimizer steps bump Tensor._version)."""
+        gemm = [(n, p) for n, p in params.items() if self._is_gemm_weight(n, p)]
+        key = tuple((n, p.data_ptr(), p.numel()) for n, p in gemm)
+        versions = tuple(p._version for _, p in gemm)
+        dev = gemm[0][1].device
+        if key != self._w16_key:
+            offsets, total = {}, 0
+            for n, p in gemm:
+                offsets[n] = total
+                total += (p.numel() + 7) // 8 * 8
+            self._w16 = torch.empty(total, dtype=torch.bfloat16, device=dev)
+            self._w16_views = {n: self._w16[offsets[n]:offsets[n] + p.numel()] for n, p in gemm}
+            table = []
+            for n, p in gemm:
+                table += [p.data_ptr(), self._w16_views[n].data_ptr(), p.numel()]
+            self._cast_table = torch.tensor(table, dtype=torch.int64).to(dev)
+            self._w16_key = key
+            self._w16_versions = None
+        if versions != self._w16_versions:
+            call("csm_cast_multi", self._cast_table, len(gemm), 32)
+            self._w16_versions = versions
+        return self._w16_views
+
+    # ------------------------------------------------------------------ workspace
+    def _buf(self, name, shape, dtype, device):
+        t = self._bufs.get(name)
+        if t is None or t.shape != torch.Size(shape) or t.dtype != dtype or t.device != device:
+            t = torch.empty(shape, dtype=dtype, device=device)
+            self._bufs[name] = t
+        return t
+
+    def workspace_bytes(self):
+        return sum(t.numel() * t.element_size() for t in self._bufs.values())
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, imgs_list, noises, mask_ratio, training):
+        m = self.model
+        dev = imgs_list[0].device
+        if dev.type != "cuda":
+            raise nat.NativeError("csmae_b200 runs on sm_100 CUDA devices only (no CPU fallback): got " + str(dev))
+        nsm = nat.sm_count(dev)
+        ns = len(imgs_list)
+        N, C, H, W = imgs_list[0].shape
+        assert H == W == m.input_size and C == m.input_channels, "input size mismatch"
+        NB = N * ns
+        L = m.num_patches
+        keep = int(L * (1 - mask_ratio))                       # MAE_ViT_Shared.py:64 (float truncation)
+        assert 1 <= keep <= L, f"mask_ratio={mask_ratio} keeps {keep} of {L} patches"
+        Se, Sd = keep + 1, L + 1
+        D, Dd, p = m.dim_model, m.decoder_embed_dim, m.patch_size
+        P = p * p * C
+        bf16, f32 = torch.bfloat16, torch.float32
+        params = dict(m.named_parameters())
+        w16 = self._refresh_weights(params)
+        buf = lambda name, shape, dt: self._buf(name, shape, dt, dev)
+        imgs_list = [im.contiguous().float() for im in imgs_list]
+
+        self.generation += 1
+        st = dict(N=N, ns=ns, NB=NB, L=L, keep=keep, Se=Se, Sd=Sd, D=D, Dd=Dd, C=C, H=H, p=p, P=P, nsm=nsm,
+                  imgs=imgs_list, training=training, generation=self.generation)
+
+        # ---- masking (MAE_ViT_Shared.py:57-84) --------------------------------------------------
+        noise = (torch.cat(noises, 0) if ns > 1 else noises[0]).contiguous().float()
+        ids_restore = buf("ids_restore", (NB, L), torch.int64)
+        ids_shuffle = buf("ids_shuffle", (NB, L), torch.int32)
+        mask = buf("mask", (NB, L), f32)
+        call("csm_random_masking", noise, NB, L, keep, ids_restore, ids_shuffle, mask)
+
+        # ---- patch embed on the kept patches only + pos embed + cls (Baseline.py:245-256) ------
+        patches = buf("patches", (NB * Se, P), bf16)
+        for s, im in enumerate(imgs_list):
+            call("csm_patch_gather", im, ids_shuffle[s * N:], patches[s * N * Se:], N, C, H, p, L, keep)
+        emb = buf("emb", (NB * Se, D), bf16)
+        call("csm_linear_fwd", patches, w16["patch_embed.proj.weight"], params["patch_embed.proj.bias"], emb, None,
+             NB * Se, D, P, EPI_BF16)
+        x = buf("enc.x0", (NB * Se, D), f32)
+        call("csm_encoder_assemble", emb, ids_shuffle, params["encoder_pos_embed"], params["cls_token"], x,
+             NB, L, keep, D)
+
+        # ---- encoder blocks; encoder_norm is computed-and-discarded upstream: skipped (Baseline.py:264)
+        x = self._blocks_fwd("enc", "encoder", len(m.encoder), x, NB, Se, D, m.encoder_num_heads, params, w16, dev)
+        enc_bf16 = buf("enc_bf16", (NB * Se, D), bf16)
+        call("csm_cast_f32_bf16", x, enc_bf16, NB * Se * D)
+
+        # ---- decoder (Baseline.py:268-297) -----------------------------------------------------
+        demb = buf("demb", (NB * Se, Dd), bf16)
+        call("csm_linear_fwd", enc_bf16, w16["decoder_embed.weight"], params["decoder_embed.bias"], demb, None,
+             NB * Se, Dd, D, EPI_BF16)
+        y = buf("dec.x0", (NB * Sd, Dd), f32)
+        call("csm_decoder_assemble", demb, ids_restore, params["mask_token"], params["decoder_pos_embed"], y,
+             NB, L, keep, Dd)
+        y = self._blocks_fwd("dec", "decoder", len(m.decoder), y, NB, Sd, Dd, m.decoder_num_heads, params, w16, dev)
+        dec_f32 = buf("dec_f32", (NB * Sd, Dd), f32)
+        dec_bf16 = buf("dec_bf16", (NB * Sd, Dd), bf16)
+        dn_mean = buf("dn_mean", (NB * Sd,), f32)
+        dn_rstd = buf("dn_rstd", (NB * Sd,), f32)
+        call("csm_layernorm_fwd", y, params["decoder_norm.weight"], params["decoder_norm.bias"], dec_bf16, dec_f32,
+             dn_mean, dn_rstd, NB * Sd, Dd, LN_EPS)
+        pred_full = buf("pred_full", (NB * Sd, P), bf16)
+        call("csm_linear_fwd", dec_bf16, w16["decoder_pred.weight"], params["decoder_pred.bias"], pred_full, None,
+             NB * Sd, P, Dd, EPI_BF16)
+
+        # ---- losses ----------------------------------------------------------------------------
+        loss_acc = buf("loss_acc", (8,), f32)
+        loss_acc.zero_()
+        norm_pix = 1 if m.norm_pix_loss else 0
+        for s, im in enumerate(imgs_list):
+            call("csm_recon_loss_fwd", pred_full[s * N * Sd:], im, mask[s * N:], loss_acc[s:], N, C, H, p, L, norm_pix)
+        n_masked = N * (L - keep)
+        red = 0.5 if (ns == 2 and getattr(m, "ms_decoder_loss_reduction", "sum") == "mean") else 1.0
+        coefs = [red / n_masked if n_masked > 0 else float("nan")] * ns + [0.0] * (8 - ns)
+        if ns == 2 and self.use_cd:
+            Hp = m.predictor[0].out_features
+            h1 = buf("pred.h1", (N * Sd, Hp), bf16)
+            call("csm_linear_fwd", dec_bf16[N * Sd:], w16["predictor.0.weight"], params["predictor.0.bias"], h1, None,
+                 N * Sd, Hp, Dd, EPI_BF16)
+            a1 = buf("pred.a1", (N * Sd, Hp), bf16)
+            bn = m.predictor[1]
+            bn_mean = buf("pred.bn_mean", (L,), f32)
+            bn_rstd = buf("pred.bn_rstd", (L,), f32)
+            call("csm_bn_patch_fwd", h1, bn.weight, bn.bias, a1, bn_mean, bn_rstd, bn.running_mean, bn.running_var,
+                 N, L, Hp, BN_EPS, BN_MOMENTUM, 1 if training else 0)
+            if training:
+                bn.num_batches_tracked.add_(1)
+            cp = buf("pred.cp", (N * Sd, Dd), bf16)
+            call("csm_linear_fwd", a1, w16["predictor.3.weight"], params["predictor.3.bias"], cp, None,
+                 N * Sd, Dd, Hp, EPI_BF16)
+            call("csm_cross_mse_fwd", cp, dec_f32, loss_acc[2:], N * Sd, Sd, Dd)
+            coefs[2] = 1.0 / (N * L * Dd)
+            st["Hp"] = Hp
+        if ns == 2 and self.use_ce:
+            zhat = buf("ntx.zhat", (NB, D), f32)
+            fnorm = buf("ntx.fnorm", (NB,), f32)
+            neg = buf("ntx.neg", (NB,), f32)
+            call("csm_ntxent_fwd", x, zhat, fnorm, neg, loss_acc[3:], N, Se, D, NTXENT_TAU, NTXENT_EPS)
+            coefs[3] = 1.0
+        ck = (tuple(coefs), dev)
+        if self._coefs_key != ck:
+            self._coefs = torch.tensor(coefs, dtype=f32).to(dev)
+            self._coefs_key = ck
+        loss = (loss_acc * self._coefs).sum()
+        st["coefs"] = coefs
+        st["red"] = red
+        self._state = st
+
+        pred = pred_full.view(NB, Sd, P)
+        enc = x.view(NB, Se, D)
+        dec = dec_f32.view(NB, Sd, Dd)
+        out = dict(loss=loss, loss_terms=loss_acc, pred=[pred[s * N:(s + 1) * N, 1:, :] for s in range(ns)],
+                   mask=[mask[s * N:(s + 1) * N] for s in range(ns)],
+                   ids_restore=[ids_restore[s * N:(s + 1) * N] for s in range(ns)],
+                   enc_emb=[enc[s * N:(s + 1) * N] for s in range(ns)],
+                   dec_emb=[dec[s * N:(s + 1) * N] for s in range(ns)])
+        return out
+
+    def _blocks_fwd(self, tag, pname, nlayers, x, NB, S, Dm, heads, params, w16, dev):
+        bf16, f32 = torch.bfloat16, torch.float32
+        rows = NB * S
+        d = Dm // heads
+        buf = lambda name, shape, dt: self._buf(name, shape, dt, dev)
+        for i in range(nlayers):
+            t, q = f"{tag}.{i}.", f"{pname}.{i}."
+            hid = params[q + "mlp.fc1.weight"].shape[0]
+            ln1 = buf(t + "ln1", (rows, Dm), bf16)
+            mean1, rstd1 = buf(t + "mean1", (rows,), f32), buf(t + "rstd1", (rows,), f32)
+            call("csm_layernorm_fwd", x, params[q + "norm1.weight"], params[q + "norm1.bias"], ln1, None, mean1, rstd1,
+                 rows, Dm, LN_EPS)
+            qkv = buf(t + "qkv", (rows, 3 * Dm), bf16)
+            call("csm_linear_fwd", ln1, w16[q + "attn.qkv.weight"], params[q + "attn.qkv.bias"], qkv, None,
+                 rows, 3 * Dm, Dm, EPI_BF16)
+            ao = buf(t + "ao", (rows, Dm), bf16)
+            lse = buf(t + "lse", (NB * heads * S,), f32)
+            call("csm_attention_fwd", qkv, ao, lse, NB, S, heads, d)
+            xmid = buf(t + "xmid", (rows, Dm), f32)
+            call("csm_linear_fwd", ao, w16[q + "attn.proj.weight"], params[q + "attn.proj.bias"], xmid, x,
+                 rows, Dm, Dm, EPI_RESID)
+            ln2 = buf(t + "ln2", (rows, Dm), bf16)
+            mean2, rstd2 = buf(t + "mean2", (rows,), f32), buf(t + "rstd2", (rows,), f32)
+            call("csm_layernorm_fwd", xmid, params[q + "norm2.weight"], params[q + "norm2.bias"], ln2, None, mean2,
+                 rstd2, rows, Dm, LN_EPS)
+            h = buf(t + "h", (rows, hid), bf16)
+            act = buf(t + "act", (rows, hid), bf16)
+            call("csm_linear_fwd", ln2, w16[q + "mlp.fc1.weight"], params[q + "mlp.fc1.bias"], h, act,
+                 rows, hid, Dm, EPI_GELU)
+            xout = buf(t + "xout", (rows, Dm), f32)
+            call("csm_linear_fwd", act, w16[q + "mlp.fc2.weight"], params[q + "mlp.fc2.bias"], xout, xmid,
+                 rows, Dm, hid, EPI_RESID)
+            x = xout
+        return x
+
+    # ------------------------------------------------------------------ backward
+    def backward(self, grad_loss, generation):
+        st = self._state
+        if st is None or st["generation"] != generation or generation != self.generation:
+            raise RuntimeError(
+                "csmae_b200: backward() of a forward whose activations were overwritten by a later forward of the "
+                "same module (the workspace holds one step); call backward before the next forward")
+        m = self.model
+        N, ns, NB, L, keep, Se, Sd = (st[k] for k in ("N", "ns", "NB", "L", "keep", "Se", "Sd"))
+        D, Dd, C, H, p, P, nsm = (st[k] for k in ("D", "Dd", "C", "H", "p", "P", "nsm"))
+        dev = st["imgs"][0].device
+        bf16, f32 = torch.bfloat16, torch.float32
+        params = dict(m.named_parameters())
+        w16 = self._w16_views
+        B = self._bufs
+        buf = lambda name, shape, dt: self._buf(name, shape, dt, dev)
+        names = self.param_names()
+        sizes = [params[n].numel() for n in names]
+        offs, total = [], 0
+        for s_ in sizes:
+            offs.append(total)
+            total += (s_ + 3) // 4 * 4                         # keep every gradient 16-byte aligned
+        flat = torch.zeros(total, dtype=f32, device=dev)
+        G = {n: flat[o:o + s_].view(params[n].shape) for n, o, s_ in zip(names, offs, sizes)}
+        g = grad_loss.detach().reshape(1).to(f32).contiguous()
+        norm_pix = 1 if m.norm_pix_loss else 0
+        rows_d, rows_e = NB * Sd, NB * Se
+
+        # ---- reconstruction loss -> decoder_pred ------------------------------------------------
+        dpred = buf("b.dpred", (rows_d, P), bf16)
+        coef = st["coefs"][0] / P
+        for s, im in enumerate(st["imgs"]):
+            call("csm_recon_loss_bwd", B["pred_full"][s * N * Sd:], im, B["mask"][s * N:], dpred[s * N * Sd:], g, coef,
+                 N, C, H, p, L, norm_pix)
+        call("csm_linear_wgrad", dpred, B["dec_bf16"], G["decoder_pred.weight"], rows_d, P, Dd, nsm)
+        call("csm_colsum_bf16", dpred, G["decoder_pred.bias"], rows_d, P, 0, nsm)
+        d_dec = buf("b.dec.dln", (rows_d, Dd), bf16)
+        call("csm_linear_dgrad", dpred, w16["decoder_pred.weight"], d_dec, None, rows_d, P, Dd, EPI_BF16)
+
+        # ---- cross-scale decoder loss through the predictor (MsLdCeCd.py:57-59) ------------------
+        dy2 = None
+        if ns == 2 and self.use_cd:
+            Hp = st["Hp"]
+            bn = m.predictor[1]
+            dy2 = buf("b.dy2", (rows_d, Dd), f32)
+            d_cp = buf("b.d_cp", (N * Sd, Dd), bf16)
+            call("csm_cross_mse_bwd", B["pred.cp"], B["dec_f32"], d_cp, dy2, g, st["coefs"][2], N * Sd, Sd, Dd)
+            call("csm_linear_wgrad", d_cp, B["pred.a1"], G["predictor.3.weight"], N * Sd, Dd, Hp, nsm)
+            call("csm_colsum_bf16", d_cp, G["predictor.3.bias"], N * Sd, Dd, 0, nsm)
+            d_a1 = buf("b.d_a1", (N * Sd, Hp), bf16)
+            call("csm_linear_dgrad", d_cp, w16["predictor.3.weight"], d_a1, None, N * Sd, Dd, Hp, EPI_BF16)
+            dh1 = buf("b.dh1", (N * Sd, Hp), bf16)
+            call("csm_bn_patch_bwd", B["pred.h1"], B["pred.a1"], d_a1, bn.weight, B["pred.bn_mean"], B["pred.bn_rstd"],
+                 dh1, G["predictor.1.weight"], G["predictor.1.bias"], N, L, Hp)
+            call("csm_linear_wgrad", dh1, B["dec_bf16"][N * Sd:], G["predictor.0.weight"], N * Sd, Hp, Dd, nsm)
+            call("csm_colsum_bf16", dh1, G["predictor.0.bias"], N * Sd, Hp, 0, nsm)
+            call("csm_linear_dgrad", dh1, w16["predictor.0.weight"], dy2[N * Sd:], None, N * Sd, Hp, Dd, EPI_F32)
+
+        # ---- decoder_norm, decoder blocks ---------------------------------------------------------
+        y_final = B[f"dec.{len(m.decoder) - 1}.xout"] if len(m.decoder) else B["dec.x0"]
+        dres = buf("b.dec.dres", (rows_d, Dd), f32)
+        dres16 = buf("b.dec.dres16", (rows_d, Dd), bf16)
+        call("csm_layernorm_bwd", d_dec, dy2, y_final, B["dn_mean"], B["dn_rstd"], params["decoder_norm.weight"], None,
+             dres, dres16, G["decoder_norm.weight"], G["decoder_norm.bias"], rows_d, Dd, nsm)
+        self._blocks_bwd("dec", "decoder", len(m.decoder), dres, dres16, NB, Sd, Dd, m.decoder_num_heads, params, w16,
+                         G, dev, nsm)
+
+        # ---- un-shuffle backward, decoder_embed ---------------------------------------------------
+        d_demb = buf("b.d_demb", (rows_e, Dd), bf16)
+        call("csm_decoder_assemble_bwd", dres, B["ids_shuffle"], d_demb, G["mask_token"], NB, L, keep, Dd)
+        call("csm_linear_wgrad", d_demb, B["enc_bf16"], G["decoder_embed.weight"], rows_e, Dd, D, nsm)
+        call("csm_colsum_bf16", d_demb, G["decoder_embed.bias"], rows_e, Dd, 0, nsm)
+        d_enc = buf("b.enc.dln", (rows_e, D), bf16)
+        call("csm_linear_dgrad", d_demb, w16["decoder_embed.weight"], d_enc, None, rows_e, Dd, D, EPI_BF16)
+
+        # ---- NT-Xent feature gradient joins the encoder output gradient ---------------------------
+        d_feat = None
+        if ns == 2 and self.use_ce:
+            d_feat = buf("b.d_feat", (NB, D), f32)
+            call("csm_ntxent_bwd", B["ntx.zhat"], B["ntx.fnorm"], B["ntx.neg"], g, d_feat, N, D, NTXENT_TAU, NTXENT_EPS)
+        eres = buf("b.enc.dres", (rows_e, D), f32)
+        eres16 = buf("b.enc.dres16", (rows_e, D), bf16)
+        call("csm_encoder_out_grad", d_enc, d_feat, eres, eres16, NB, Se, D)
+        self._blocks_bwd("enc", "encoder", len(m.encoder), eres, eres16, NB, Se, D, m.encoder_num_heads, params, w16,
+                         G, dev, nsm)
+
+        # ---- cls token, patch embed (only the kept patches carry gradient; cls-slot rows are zero) -
+        call("csm_cls_grad", eres, G["cls_token"], NB, Se, D)
+        call("csm_linear_wgrad", eres16, B["patches"], G["patch_embed.proj.weight"], rows_e, D, P, nsm)
+        call("csm_colsum_bf16", eres16, G["patch_embed.proj.bias"], rows_e, D, Se, nsm)
+        self._state = None
+        return [G[n] for n in names]
+
+    def _blocks_bwd(self, tag, pname, nlayers, dres, dres16, NB, S, Dm, heads, params, w16, G, dev, nsm):
+        bf16, f32 = torch.bfloat16, torch.float32
+        rows = NB * S
+        d = Dm // heads
+        B = self._bufs
+        buf = lambda name, shape, dt: self._buf(name, shape, dt, dev)
+        for i in reversed(range(nlayers)):
+            t, q = f"{tag}.{i}.", f"{pname}.{i}."
+            hid = params[q + "mlp.fc1.weight"].shape[0]
+            x_in = B[f"{tag}.{i - 1}.xout"] if i > 0 else B[f"{tag}.x0"]
+            # MLP branch: x_out = x_mid + fc2(gelu(fc1(norm2(x_mid))))
+            call("csm_linear_wgrad", dres16, B[t + "act"], G[q + "mlp.fc2.weight"], rows, Dm, hid, nsm)
+            call("csm_colsum_bf16", dres16, G[q + "mlp.fc2.bias"], rows, Dm, 0, nsm)
+            dh = buf(f"b.{tag}.dh", (rows, hid), bf16)
+            call("csm_linear_dgrad", dres16, w16[q + "mlp.fc2.weight"], dh, B[t + "h"], rows, Dm, hid, EPI_DGELU)
+            call("csm_linear_wgrad", dh, B[t + "ln2"], G[q + "mlp.fc1.weight"], rows, hid, Dm, nsm)
+            call("csm_colsum_bf16", dh, G[q + "mlp.fc1.bias"], rows, hid, 0, nsm)
+            dln = buf(f"b.{tag}.dln", (rows, Dm), bf16)
+            call("csm_linear_dgrad", dh, w16[q + "mlp.fc1.weight"], dln, None, rows, hid, Dm, EPI_BF16)
+            call("csm_layernorm_bwd", dln, None, B[t + "xmid"], B[t + "mean2"], B[t + "rstd2"],
+                 params[q + "norm2.weight"], dres, dres, dres16, G[q + "norm2.weight"], G[q + "norm2.bias"],
+                 rows, Dm, nsm)
+            # attention branch: x_mid = x_in + proj(attn(qkv(norm1(x_in))))
+            call("csm_linear_wgrad", dres16, B[t + "ao"], G[q + "attn.proj.weight"], rows, Dm, Dm, nsm)
+            call("csm_colsum_bf16", dres16, G[q + "attn.proj.bias"], rows, Dm, 0, nsm)
+            d_ao = buf(f"b.{tag}.d_ao", (rows, Dm), bf16)
+            call("csm_linear_dgrad", dres16, w16[q + "attn.proj.weight"], d_ao, None, rows, Dm, Dm, EPI_BF16)
+            dqkv = buf(f"b.{tag}.dqkv", (rows, 3 * Dm), bf16)
+            delta = buf(f"b.{tag}.delta", (NB * heads * S,), f32)
+            call("csm_attention_bwd", B[t + "qkv"], B[t + "ao"], d_ao, B[t + "lse"], delta, dqkv, NB, S, heads, d)
+            call("csm_linear_wgrad", dqkv, B[t + "ln1"], G[q + "attn.qkv.weight"], rows, 3 * Dm, Dm, nsm)
+            call("csm_colsum_bf16", dqkv, G[q + "attn.qkv.bias"], rows, 3 * Dm, 0, nsm)
+            call("csm_linear_dgrad", dqkv, w16[q + "attn.qkv.weight"], dln, None, rows, 3 * Dm, Dm, EPI_BF16)
+            call("csm_layernorm_bwd", dln, None, x_in, B[t + "mean1"], B[t + "rstd1"], params[q + "norm1.weight"],
+                 dres, dres, dres16, G[q + "norm1.weight"], G[q + "norm1.bias"], rows, Dm, nsm)
+
+
+class CrossScaleStep(torch.autograd.Function):
+    """Whole forward as one autograd node; its backward is the hand-written chain above.  The
+    parameters are explicit inputs so DDP's unused-parameter walk sees exactly the ones used."""
+
+    @staticmethod
+    def forward(ctx, engine, imgs_list, noises, mask_ratio, training, *params):
+        out = engine.forward(imgs_list, noises, mask_ratio, training)
+        ctx.engine = engine
+        ctx.generation = engine.generation
+        ctx.n_params = len(params)
+        engine._last_out = out
+        return out["loss"]
+
+    @staticmethod
+    def backward(ctx, grad_loss):
+        grads = ctx.engine.backward(grad_loss, ctx.generation)
+        assert len(grads) == ctx.n_params
+        return (None, None, None, None, None, *grads)

@@ -1,0 +1,485 @@
+// Fused multi-head self-attention forward / backward for the timm Block attention of the MAE
+// encoder (S = keep+1, d = 64) and decoder (S = L+1, d = 32): softmax((q k^T) * d^-1/2) v, no mask,
+// no dropout (timm 0.4.12 Attention as restated in oracle/timm_shim.py; call sites
+// models_mae/MAE_ViT_Baseline.py:160-188).
+//
+// Layout: qkv is the [rows, 3*Dm] bf16 output of the qkv Linear, row = b*S + s, columns
+// [which*Dm + h*d + j]; the output is [rows, Dm] with column h*d + j (== transpose(1,2).reshape).
+//
+// The whole K/V (or Q/dO) of one head is staged in shared memory, so the S x S score matrix never
+// exists in HBM (the reference materialises it in fp32: 159 MB per decoder layer at B=64).
+// Rounding points follow the autocast graph: scores are rounded to bf16, scaled, rounded again;
+// softmax statistics in fp32; probabilities rounded to bf16 for the PV product.
+//
+// Round-1 implementation note: the three kernels use warp-level mma.sync.m16n8k16 (bf16, f32
+// accumulate) with ldmatrix operand fetch.  Attention is ~4 % of the step's FLOPs; moving it onto
+// tcgen05/TMEM is tracked in DESIGN.md as the next step for this file.
+#include "common.cuh"
+
+namespace {
+using namespace csm;
+
+constexpr float kLog2e = 1.4426950408889634f;
+
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+      "{%0, %1, %2, %3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// Copy `nrows_pad` rows of DH bf16 (row pitch ld_g elements in global) into padded smem rows of
+// DH + 8 elements; rows >= nrows_valid are zero-filled.
+template <int DH>
+__device__ __forceinline__ void load_rows(__nv_bfloat16* s, const __nv_bfloat16* g, int row0, int nrows_valid_total,
+                                          int nrows_pad, size_t ld_g) {
+  constexpr int CH = DH / 8;  // 16-byte chunks per row
+  for (int idx = threadIdx.x; idx < nrows_pad * CH; idx += blockDim.x) {
+    const int r = idx / CH, c = idx % CH;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (row0 + r < nrows_valid_total) v = *reinterpret_cast<const uint4*>(g + static_cast<size_t>(row0 + r) * ld_g + c * 8);
+    *reinterpret_cast<uint4*>(s + r * (DH + 8) + c * 8) = v;
+  }
+}
+
+// A fragments (16 rows x DH) from padded smem rows starting at `row`.
+template <int DH>
+__device__ __forceinline__ void load_a_frags(uint32_t (&f)[DH / 16][4], const __nv_bfloat16* s, int row, int lane) {
+  const int r = row + (lane & 7) + ((lane >> 3) & 1) * 8;
+  const int c = (lane >> 4) * 8;
+#pragma unroll
+  for (int kk = 0; kk < DH / 16; ++kk) ldsm_x4(f[kk], smem_u32(s + r * (DH + 8) + kk * 16 + c));
+}
+
+// acc[nt] (+)= A(16 x DH) . M[row0 + nt*8 .. +8][0..DH)^T  for NT n-tiles  (B operand: n = smem row, k = column)
+template <int DH, int NT>
+__device__ __forceinline__ void mma_a_rowsT(float (&acc)[NT][4], const uint32_t (&a)[DH / 16][4],
+                                            const __nv_bfloat16* s, int row0, int lane) {
+  const int r = (lane & 7) + (lane >> 4) * 8;
+  const int c = ((lane >> 3) & 1) * 8;
+#pragma unroll
+  for (int kk = 0; kk < DH / 16; ++kk) {
+#pragma unroll
+    for (int np = 0; np < NT / 2; ++np) {
+      uint32_t b[4];
+      ldsm_x4(b, smem_u32(s + (row0 + np * 16 + r) * (DH + 8) + kk * 16 + c));
+      mma_bf16(acc[2 * np], a[kk], b[0], b[1]);
+      mma_bf16(acc[2 * np + 1], a[kk], b[2], b[3]);
+    }
+  }
+}
+
+// acc[dn] += P(16 x 16, A fragment) . M[row0 .. row0+16][0..DH)   (B operand: k = smem row, n = column)
+template <int DH>
+__device__ __forceinline__ void mma_p_rows(float (&acc)[DH / 8][4], const uint32_t (&a)[4], const __nv_bfloat16* s,
+                                           int row0, int lane) {
+  const int r = (lane & 7) + ((lane >> 3) & 1) * 8;
+  const int c = (lane >> 4) * 8;
+#pragma unroll
+  for (int dp = 0; dp < DH / 16; ++dp) {
+    uint32_t b[4];
+    ldsm_x4_trans(b, smem_u32(s + (row0 + r) * (DH + 8) + dp * 16 + c));
+    mma_bf16(acc[2 * dp], a, b[0], b[1]);
+    mma_bf16(acc[2 * dp + 1], a, b[2], b[3]);
+  }
+}
+
+// Write a warp's 16 x DH f32 accumulator tile as bf16 rows through its private smem scratch.
+template <int DH>
+__device__ __forceinline__ void store_tile_bf16(const float (&acc)[DH / 8][4], __nv_bfloat16* scratch,
+                                                __nv_bfloat16* g, int row0, int nrows_total, size_t ld_g, int lane) {
+  const int gq = lane >> 2, t = lane & 3;
+  __syncwarp();
+#pragma unroll
+  for (int dn = 0; dn < DH / 8; ++dn) {
+    *reinterpret_cast<uint32_t*>(scratch + gq * (DH + 8) + dn * 8 + 2 * t) = pack_bf16x2(acc[dn][0], acc[dn][1]);
+    *reinterpret_cast<uint32_t*>(scratch + (gq + 8) * (DH + 8) + dn * 8 + 2 * t) = pack_bf16x2(acc[dn][2], acc[dn][3]);
+  }
+  __syncwarp();
+  constexpr int CH = DH / 8;
+  for (int idx = lane; idx < 16 * CH; idx += 32) {
+    const int r = idx / CH, c = idx % CH;
+    if (row0 + r < nrows_total)
+      *reinterpret_cast<uint4*>(g + static_cast<size_t>(row0 + r) * ld_g + c * 8) =
+          *reinterpret_cast<const uint4*>(scratch + r * (DH + 8) + c * 8);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// forward: grid (B*H, ceil(S/64)); 4 warps, 16 query rows each; keys consumed 64 at a time
+// ---------------------------------------------------------------------------------------------
+template <int DH>
+__global__ void __launch_bounds__(128)
+attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, float* __restrict__ lse,
+                int S, int H, int Dm, float scale) {
+  extern __shared__ __align__(16) uint8_t smem_attn[];
+  constexpr int LDS = DH + 8;
+  const int S_pad = (S + 63) / 64 * 64;
+  __nv_bfloat16* sK = reinterpret_cast<__nv_bfloat16*>(smem_attn);
+  __nv_bfloat16* sV = sK + S_pad * LDS;
+  __nv_bfloat16* sQ = sV + S_pad * LDS;
+  const int bh = blockIdx.x, b = bh / H, h = bh % H;
+  const int q0 = blockIdx.y * 64;
+  const size_t ld = static_cast<size_t>(3) * Dm;
+  const __nv_bfloat16* base = qkv + static_cast<size_t>(b) * S * ld + h * DH;
+  load_rows<DH>(sK, base + Dm, 0, S, S_pad, ld);
+  load_rows<DH>(sV, base + 2 * Dm, 0, S, S_pad, ld);
+  load_rows<DH>(sQ, base, q0, S, 64, ld);
+  __syncthreads();
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int gq = lane >> 2, t = lane & 3;
+  const int r0 = q0 + warp * 16;
+  if (r0 >= S) return;
+
+  uint32_t qf[DH / 16][4];
+  load_a_frags<DH>(qf, sQ, warp * 16, lane);
+  float o[DH / 8][4];
+#pragma unroll
+  for (int i = 0; i < DH / 8; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
+  float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
+
+  for (int kb0 = 0; kb0 < S_pad; kb0 += 64) {
+    float s[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
+    mma_a_rowsT<DH, 8>(s, qf, sK, kb0, lane);
+    float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int key = kb0 + nt * 8 + 2 * t + (e & 1);
+        float v = bf16_round(bf16_round(s[nt][e]) * scale);
+        v = key < S ? v : -INFINITY;
+        s[nt][e] = v;
+        mx[e >> 1] = fmaxf(mx[e >> 1], v);
+      }
+    }
+    float alpha[2];
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+      mx[hh] = fmaxf(mx[hh], __shfl_xor_sync(0xffffffffu, mx[hh], 1));
+      mx[hh] = fmaxf(mx[hh], __shfl_xor_sync(0xffffffffu, mx[hh], 2));
+      const float m_new = fmaxf(m_run[hh], mx[hh]);
+      alpha[hh] = exp2f((m_run[hh] - m_new) * kLog2e);
+      m_run[hh] = m_new;
+      l_run[hh] *= alpha[hh];
+    }
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float pv = exp2f((s[nt][e] - m_run[e >> 1]) * kLog2e);
+        s[nt][e] = pv;
+        l_run[e >> 1] += pv;
+      }
+    }
+#pragma unroll
+    for (int dn = 0; dn < DH / 8; ++dn) {
+      o[dn][0] *= alpha[0]; o[dn][1] *= alpha[0];
+      o[dn][2] *= alpha[1]; o[dn][3] *= alpha[1];
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      uint32_t a[4];
+      a[0] = pack_bf16x2(s[2 * j][0], s[2 * j][1]);
+      a[1] = pack_bf16x2(s[2 * j][2], s[2 * j][3]);
+      a[2] = pack_bf16x2(s[2 * j + 1][0], s[2 * j + 1][1]);
+      a[3] = pack_bf16x2(s[2 * j + 1][2], s[2 * j + 1][3]);
+      mma_p_rows<DH>(o, a, sV, kb0 + j * 16, lane);
+    }
+  }
+#pragma unroll
+  for (int hh = 0; hh < 2; ++hh) {
+    l_run[hh] += __shfl_xor_sync(0xffffffffu, l_run[hh], 1);
+    l_run[hh] += __shfl_xor_sync(0xffffffffu, l_run[hh], 2);
+  }
+  const float inv0 = 1.f / l_run[0], inv1 = 1.f / l_run[1];
+#pragma unroll
+  for (int dn = 0; dn < DH / 8; ++dn) {
+    o[dn][0] *= inv0; o[dn][1] *= inv0;
+    o[dn][2] *= inv1; o[dn][3] *= inv1;
+  }
+  if (t == 0) {
+    if (r0 + gq < S) lse[static_cast<size_t>(bh) * S + r0 + gq] = m_run[0] + logf(l_run[0]);
+    if (r0 + gq + 8 < S) lse[static_cast<size_t>(bh) * S + r0 + gq + 8] = m_run[1] + logf(l_run[1]);
+  }
+  __nv_bfloat16* og = out + static_cast<size_t>(b) * S * Dm + h * DH;
+  store_tile_bf16<DH>(o, sQ + warp * 16 * LDS, og, r0, S, Dm, lane);
+}
+
+// ---------------------------------------------------------------------------------------------
+// backward, dQ: grid (B*H, ceil(S/64)); K,V of the head + the Q/dO/O rows of this block in smem.
+// Also writes delta[bh, s] = sum_j dO[s, j] * O[s, j] for the dK/dV kernel.
+// ---------------------------------------------------------------------------------------------
+template <int DH>
+__global__ void __launch_bounds__(128)
+attn_bwd_dq_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ o_fwd,
+                   const __nv_bfloat16* __restrict__ d_out, const float* __restrict__ lse,
+                   float* __restrict__ delta, __nv_bfloat16* __restrict__ dqkv, int S, int H, int Dm, float scale) {
+  extern __shared__ __align__(16) uint8_t smem_attn[];
+  constexpr int LDS = DH + 8;
+  const int S_pad = (S + 31) / 32 * 32;
+  __nv_bfloat16* sK = reinterpret_cast<__nv_bfloat16*>(smem_attn);
+  __nv_bfloat16* sV = sK + S_pad * LDS;
+  __nv_bfloat16* sQ = sV + S_pad * LDS;
+  __nv_bfloat16* sdO = sQ + 64 * LDS;
+  __nv_bfloat16* sO = sdO + 64 * LDS;
+  const int bh = blockIdx.x, b = bh / H, h = bh % H;
+  const int q0 = blockIdx.y * 64;
+  const size_t ld = static_cast<size_t>(3) * Dm;
+  const __nv_bfloat16* base = qkv + static_cast<size_t>(b) * S * ld + h * DH;
+  const size_t obase = static_cast<size_t>(b) * S * Dm + h * DH;
+  load_rows<DH>(sK, base + Dm, 0, S, S_pad, ld);
+  load_rows<DH>(sV, base + 2 * Dm, 0, S, S_pad, ld);
+  load_rows<DH>(sQ, base, q0, S, 64, ld);
+  load_rows<DH>(sdO, d_out + obase, q0, S, 64, Dm);
+  load_rows<DH>(sO, o_fwd + obase, q0, S, 64, Dm);
+  __syncthreads();
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int gq = lane >> 2, t = lane & 3;
+  const int r0 = q0 + warp * 16;
+  if (r0 >= S) return;
+
+  // delta: lane pair (2r, 2r+1) reduces row r of this warp's tile
+  float dsum = 0.f;
+  {
+    const int r = warp * 16 + (lane >> 1);
+    const int c0 = (lane & 1) * (DH / 2);
+#pragma unroll
+    for (int c = 0; c < DH / 2; c += 2) {
+      const float2 a = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(sdO + r * LDS + c0 + c));
+      const float2 bb = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(sO + r * LDS + c0 + c));
+      dsum += a.x * bb.x + a.y * bb.y;
+    }
+    dsum += __shfl_xor_sync(0xffffffffu, dsum, 1);
+    if ((lane & 1) == 0 && r0 + (lane >> 1) < S) delta[static_cast<size_t>(bh) * S + r0 + (lane >> 1)] = dsum;
+  }
+  float dl[2], ls[2];
+  dl[0] = __shfl_sync(0xffffffffu, dsum, 2 * gq);
+  dl[1] = __shfl_sync(0xffffffffu, dsum, 2 * (gq + 8));
+  ls[0] = r0 + gq < S ? lse[static_cast<size_t>(bh) * S + r0 + gq] : INFINITY;
+  ls[1] = r0 + gq + 8 < S ? lse[static_cast<size_t>(bh) * S + r0 + gq + 8] : INFINITY;
+
+  uint32_t qf[DH / 16][4], dof[DH / 16][4];
+  load_a_frags<DH>(qf, sQ, warp * 16, lane);
+  load_a_frags<DH>(dof, sdO, warp * 16, lane);
+  float dq[DH / 8][4];
+#pragma unroll
+  for (int i = 0; i < DH / 8; ++i) dq[i][0] = dq[i][1] = dq[i][2] = dq[i][3] = 0.f;
+
+  for (int kb0 = 0; kb0 < S_pad; kb0 += 32) {
+    float s[4][4], dp[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
+      dp[i][0] = dp[i][1] = dp[i][2] = dp[i][3] = 0.f;
+    }
+    mma_a_rowsT<DH, 4>(s, qf, sK, kb0, lane);
+    mma_a_rowsT<DH, 4>(dp, dof, sV, kb0, lane);
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int key = kb0 + nt * 8 + 2 * t + (e & 1);
+        const float sv = bf16_round(bf16_round(s[nt][e]) * scale);
+        const float p = key < S ? exp2f((sv - ls[e >> 1]) * kLog2e) : 0.f;
+        const float ds = p * (bf16_round(dp[nt][e]) - dl[e >> 1]);
+        s[nt][e] = bf16_round(ds) * scale;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      uint32_t a[4];
+      a[0] = pack_bf16x2(s[2 * j][0], s[2 * j][1]);
+      a[1] = pack_bf16x2(s[2 * j][2], s[2 * j][3]);
+      a[2] = pack_bf16x2(s[2 * j + 1][0], s[2 * j + 1][1]);
+      a[3] = pack_bf16x2(s[2 * j + 1][2], s[2 * j + 1][3]);
+      mma_p_rows<DH>(dq, a, sK, kb0 + j * 16, lane);
+    }
+  }
+  __nv_bfloat16* dqg = dqkv + static_cast<size_t>(b) * S * ld + h * DH;
+  store_tile_bf16<DH>(dq, sQ + warp * 16 * LDS, dqg, r0, S, ld, lane);
+}
+
+// ---------------------------------------------------------------------------------------------
+// backward, dK/dV: grid (B*H, ceil(S/64)); Q,dO of the head + the K/V rows of this block in smem.
+// ---------------------------------------------------------------------------------------------
+template <int DH>
+__global__ void __launch_bounds__(128)
+attn_bwd_dkv_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ d_out,
+                    const float* __restrict__ lse, const float* __restrict__ delta,
+                    __nv_bfloat16* __restrict__ dqkv, int S, int H, int Dm, float scale) {
+  extern __shared__ __align__(16) uint8_t smem_attn[];
+  constexpr int LDS = DH + 8;
+  const int S_pad = (S + 31) / 32 * 32;
+  __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(smem_attn);
+  __nv_bfloat16* sdO = sQ + S_pad * LDS;
+  __nv_bfloat16* sK = sdO + S_pad * LDS;
+  __nv_bfloat16* sV = sK + 64 * LDS;
+  float* sLse = reinterpret_cast<float*>(sV + 64 * LDS);
+  float* sDelta = sLse + S_pad;
+  const int bh = blockIdx.x, b = bh / H, h = bh % H;
+  const int k0 = blockIdx.y * 64;
+  const size_t ld = static_cast<size_t>(3) * Dm;
+  const __nv_bfloat16* base = qkv + static_cast<size_t>(b) * S * ld + h * DH;
+  const size_t obase = static_cast<size_t>(b) * S * Dm + h * DH;
+  load_rows<DH>(sQ, base, 0, S, S_pad, ld);
+  load_rows<DH>(sdO, d_out + obase, 0, S, S_pad, Dm);
+  load_rows<DH>(sK, base + Dm, k0, S, 64, ld);
+  load_rows<DH>(sV, base + 2 * Dm, k0, S, 64, ld);
+  for (int i = threadIdx.x; i < S_pad; i += blockDim.x) {
+    sLse[i] = i < S ? lse[static_cast<size_t>(bh) * S + i] : INFINITY;
+    sDelta[i] = i < S ? delta[static_cast<size_t>(bh) * S + i] : 0.f;
+  }
+  __syncthreads();
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int t = lane & 3;
+  const int kr0 = k0 + warp * 16;
+  if (kr0 >= S) return;
+
+  uint32_t kf[DH / 16][4], vf[DH / 16][4];
+  load_a_frags<DH>(kf, sK, warp * 16, lane);
+  load_a_frags<DH>(vf, sV, warp * 16, lane);
+  float dk[DH / 8][4], dv[DH / 8][4];
+#pragma unroll
+  for (int i = 0; i < DH / 8; ++i) {
+    dk[i][0] = dk[i][1] = dk[i][2] = dk[i][3] = 0.f;
+    dv[i][0] = dv[i][1] = dv[i][2] = dv[i][3] = 0.f;
+  }
+
+  for (int qb0 = 0; qb0 < S_pad; qb0 += 32) {
+    float st[4][4], dpt[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      st[i][0] = st[i][1] = st[i][2] = st[i][3] = 0.f;
+      dpt[i][0] = dpt[i][1] = dpt[i][2] = dpt[i][3] = 0.f;
+    }
+    mma_a_rowsT<DH, 4>(st, kf, sQ, qb0, lane);
+    mma_a_rowsT<DH, 4>(dpt, vf, sdO, qb0, lane);
+    uint32_t pa[2][4], da[2][4];
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      float pv[4], dsv[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int query = qb0 + nt * 8 + 2 * t + (e & 1);
+        const float sv = bf16_round(bf16_round(st[nt][e]) * scale);
+        const float p = exp2f((sv - sLse[query]) * kLog2e);   // lse = +inf for padded queries -> 0
+        const float ds = p * (bf16_round(dpt[nt][e]) - sDelta[query]);
+        pv[e] = p;
+        dsv[e] = bf16_round(ds) * scale;
+      }
+      const int j = nt >> 1, hi = (nt & 1) * 2;
+      pa[j][hi + 0] = pack_bf16x2(pv[0], pv[1]);
+      pa[j][hi + 1] = pack_bf16x2(pv[2], pv[3]);
+      da[j][hi + 0] = pack_bf16x2(dsv[0], dsv[1]);
+      da[j][hi + 1] = pack_bf16x2(dsv[2], dsv[3]);
+    }
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      mma_p_rows<DH>(dv, pa[j], sdO, qb0 + j * 16, lane);
+      mma_p_rows<DH>(dk, da[j], sQ, qb0 + j * 16, lane);
+    }
+  }
+  __nv_bfloat16* dkg = dqkv + static_cast<size_t>(b) * S * ld + Dm + h * DH;
+  __nv_bfloat16* dvg = dqkv + static_cast<size_t>(b) * S * ld + 2 * Dm + h * DH;
+  // both tiles go out through this warp's private K-row scratch (its fragments are already in registers)
+  store_tile_bf16<DH>(dk, sK + warp * 16 * LDS, dkg, kr0, S, ld, lane);
+  store_tile_bf16<DH>(dv, sK + warp * 16 * LDS, dvg, kr0, S, ld, lane);
+}
+
+template <typename K>
+int set_smem(K kern, size_t bytes, size_t* configured, const char* name) {
+  if (bytes <= *configured) return CSM_OK;
+  if (bytes > 227 * 1024) {
+    csm_set_error("%s: sequence too long for the whole-head-in-shared-memory kernel (%zu bytes needed)", name, bytes);
+    return CSM_ERR_ARG;
+  }
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes));
+  if (e != cudaSuccess) {
+    csm_set_error("%s: cudaFuncSetAttribute(%zu) failed: %s", name, bytes, cudaGetErrorString(e));
+    return CSM_ERR_CUDA;
+  }
+  *configured = bytes;
+  return CSM_OK;
+}
+
+template <int DH>
+int attn_fwd_launch(const void* qkv, void* out, float* lse, int B, int S, int H, cudaStream_t stream) {
+  const int Dm = H * DH;
+  const int S_pad = (S + 63) / 64 * 64;
+  const size_t smem = static_cast<size_t>(2 * S_pad + 64) * (DH + 8) * 2;
+  static size_t cfg_fwd = 0;
+  int rc = set_smem(attn_fwd_kernel<DH>, smem, &cfg_fwd, "attention_fwd");
+  if (rc) return rc;
+  dim3 grid(B * H, (S + 63) / 64);
+  attn_fwd_kernel<DH><<<grid, 128, smem, stream>>>(reinterpret_cast<const __nv_bfloat16*>(qkv),
+                                                   reinterpret_cast<__nv_bfloat16*>(out), lse, S, H, Dm,
+                                                   1.0f / sqrtf(static_cast<float>(DH)));
+  CSM_CHECK_LAUNCH("attention_fwd");
+  return CSM_OK;
+}
+
+template <int DH>
+int attn_bwd_launch(const void* qkv, const void* o, const void* d_out, const float* lse, float* delta, void* dqkv,
+                    int B, int S, int H, cudaStream_t stream) {
+  const int Dm = H * DH;
+  const int S_pad = (S + 31) / 32 * 32;
+  const float scale = 1.0f / sqrtf(static_cast<float>(DH));
+  dim3 grid(B * H, (S + 63) / 64);
+  const size_t smem_dq = static_cast<size_t>(2 * S_pad + 3 * 64) * (DH + 8) * 2;
+  static size_t cfg_dq = 0, cfg_dkv = 0;
+  int rc = set_smem(attn_bwd_dq_kernel<DH>, smem_dq, &cfg_dq, "attention_bwd_dq");
+  if (rc) return rc;
+  attn_bwd_dq_kernel<DH><<<grid, 128, smem_dq, stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(qkv), reinterpret_cast<const __nv_bfloat16*>(o),
+      reinterpret_cast<const __nv_bfloat16*>(d_out), lse, delta, reinterpret_cast<__nv_bfloat16*>(dqkv), S, H, Dm,
+      scale);
+  CSM_CHECK_LAUNCH("attention_bwd_dq");
+  const size_t smem_dkv = static_cast<size_t>(2 * S_pad + 2 * 64) * (DH + 8) * 2 + static_cast<size_t>(2) * S_pad * 4;
+  rc = set_smem(attn_bwd_dkv_kernel<DH>, smem_dkv, &cfg_dkv, "attention_bwd_dkv");
+  if (rc) return rc;
+  attn_bwd_dkv_kernel<DH><<<grid, 128, smem_dkv, stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(qkv), reinterpret_cast<const __nv_bfloat16*>(d_out), lse, delta,
+      reinterpret_cast<__nv_bfloat16*>(dqkv), S, H, Dm, scale);
+  CSM_CHECK_LAUNCH("attention_bwd_dkv");
+  return CSM_OK;
+}
+
+}  // namespace
+
+extern "C" int csm_attention_fwd(const void* qkv_bf16, void* out_bf16, float* lse, int B, int S, int H, int head_dim,
+                                 cudaStream_t stream) {
+  CSM_CHECK_ARG(B > 0 && S > 0 && H > 0, "csm_attention_fwd: bad sizes B=%d S=%d H=%d", B, S, H);
+  if (head_dim == 32) return attn_fwd_launch<32>(qkv_bf16, out_bf16, lse, B, S, H, stream);
+  if (head_dim == 64) return attn_fwd_launch<64>(qkv_bf16, out_bf16, lse, B, S, H, stream);
+  csm_set_error("csm_attention_fwd: head_dim must be 32 or 64 (got %d)", head_dim);
+  return CSM_ERR_ARG;
+}
+
+extern "C" int csm_attention_bwd(const void* qkv_bf16, const void* out_bf16, const void* d_out_bf16, const float* lse,
+                                 float* delta_scratch, void* dqkv_bf16, int B, int S, int H, int head_dim,
+                                 cudaStream_t stream) {
+  CSM_CHECK_ARG(B > 0 && S > 0 && H > 0, "csm_attention_bwd: bad sizes B=%d S=%d H=%d", B, S, H);
+  if (head_dim == 32)
+    return attn_bwd_launch<32>(qkv_bf16, out_bf16, d_out_bf16, lse, delta_scratch, dqkv_bf16, B, S, H, stream);
+  if (head_dim == 64)
+    return attn_bwd_launch<64>(qkv_bf16, out_bf16, d_out_bf16, lse, delta_scratch, dqkv_bf16, B, S, H, stream);
+  csm_set_error("csm_attention_bwd: head_dim must be 32 or 64 (got %d)", head_dim);
+  return CSM_ERR_ARG;
+}

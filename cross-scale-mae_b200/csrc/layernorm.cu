@@ -1,0 +1,309 @@
+// LayerNorm forward / backward over the fp32 residual stream (timm Block norm1/norm2 and decoder_norm,
+// eps = 1e-6: models_mae/MAE_ViT_Baseline.py:43-45,160-188,292), bias-gradient column sums and the
+// fp32 -> bf16 weight cast.  HBM-bound warp-per-row kernels with 16-byte accesses.
+#include "common.cuh"
+
+namespace {
+using namespace csm;
+
+constexpr int LN_MAX_VEC = 8;  // float4 per lane -> D <= 1024
+
+// One warp per row.  Statistics in fp32 (two-pass: mean, then centred variance), output rounded once.
+__global__ void layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                     const float* __restrict__ beta, __nv_bfloat16* __restrict__ out_bf16,
+                                     float* __restrict__ out_f32, float* __restrict__ mean_out,
+                                     float* __restrict__ rstd_out, int rows, int D, float eps) {
+  const int warps = blockDim.x >> 5;
+  const int row = blockIdx.x * warps + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float* xr = x + static_cast<size_t>(row) * D;
+  float4 v[LN_MAX_VEC];
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < LN_MAX_VEC; ++k) {
+    const int i = (k * 32 + lane) * 4;
+    if (i < D) {
+      v[k] = *reinterpret_cast<const float4*>(xr + i);
+      s += v[k].x + v[k].y + v[k].z + v[k].w;
+    }
+  }
+  const float mean = warp_sum(s) / D;
+  float ss = 0.f;
+#pragma unroll
+  for (int k = 0; k < LN_MAX_VEC; ++k) {
+    const int i = (k * 32 + lane) * 4;
+    if (i < D) {
+      const float a = v[k].x - mean, b = v[k].y - mean, c = v[k].z - mean, d = v[k].w - mean;
+      ss += a * a + b * b + c * c + d * d;
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(ss) / D + eps);
+  if (lane == 0) {
+    mean_out[row] = mean;
+    rstd_out[row] = rstd;
+  }
+#pragma unroll
+  for (int k = 0; k < LN_MAX_VEC; ++k) {
+    const int i = (k * 32 + lane) * 4;
+    if (i < D) {
+      const float4 g = *reinterpret_cast<const float4*>(gamma + i);
+      const float4 b = *reinterpret_cast<const float4*>(beta + i);
+      float4 o;
+      o.x = (v[k].x - mean) * rstd * g.x + b.x;
+      o.y = (v[k].y - mean) * rstd * g.y + b.y;
+      o.z = (v[k].z - mean) * rstd * g.z + b.z;
+      o.w = (v[k].w - mean) * rstd * g.w + b.w;
+      if (out_f32 != nullptr) *reinterpret_cast<float4*>(out_f32 + static_cast<size_t>(row) * D + i) = o;
+      if (out_bf16 != nullptr) {
+        uint2 pk;
+        pk.x = pack_bf16x2(o.x, o.y);
+        pk.y = pack_bf16x2(o.z, o.w);
+        *reinterpret_cast<uint2*>(out_bf16 + static_cast<size_t>(row) * D + i) = pk;
+      }
+    }
+  }
+}
+
+// dy = float(dy_bf16) + dy2_f32 (either may be null).  dx_ln = rstd * (g - mean(g) - xhat * mean(g * xhat)),
+// g = dy * gamma.  dres_out = (dres_in ? dres_in : 0) + dx_ln, plus a bf16 copy for the following GEMMs.
+// dgamma / dbeta: every lane owns fixed columns, accumulates over the rows its warp visits, then the
+// CTA reduces through shared memory and issues one atomicAdd per column.
+__global__ void layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy_bf16, const float* __restrict__ dy2,
+                                     const float* __restrict__ x, const float* __restrict__ mean_in,
+                                     const float* __restrict__ rstd_in, const float* __restrict__ gamma,
+                                     const float* __restrict__ dres_in, float* __restrict__ dres_out,
+                                     __nv_bfloat16* __restrict__ dres_bf16, float* __restrict__ dgamma,
+                                     float* __restrict__ dbeta, int rows, int D) {
+  extern __shared__ float s_red[];  // [2][warps][D]
+  const int warps = blockDim.x >> 5;
+  const int w = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  float4 ag[LN_MAX_VEC], ab[LN_MAX_VEC];
+#pragma unroll
+  for (int k = 0; k < LN_MAX_VEC; ++k) {
+    ag[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    ab[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  for (int row = blockIdx.x * warps + w; row < rows; row += gridDim.x * warps) {
+    const size_t base = static_cast<size_t>(row) * D;
+    const float mean = mean_in[row], rstd = rstd_in[row];
+    float4 xh[LN_MAX_VEC], g[LN_MAX_VEC];
+    float c1 = 0.f, c2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < LN_MAX_VEC; ++k) {
+      const int i = (k * 32 + lane) * 4;
+      if (i < D) {
+        const float4 xv = *reinterpret_cast<const float4*>(x + base + i);
+        float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (dy_bf16 != nullptr) {
+          const uint2 ev = *reinterpret_cast<const uint2*>(dy_bf16 + base + i);
+          const float2 e0 = unpack_bf16x2(ev.x), e1 = unpack_bf16x2(ev.y);
+          d = make_float4(e0.x, e0.y, e1.x, e1.y);
+        }
+        if (dy2 != nullptr) {
+          const float4 d2 = *reinterpret_cast<const float4*>(dy2 + base + i);
+          d.x += d2.x; d.y += d2.y; d.z += d2.z; d.w += d2.w;
+        }
+        const float4 gm = *reinterpret_cast<const float4*>(gamma + i);
+        xh[k] = make_float4((xv.x - mean) * rstd, (xv.y - mean) * rstd, (xv.z - mean) * rstd, (xv.w - mean) * rstd);
+        g[k] = make_float4(d.x * gm.x, d.y * gm.y, d.z * gm.z, d.w * gm.w);
+        c1 += g[k].x + g[k].y + g[k].z + g[k].w;
+        c2 += g[k].x * xh[k].x + g[k].y * xh[k].y + g[k].z * xh[k].z + g[k].w * xh[k].w;
+        ag[k].x += d.x * xh[k].x; ag[k].y += d.y * xh[k].y; ag[k].z += d.z * xh[k].z; ag[k].w += d.w * xh[k].w;
+        ab[k].x += d.x; ab[k].y += d.y; ab[k].z += d.z; ab[k].w += d.w;
+      }
+    }
+    c1 = warp_sum(c1) / D;
+    c2 = warp_sum(c2) / D;
+#pragma unroll
+    for (int k = 0; k < LN_MAX_VEC; ++k) {
+      const int i = (k * 32 + lane) * 4;
+      if (i < D) {
+        float4 o;
+        o.x = rstd * (g[k].x - c1 - xh[k].x * c2);
+        o.y = rstd * (g[k].y - c1 - xh[k].y * c2);
+        o.z = rstd * (g[k].z - c1 - xh[k].z * c2);
+        o.w = rstd * (g[k].w - c1 - xh[k].w * c2);
+        if (dres_in != nullptr) {
+          const float4 r = *reinterpret_cast<const float4*>(dres_in + base + i);
+          o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+        }
+        *reinterpret_cast<float4*>(dres_out + base + i) = o;
+        if (dres_bf16 != nullptr) {
+          uint2 pk;
+          pk.x = pack_bf16x2(o.x, o.y);
+          pk.y = pack_bf16x2(o.z, o.w);
+          *reinterpret_cast<uint2*>(dres_bf16 + base + i) = pk;
+        }
+      }
+    }
+  }
+  float* sg = s_red;
+  float* sb = s_red + warps * D;
+#pragma unroll
+  for (int k = 0; k < LN_MAX_VEC; ++k) {
+    const int i = (k * 32 + lane) * 4;
+    if (i < D) {
+      *reinterpret_cast<float4*>(sg + w * D + i) = ag[k];
+      *reinterpret_cast<float4*>(sb + w * D + i) = ab[k];
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < D; i += blockDim.x) {
+    float a = 0.f, b = 0.f;
+    for (int ww = 0; ww < warps; ++ww) {
+      a += sg[ww * D + i];
+      b += sb[ww * D + i];
+    }
+    atomicAdd(dgamma + i, a);
+    atomicAdd(dbeta + i, b);
+  }
+}
+
+// db[n] += sum over rows r (r % skip_period != 0 when skip_period > 0) of dy[r, n]
+__global__ void colsum_bf16_kernel(const __nv_bfloat16* __restrict__ dy, float* __restrict__ db, int rows, int N,
+                                   int skip_period) {
+  __shared__ float s[8][256 + 8];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int col = blockIdx.x * 256 + tx * 8;
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  if (col < N) {
+    for (int r = blockIdx.y * 8 + ty; r < rows; r += gridDim.y * 8) {
+      if (skip_period > 0 && (r % skip_period) == 0) continue;
+      const uint4 v = *reinterpret_cast<const uint4*>(dy + static_cast<size_t>(r) * N + col);
+      const uint32_t wv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = unpack_bf16x2(wv[j]);
+        acc[2 * j] += f.x;
+        acc[2 * j + 1] += f.y;
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s[ty][tx * 8 + j] = acc[j];
+  __syncthreads();
+  const int c = threadIdx.x;  // 256 threads, one column each
+  if (blockIdx.x * 256 + c < N) {
+    float a = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a += s[k][c];
+    atomicAdd(db + blockIdx.x * 256 + c, a);
+  }
+}
+
+struct CastEntry {
+  const float* src;
+  __nv_bfloat16* dst;
+  long long n;
+};
+
+// Multi-tensor fp32 -> bf16 cast (master weights -> tensor-core operands): blockIdx.y selects the tensor.
+__global__ void cast_multi_kernel(const CastEntry* __restrict__ table) {
+  const CastEntry e = table[blockIdx.y];
+  const long long n4 = e.n >> 2;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n4;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float4 v = *reinterpret_cast<const float4*>(e.src + i * 4);
+    uint2 pk;
+    pk.x = pack_bf16x2(v.x, v.y);
+    pk.y = pack_bf16x2(v.z, v.w);
+    *reinterpret_cast<uint2*>(e.dst + i * 4) = pk;
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (e.n & 3)) {
+    const long long i = (n4 << 2) + threadIdx.x;
+    e.dst[i] = __float2bfloat16_rn(e.src[i]);
+  }
+}
+
+__global__ void cast_f32_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long n) {
+  const long long n4 = n >> 2;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n4;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float4 v = *reinterpret_cast<const float4*>(src + i * 4);
+    uint2 pk;
+    pk.x = pack_bf16x2(v.x, v.y);
+    pk.y = pack_bf16x2(v.z, v.w);
+    *reinterpret_cast<uint2*>(dst + i * 4) = pk;
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+    const long long i = (n4 << 2) + threadIdx.x;
+    dst[i] = __float2bfloat16_rn(src[i]);
+  }
+}
+
+}  // namespace
+
+extern "C" int csm_layernorm_fwd(const float* x, const float* gamma, const float* beta, void* out_bf16,
+                                 float* out_f32, float* mean, float* rstd, int rows, int D, float eps,
+                                 cudaStream_t stream) {
+  CSM_CHECK_ARG(rows > 0 && D > 0 && D % 4 == 0 && D <= LN_MAX_VEC * 128,
+                "csm_layernorm_fwd: D must be a multiple of 4 and <= %d (rows=%d D=%d)", LN_MAX_VEC * 128, rows, D);
+  const int wpb = 8;
+  layernorm_fwd_kernel<<<csm_cdiv(rows, wpb), wpb * 32, 0, stream>>>(
+      x, gamma, beta, reinterpret_cast<__nv_bfloat16*>(out_bf16), out_f32, mean, rstd, rows, D, eps);
+  CSM_CHECK_LAUNCH("layernorm_fwd");
+  return CSM_OK;
+}
+
+extern "C" int csm_layernorm_bwd(const void* dy_bf16, const float* dy2_f32, const float* x, const float* mean,
+                                 const float* rstd, const float* gamma, const float* dres_in, float* dres_out,
+                                 void* dres_bf16, float* dgamma, float* dbeta, int rows, int D, int num_sms,
+                                 cudaStream_t stream) {
+  CSM_CHECK_ARG(rows > 0 && D > 0 && D % 4 == 0 && D <= LN_MAX_VEC * 128,
+                "csm_layernorm_bwd: D must be a multiple of 4 and <= %d (rows=%d D=%d)", LN_MAX_VEC * 128, rows, D);
+  CSM_CHECK_ARG(dy_bf16 != nullptr || dy2_f32 != nullptr, "csm_layernorm_bwd: no incoming gradient");
+  const int wpb = 8;
+  if (num_sms <= 0) num_sms = 148;
+  int grid = csm_cdiv(rows, wpb);
+  if (grid > num_sms * 2) grid = num_sms * 2;
+  const size_t smem = static_cast<size_t>(2) * wpb * D * sizeof(float);
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(layernorm_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         2 * wpb * LN_MAX_VEC * 128 * (int)sizeof(float));
+    configured = true;
+  }
+  layernorm_bwd_kernel<<<grid, wpb * 32, smem, stream>>>(reinterpret_cast<const __nv_bfloat16*>(dy_bf16), dy2_f32, x,
+                                                         mean, rstd, gamma, dres_in, dres_out,
+                                                         reinterpret_cast<__nv_bfloat16*>(dres_bf16), dgamma, dbeta,
+                                                         rows, D);
+  CSM_CHECK_LAUNCH("layernorm_bwd");
+  return CSM_OK;
+}
+
+extern "C" int csm_colsum_bf16(const void* dy_bf16, float* db, int rows, int N, int skip_period, int num_sms,
+                               cudaStream_t stream) {
+  CSM_CHECK_ARG(rows > 0 && N > 0 && N % 8 == 0, "csm_colsum_bf16: N must be a multiple of 8 (rows=%d N=%d)", rows, N);
+  if (num_sms <= 0) num_sms = 148;
+  const int gx = csm_cdiv(N, 256);
+  int gy = csm_cdiv(2 * num_sms, gx);
+  const int max_gy = csm_cdiv(rows, 8);
+  if (gy > max_gy) gy = max_gy;
+  colsum_bf16_kernel<<<dim3(gx, gy), 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(dy_bf16), db, rows, N,
+                                                       skip_period);
+  CSM_CHECK_LAUNCH("colsum_bf16");
+  return CSM_OK;
+}
+
+// table: device array of {const float* src, bf16* dst, int64 n} (24 bytes per entry), every pointer 16B aligned.
+extern "C" int csm_cast_multi(const void* table_dev, int num_tensors, int blocks_per_tensor, cudaStream_t stream) {
+  CSM_CHECK_ARG(num_tensors > 0 && blocks_per_tensor > 0, "csm_cast_multi: empty table");
+  cast_multi_kernel<<<dim3(blocks_per_tensor, num_tensors), 256, 0, stream>>>(
+      reinterpret_cast<const CastEntry*>(table_dev));
+  CSM_CHECK_LAUNCH("cast_multi");
+  return CSM_OK;
+}
+
+extern "C" int csm_cast_f32_bf16(const float* src, void* dst_bf16, long long n, cudaStream_t stream) {
+  CSM_CHECK_ARG(n > 0, "csm_cast_f32_bf16: empty tensor");
+  long long blocks = (n / 4 + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks < 1) blocks = 1;
+  cast_f32_bf16_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(src, reinterpret_cast<__nv_bfloat16*>(dst_bf16), n);
+  CSM_CHECK_LAUNCH("cast_f32_bf16");
+  return CSM_OK;
+}

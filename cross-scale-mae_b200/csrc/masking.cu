@@ -1,0 +1,264 @@
+// Random masking, kept-patch gather and the token (un)shuffle kernels of the MAE encoder/decoder.
+//
+// Reference semantics (paths relative to the upstream repo):
+//   models_mae/MAE_ViT_Shared.py:57-84     random_masking (noise -> argsort -> argsort -> keep / mask)
+//   models_mae/MAE_ViT_Baseline.py:245-256 patch-embed + pos-embed, masking, cls concat
+//   models_mae/MAE_ViT_Baseline.py:270-283 decoder_embed output + mask tokens, un-shuffle, + decoder pos-embed
+//
+// All of this is HBM-/latency-bound integer and copy work: coalesced, 16-byte vectorised accesses,
+// no tensor cores.  Index outputs are bit-exact against a stable argsort.
+#include "common.cuh"
+
+namespace {
+using namespace csm;
+
+// One CTA per image row.  rank[i] = #{j : noise[j] < noise[i] or (noise[j] == noise[i] and j < i)}
+// is the position of element i in the stable ascending sort, i.e. ids_restore[i].
+__global__ void random_masking_kernel(const float* __restrict__ noise, int L, int keep,
+                                      long long* __restrict__ ids_restore, int* __restrict__ ids_shuffle,
+                                      float* __restrict__ mask) {
+  extern __shared__ float s_noise[];
+  const int n = blockIdx.x;
+  const float* row = noise + static_cast<size_t>(n) * L;
+  for (int i = threadIdx.x; i < L; i += blockDim.x) s_noise[i] = row[i];
+  __syncthreads();
+  for (int i = threadIdx.x; i < L; i += blockDim.x) {
+    const float v = s_noise[i];
+    int rank = 0;
+    for (int j = 0; j < L; ++j) {
+      const float u = s_noise[j];
+      rank += (u < v) || (u == v && j < i);
+    }
+    ids_restore[static_cast<size_t>(n) * L + i] = rank;
+    ids_shuffle[static_cast<size_t>(n) * L + rank] = i;
+    mask[static_cast<size_t>(n) * L + i] = rank >= keep ? 1.0f : 0.0f;
+  }
+}
+
+// A[(n*Se + 1 + j), (c, py, px)] = bf16(img[n, c, h*p + py, w*p + px]) for the j-th kept patch
+// (h, w) = divmod(ids_shuffle[n, j], G); row n*Se + 0 (the cls slot) is zero.
+// One warp per output row; 16 consecutive pixels (64 B) per (c, py).
+__global__ void patch_gather_kernel(const float* __restrict__ imgs, const int* __restrict__ ids_shuffle,
+                                    __nv_bfloat16* __restrict__ out, int nimg, int C, int H, int p, int L,
+                                    int keep) {
+  const int Se = keep + 1;
+  const int warps_per_block = blockDim.x >> 5;
+  const int row = blockIdx.x * warps_per_block + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= nimg * Se) return;
+  const int n = row / Se, t = row % Se;
+  const int K = C * p * p;
+  __nv_bfloat16* o = out + static_cast<size_t>(row) * K;
+  if (t == 0) {
+    for (int i = lane * 8; i < K; i += 32 * 8) *reinterpret_cast<uint4*>(o + i) = make_uint4(0, 0, 0, 0);
+    return;
+  }
+  const int G = H / p;
+  const int patch = ids_shuffle[static_cast<size_t>(n) * L + (t - 1)];
+  const int ph = patch / G, pw = patch % G;
+  const float* base = imgs + static_cast<size_t>(n) * C * H * H + static_cast<size_t>(ph) * p * H + pw * p;
+  // element e = (c*p + py)*p + px; 4 consecutive px per thread
+  for (int e = lane * 4; e < K; e += 32 * 4) {
+    const int px = e % p, cy = e / p;
+    const int py = cy % p, c = cy / p;
+    const float4 v = *reinterpret_cast<const float4*>(base + (static_cast<size_t>(c) * H + py) * H + px);
+    uint2 pk;
+    pk.x = pack_bf16x2(v.x, v.y);
+    pk.y = pack_bf16x2(v.z, v.w);
+    *reinterpret_cast<uint2*>(o + e) = pk;
+  }
+}
+
+// x[n, 0] = cls + pos[0];  x[n, 1 + j] = float(emb[n*Se + 1 + j]) + pos[1 + ids_shuffle[n, j]]
+__global__ void encoder_assemble_kernel(const __nv_bfloat16* __restrict__ emb, const int* __restrict__ ids_shuffle,
+                                        const float* __restrict__ pos, const float* __restrict__ cls,
+                                        float* __restrict__ x, int nimg, int L, int keep, int D) {
+  const int Se = keep + 1;
+  const int row = blockIdx.x;
+  const int n = row / Se, t = row % Se;
+  float* o = x + static_cast<size_t>(row) * D;
+  if (t == 0) {
+    for (int i = threadIdx.x * 4; i < D; i += blockDim.x * 4) {
+      const float4 a = *reinterpret_cast<const float4*>(cls + i);
+      const float4 b = *reinterpret_cast<const float4*>(pos + i);
+      *reinterpret_cast<float4*>(o + i) = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+    }
+    return;
+  }
+  const int patch = ids_shuffle[static_cast<size_t>(n) * L + (t - 1)];
+  const float* pr = pos + static_cast<size_t>(1 + patch) * D;
+  const __nv_bfloat16* e = emb + static_cast<size_t>(row) * D;
+  for (int i = threadIdx.x * 4; i < D; i += blockDim.x * 4) {
+    const uint2 ev = *reinterpret_cast<const uint2*>(e + i);
+    const float2 e0 = unpack_bf16x2(ev.x), e1 = unpack_bf16x2(ev.y);
+    const float4 b = *reinterpret_cast<const float4*>(pr + i);
+    *reinterpret_cast<float4*>(o + i) = make_float4(e0.x + b.x, e0.y + b.y, e1.x + b.z, e1.y + b.w);
+  }
+}
+
+// y[n, 0] = float(demb[n, 0]) + dpos[0]
+// y[n, 1 + i] = (r < keep ? float(demb[n, 1 + r]) : mask_token) + dpos[1 + i],  r = ids_restore[n, i]
+__global__ void decoder_assemble_kernel(const __nv_bfloat16* __restrict__ demb,
+                                        const long long* __restrict__ ids_restore,
+                                        const float* __restrict__ mask_token, const float* __restrict__ dpos,
+                                        float* __restrict__ y, int L, int keep, int Dd) {
+  const int Sd = L + 1, Se = keep + 1;
+  const int row = blockIdx.x;
+  const int n = row / Sd, t = row % Sd;
+  float* o = y + static_cast<size_t>(row) * Dd;
+  const float* pr = dpos + static_cast<size_t>(t) * Dd;
+  int src = 0;
+  if (t > 0) {
+    const int r = static_cast<int>(ids_restore[static_cast<size_t>(n) * L + (t - 1)]);
+    src = r < keep ? 1 + r : -1;
+  }
+  if (src >= 0) {
+    const __nv_bfloat16* e = demb + (static_cast<size_t>(n) * Se + src) * Dd;
+    for (int i = threadIdx.x * 4; i < Dd; i += blockDim.x * 4) {
+      const uint2 ev = *reinterpret_cast<const uint2*>(e + i);
+      const float2 e0 = unpack_bf16x2(ev.x), e1 = unpack_bf16x2(ev.y);
+      const float4 b = *reinterpret_cast<const float4*>(pr + i);
+      *reinterpret_cast<float4*>(o + i) = make_float4(e0.x + b.x, e0.y + b.y, e1.x + b.z, e1.y + b.w);
+    }
+  } else {
+    for (int i = threadIdx.x * 4; i < Dd; i += blockDim.x * 4) {
+      const float4 a = *reinterpret_cast<const float4*>(mask_token + i);
+      const float4 b = *reinterpret_cast<const float4*>(pr + i);
+      *reinterpret_cast<float4*>(o + i) = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+    }
+  }
+}
+
+// Backward of decoder_assemble.
+//   d_demb[n, 0]     = bf16(dy[n, 0])
+//   d_demb[n, 1 + r] = bf16(dy[n, 1 + ids_shuffle[n, r]])          r < keep
+//   d_mask_token    += sum over masked positions (and images) of dy (one CTA per image, then red.add)
+__global__ void decoder_assemble_bwd_kernel(const float* __restrict__ dy, const int* __restrict__ ids_shuffle,
+                                            __nv_bfloat16* __restrict__ d_demb, float* __restrict__ d_mask_token,
+                                            int L, int keep, int Dd) {
+  const int Sd = L + 1, Se = keep + 1;
+  const int n = blockIdx.x;
+  const float* dyn = dy + static_cast<size_t>(n) * Sd * Dd;
+  const int* sh = ids_shuffle + static_cast<size_t>(n) * L;
+  for (int idx = threadIdx.x; idx < Se * (Dd / 4); idx += blockDim.x) {
+    const int t = idx / (Dd / 4), i = (idx % (Dd / 4)) * 4;
+    const int src = t == 0 ? 0 : 1 + sh[t - 1];
+    const float4 v = *reinterpret_cast<const float4*>(dyn + static_cast<size_t>(src) * Dd + i);
+    uint2 pk;
+    pk.x = pack_bf16x2(v.x, v.y);
+    pk.y = pack_bf16x2(v.z, v.w);
+    *reinterpret_cast<uint2*>(d_demb + (static_cast<size_t>(n) * Se + t) * Dd + i) = pk;
+  }
+  for (int i = threadIdx.x; i < Dd; i += blockDim.x) {
+    float acc = 0.f;
+    for (int r = keep; r < L; ++r) acc += dyn[static_cast<size_t>(1 + sh[r]) * Dd + i];
+    atomicAdd(d_mask_token + i, acc);
+  }
+}
+
+// Gradient entering the encoder output (un-normed: the reference discards encoder_norm,
+// MAE_ViT_Baseline.py:264):  d_x[n, t] = float(d_enc_bf16[n, t]) + (t >= 1 ? d_feat[n] / keep : 0)
+// where d_feat is the NT-Xent gradient w.r.t. the token-mean feature (MAE_ViT_MsLdCeCd.py:64-65).
+// Also emits the bf16 copy the next wgrad/dgrad GEMMs consume.
+__global__ void encoder_out_grad_kernel(const __nv_bfloat16* __restrict__ d_enc, const float* __restrict__ d_feat,
+                                        float* __restrict__ dx, __nv_bfloat16* __restrict__ dx_bf16, int Se, int D,
+                                        float inv_keep) {
+  const int row = blockIdx.x;
+  const int n = row / Se, t = row % Se;
+  const __nv_bfloat16* s = d_enc + static_cast<size_t>(row) * D;
+  const float* f = d_feat ? d_feat + static_cast<size_t>(n) * D : nullptr;
+  for (int i = threadIdx.x * 4; i < D; i += blockDim.x * 4) {
+    const uint2 ev = *reinterpret_cast<const uint2*>(s + i);
+    const float2 e0 = unpack_bf16x2(ev.x), e1 = unpack_bf16x2(ev.y);
+    float4 v = make_float4(e0.x, e0.y, e1.x, e1.y);
+    if (f != nullptr && t >= 1) {
+      const float4 g = *reinterpret_cast<const float4*>(f + i);
+      v.x += g.x * inv_keep; v.y += g.y * inv_keep; v.z += g.z * inv_keep; v.w += g.w * inv_keep;
+    }
+    *reinterpret_cast<float4*>(dx + static_cast<size_t>(row) * D + i) = v;
+    uint2 pk;
+    pk.x = pack_bf16x2(v.x, v.y);
+    pk.y = pack_bf16x2(v.z, v.w);
+    *reinterpret_cast<uint2*>(dx_bf16 + static_cast<size_t>(row) * D + i) = pk;
+  }
+}
+
+// d_cls[i] = sum_n dx[n, 0, i]
+__global__ void cls_grad_kernel(const float* __restrict__ dx, float* __restrict__ d_cls, int nimg, int Se, int D) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= D) return;
+  float acc = 0.f;
+  for (int n = 0; n < nimg; ++n) acc += dx[static_cast<size_t>(n) * Se * D + i];
+  d_cls[i] = acc;
+}
+
+}  // namespace
+
+extern "C" int csm_random_masking(const float* noise, int nimg, int L, int keep, long long* ids_restore,
+                                  int* ids_shuffle, float* mask, cudaStream_t stream) {
+  CSM_CHECK_ARG(nimg > 0 && L > 0 && keep >= 0 && keep <= L, "csm_random_masking: bad sizes nimg=%d L=%d keep=%d",
+                nimg, L, keep);
+  CSM_CHECK_ARG(L <= 12288, "csm_random_masking: L=%d exceeds the shared-memory row limit", L);
+  const int threads = L >= 512 ? 512 : (L >= 256 ? 256 : 128);
+  random_masking_kernel<<<nimg, threads, L * sizeof(float), stream>>>(noise, L, keep, ids_restore, ids_shuffle, mask);
+  CSM_CHECK_LAUNCH("random_masking");
+  return CSM_OK;
+}
+
+extern "C" int csm_patch_gather(const float* imgs, const int* ids_shuffle, void* out_bf16, int nimg, int C, int H,
+                                int p, int L, int keep, cudaStream_t stream) {
+  CSM_CHECK_ARG(nimg > 0 && H % p == 0 && (H / p) * (H / p) == L, "csm_patch_gather: bad geometry H=%d p=%d L=%d", H,
+                p, L);
+  CSM_CHECK_ARG(p % 4 == 0 && (C * p * p) % 8 == 0, "csm_patch_gather: patch size must be a multiple of 4 (p=%d)", p);
+  CSM_CHECK_ARG((reinterpret_cast<uintptr_t>(imgs) & 15) == 0, "csm_patch_gather: imgs must be 16-byte aligned");
+  const int rows = nimg * (keep + 1);
+  const int wpb = 8;
+  patch_gather_kernel<<<csm_cdiv(rows, wpb), wpb * 32, 0, stream>>>(
+      imgs, ids_shuffle, reinterpret_cast<__nv_bfloat16*>(out_bf16), nimg, C, H, p, L, keep);
+  CSM_CHECK_LAUNCH("patch_gather");
+  return CSM_OK;
+}
+
+extern "C" int csm_encoder_assemble(const void* emb_bf16, const int* ids_shuffle, const float* pos, const float* cls,
+                                    float* x, int nimg, int L, int keep, int D, cudaStream_t stream) {
+  CSM_CHECK_ARG(D % 4 == 0, "csm_encoder_assemble: D must be a multiple of 4 (D=%d)", D);
+  encoder_assemble_kernel<<<nimg * (keep + 1), 128, 0, stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(emb_bf16), ids_shuffle, pos, cls, x, nimg, L, keep, D);
+  CSM_CHECK_LAUNCH("encoder_assemble");
+  return CSM_OK;
+}
+
+extern "C" int csm_decoder_assemble(const void* demb_bf16, const long long* ids_restore, const float* mask_token,
+                                    const float* dpos, float* y, int nimg, int L, int keep, int Dd,
+                                    cudaStream_t stream) {
+  CSM_CHECK_ARG(Dd % 4 == 0, "csm_decoder_assemble: Dd must be a multiple of 4 (Dd=%d)", Dd);
+  decoder_assemble_kernel<<<nimg * (L + 1), 128, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(demb_bf16),
+                                                             ids_restore, mask_token, dpos, y, L, keep, Dd);
+  CSM_CHECK_LAUNCH("decoder_assemble");
+  return CSM_OK;
+}
+
+extern "C" int csm_decoder_assemble_bwd(const float* dy, const int* ids_shuffle, void* d_demb_bf16,
+                                        float* d_mask_token, int nimg, int L, int keep, int Dd, cudaStream_t stream) {
+  CSM_CHECK_ARG(Dd % 4 == 0, "csm_decoder_assemble_bwd: Dd must be a multiple of 4 (Dd=%d)", Dd);
+  decoder_assemble_bwd_kernel<<<nimg, 256, 0, stream>>>(dy, ids_shuffle, reinterpret_cast<__nv_bfloat16*>(d_demb_bf16),
+                                                        d_mask_token, L, keep, Dd);
+  CSM_CHECK_LAUNCH("decoder_assemble_bwd");
+  return CSM_OK;
+}
+
+extern "C" int csm_encoder_out_grad(const void* d_enc_bf16, const float* d_feat, float* dx, void* dx_bf16, int nimg,
+                                    int Se, int D, cudaStream_t stream) {
+  CSM_CHECK_ARG(D % 4 == 0 && Se >= 2, "csm_encoder_out_grad: bad sizes Se=%d D=%d", Se, D);
+  encoder_out_grad_kernel<<<nimg * Se, 128, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(d_enc_bf16), d_feat,
+                                                         dx, reinterpret_cast<__nv_bfloat16*>(dx_bf16), Se, D,
+                                                         1.0f / static_cast<float>(Se - 1));
+  CSM_CHECK_LAUNCH("encoder_out_grad");
+  return CSM_OK;
+}
+
+extern "C" int csm_cls_grad(const float* dx, float* d_cls, int nimg, int Se, int D, cudaStream_t stream) {
+  cls_grad_kernel<<<csm_cdiv(D, 128), 128, 0, stream>>>(dx, d_cls, nimg, Se, D);
+  CSM_CHECK_LAUNCH("cls_grad");
+  return CSM_OK;
+}

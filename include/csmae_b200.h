@@ -1,0 +1,124 @@
+/* csmae_b200 -- C-ABI of the B200-native Cross-Scale MAE pretraining hot path.
+ *
+ * The reference (aicip/Cross-Scale-MAE) is pure Python/PyTorch: it has no native library and no FFI.
+ * Its "operator interface" for this path is the set of ATen calls made by
+ * models_mae/MAE_ViT_{Shared,Baseline,MsLd,MsLdCeCd}.py, models_mae/MLP.py and util/contrast_loss.py.
+ * Every entry point below replaces one group of those calls; the citation next to each one is the
+ * reference file:line whose arithmetic it reproduces (paths relative to the upstream repo root).
+ * The Python binding a maintainer would add (ctypes over torch tensors' data_ptr()) is shown in
+ * INTEGRATION.md and implemented in cross-scale-mae_b200/csmae_b200/_native.py.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all pointers are DEVICE pointers into caller-owned memory;
+ *   - activations are contiguous row-major [rows, features] with rows = image-major tokens;
+ *   - "bf16" buffers hold __nv_bfloat16, residual stream / statistics / losses / gradients are f32,
+ *     ids_restore is int64 (interchangeable with torch.gather users), mask is f32;
+ *   - every call is asynchronous on `stream` and never synchronises with the host;
+ *   - return value: 0 on success, negative on error (csm_last_error() holds the message;
+ *     no exception ever crosses the boundary);
+ *   - the library contains sm_100a code only: csm_device_check() refuses any other device and there
+ *     is no CPU or generic-GPU fallback.
+ */
+#ifndef CSMAE_B200_H
+#define CSMAE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* csm_stream_t; /* == cudaStream_t */
+
+/* ---- runtime ------------------------------------------------------------------------------ */
+const char* csm_last_error(void);
+int csm_version(void);
+/* returns the SM count (> 0) when `device` is an sm_100 part, else a negative error */
+int csm_device_check(int device);
+
+/* ---- tcgen05 GEMMs: nn.Linear forward / dgrad / wgrad ---------------------------------------
+ * timm Block qkv/proj/fc1/fc2 (MAE_ViT_Baseline.py:160-188), patch_embed.proj as a GEMM (:75-77,245),
+ * decoder_embed (:270), decoder_pred (:295), predictor Linears (MLP.py:6,9).
+ * epilogue codes: 0 out_bf16 = bf16(acc + bias)
+ *                 1 out_bf16 = h = bf16(acc + bias), aux_bf16 = bf16(gelu_erf(h))          (fc1 + nn.GELU)
+ *                 2 out_f32  = aux_f32 + bf16(acc + bias)                                  (x = x + proj/fc2)
+ *                 3 out_bf16 = bf16(bf16(acc) * gelu'(aux_bf16))                           (dgrad only)
+ *                 5 out_f32  = acc + bias
+ */
+int csm_linear_fwd(const void* x_bf16, const void* w_bf16, const float* bias, void* out, void* aux, int M, int N,
+                   int K, int epilogue, csm_stream_t stream);
+/* dX[M,K] = dY[M,N] . W[N,K]  (W read in its stored [N,K] layout) ; epilogue 0, 3 or 5 */
+int csm_linear_dgrad(const void* dy_bf16, const void* w_bf16, void* dx, const void* aux, int M, int N, int K,
+                     int epilogue, csm_stream_t stream);
+/* dW[N,K] += dY[rows,N]^T . X[rows,K]   (f32, split over the token rows, red.global.add) */
+int csm_linear_wgrad(const void* dy_bf16, const void* x_bf16, float* dw, int rows, int N, int K, int num_sms,
+                     csm_stream_t stream);
+/* db[N] += column sums of dY[rows,N]; rows with (row % skip_period == 0) are skipped when skip_period > 0 */
+int csm_colsum_bf16(const void* dy_bf16, float* db, int rows, int N, int skip_period, int num_sms,
+                    csm_stream_t stream);
+
+/* ---- masking / token shuffles ---------------------------------------------------------------
+ * random_masking: MAE_ViT_Shared.py:57-84 (stable-by-index argsort of the caller's noise) */
+int csm_random_masking(const float* noise, int nimg, int L, int keep, long long* ids_restore, int* ids_shuffle,
+                       float* mask, csm_stream_t stream);
+/* kept patches -> GEMM operand rows [(nimg*(keep+1)), C*p*p] in Conv2d (c,py,px) order; cls slot rows zero
+ * (timm PatchEmbed conv, MAE_ViT_Baseline.py:75-77,245, fused with the masking gather :251) */
+int csm_patch_gather(const float* imgs, const int* ids_shuffle, void* out_bf16, int nimg, int C, int H, int p, int L,
+                     int keep, csm_stream_t stream);
+/* + pos-embed of the kept patch, cls token row (MAE_ViT_Baseline.py:248,254-256) */
+int csm_encoder_assemble(const void* emb_bf16, const int* ids_shuffle, const float* pos, const float* cls, float* x,
+                         int nimg, int L, int keep, int D, csm_stream_t stream);
+/* mask tokens + un-shuffle + decoder pos-embed (MAE_ViT_Baseline.py:273-283) and its backward */
+int csm_decoder_assemble(const void* demb_bf16, const long long* ids_restore, const float* mask_token,
+                         const float* dpos, float* y, int nimg, int L, int keep, int Dd, csm_stream_t stream);
+int csm_decoder_assemble_bwd(const float* dy, const int* ids_shuffle, void* d_demb_bf16, float* d_mask_token,
+                             int nimg, int L, int keep, int Dd, csm_stream_t stream);
+/* gradient entering the (un-normed, MAE_ViT_Baseline.py:264) encoder output: decoder_embed dgrad + NT-Xent feature grad */
+int csm_encoder_out_grad(const void* d_enc_bf16, const float* d_feat, float* dx, void* dx_bf16, int nimg, int Se,
+                         int D, csm_stream_t stream);
+int csm_cls_grad(const float* dx, float* d_cls, int nimg, int Se, int D, csm_stream_t stream);
+
+/* ---- LayerNorm (eps 1e-6, MAE_ViT_Baseline.py:43-45) and casts -------------------------------- */
+int csm_layernorm_fwd(const float* x, const float* gamma, const float* beta, void* out_bf16, float* out_f32,
+                      float* mean, float* rstd, int rows, int D, float eps, csm_stream_t stream);
+int csm_layernorm_bwd(const void* dy_bf16, const float* dy2_f32, const float* x, const float* mean, const float* rstd,
+                      const float* gamma, const float* dres_in, float* dres_out, void* dres_bf16, float* dgamma,
+                      float* dbeta, int rows, int D, int num_sms, csm_stream_t stream);
+int csm_cast_multi(const void* table_dev, int num_tensors, int blocks_per_tensor, csm_stream_t stream);
+int csm_cast_f32_bf16(const float* src, void* dst_bf16, long long n, csm_stream_t stream);
+
+/* ---- attention (timm 0.4.12 Attention; MAE_ViT_Baseline.py:160-188) -------------------------- */
+int csm_attention_fwd(const void* qkv_bf16, void* out_bf16, float* lse, int B, int S, int H, int head_dim,
+                      csm_stream_t stream);
+int csm_attention_bwd(const void* qkv_bf16, const void* out_bf16, const void* d_out_bf16, const float* lse,
+                      float* delta_scratch, void* dqkv_bf16, int B, int S, int H, int head_dim, csm_stream_t stream);
+
+/* ---- losses ---------------------------------------------------------------------------------
+ * masked per-patch MSE against the image read in patch order (MAE_ViT_Shared.py:24-39,97-120) */
+int csm_recon_loss_fwd(const void* pred_full_bf16, const float* imgs, const float* mask, float* loss_sum, int nimg,
+                       int C, int H, int p, int L, int norm_pix, csm_stream_t stream);
+int csm_recon_loss_bwd(const void* pred_full_bf16, const float* imgs, const float* mask, void* dpred_bf16,
+                       const float* grad_scalar, float coef, int nimg, int C, int H, int p, int L, int norm_pix,
+                       csm_stream_t stream);
+/* cross-scale decoder MSE, target not detached (MAE_ViT_MsLdCeCd.py:57-59) */
+int csm_cross_mse_fwd(const void* cp_bf16, const float* tgt, float* loss_sum, int rows, int Sd, int Dd,
+                      csm_stream_t stream);
+int csm_cross_mse_bwd(const void* cp_bf16, const float* tgt, void* d_cp_bf16, float* d_tgt, const float* grad_scalar,
+                      float coef, int rows, int Sd, int Dd, csm_stream_t stream);
+/* BatchNorm1d(num_patches) over [N, L, Hp] + ReLU, train mode (MLP.py:7-8) */
+int csm_bn_patch_fwd(const void* h_bf16, const float* gamma, const float* beta, void* out_bf16, float* mean,
+                     float* rstd, float* running_mean, float* running_var, int N, int L, int Hp, float eps,
+                     float momentum, int training, csm_stream_t stream);
+int csm_bn_patch_bwd(const void* h_bf16, const void* out_bf16, const void* d_out_bf16, const float* gamma,
+                     const float* mean, const float* rstd, void* dh_bf16, float* dgamma, float* dbeta, int N, int L,
+                     int Hp, csm_stream_t stream);
+/* NT-Xent on the token-mean encoder features (util/contrast_loss.py:71-101; MAE_ViT_MsLdCeCd.py:62-69) */
+int csm_ntxent_fwd(const float* enc_out, float* zhat, float* fnorm, float* neg, float* loss_sum, int B, int Se, int D,
+                   float tau, float eps, csm_stream_t stream);
+int csm_ntxent_bwd(const float* zhat, const float* fnorm, const float* neg, const float* grad_scalar, float* d_feat,
+                   int B, int D, float tau, float eps, csm_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CSMAE_B200_H */

@@ -1,0 +1,381 @@
+"""GPU parity of every C-ABI kernel against the plain torch expression of the reference op it
+replaces (fp32 math on the same bf16-rounded inputs).  Index outputs are bit-exact; floating-point
+tolerances are written next to each check."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+bf16, f32 = torch.bfloat16, torch.float32
+
+
+@pytest.fixture(scope="module")
+def nat():
+    from csmae_b200 import _native
+    _native.load()
+    assert _native.sm_count(0) > 0
+    return _native
+
+
+def rnd(*shape, scale=1.0, dtype=f32, seed=None):
+    g = torch.Generator(device="cuda")
+    g.manual_seed(seed if seed is not None else (hash(shape) & 0xFFFF))
+    return (torch.randn(*shape, device="cuda", generator=g) * scale).to(dtype)
+
+
+def close(a, b, rtol, atol, what=""):
+    a, b = a.float(), b.float()
+    err = (a - b).abs()
+    tol = atol + rtol * b.abs()
+    bad = err > tol
+    assert not bad.any(), f"{what}: {int(bad.sum())}/{bad.numel()} off, max err {err.max().item():.3e} " \
+                          f"(ref max {b.abs().max().item():.3e})"
+
+
+# ------------------------------------------------------------------------------------------------ GEMM
+GEMM_SHAPES = [(128, 128, 64), (256, 384, 128), (200, 136, 72), (3200, 768, 768), (1000, 2304, 768),
+               (394, 64, 64), (64, 192, 64), (12608, 512, 2048)]
+
+
+@pytest.mark.parametrize("M,N,K", GEMM_SHAPES)
+def test_linear_fwd_bf16(nat, M, N, K):
+    x, w, b = rnd(M, K, dtype=bf16), rnd(N, K, scale=K ** -0.5, dtype=bf16), rnd(N)
+    out = torch.full((M, N), float("nan"), device="cuda", dtype=bf16)
+    nat.call("csm_linear_fwd", x, w, b, out, None, M, N, K, nat.EPI_BF16)
+    ref = x.float() @ w.float().t() + b
+    close(out, ref, 1e-2, 1e-2, "linear_fwd bf16")      # bf16 output rounding (2^-8 relative)
+
+
+@pytest.mark.parametrize("M,N,K", [(256, 256, 128), (1000, 3072, 768), (200, 136, 72)])
+def test_linear_fwd_gelu_resid_f32(nat, M, N, K):
+    x, w, b = rnd(M, K, dtype=bf16), rnd(N, K, scale=K ** -0.5, dtype=bf16), rnd(N)
+    ref = x.float() @ w.float().t() + b
+    h = torch.empty(M, N, device="cuda", dtype=bf16)
+    act = torch.empty(M, N, device="cuda", dtype=bf16)
+    nat.call("csm_linear_fwd", x, w, b, h, act, M, N, K, nat.EPI_GELU)
+    close(h, ref, 1e-2, 1e-2, "gelu epilogue: pre-activation")
+    close(act, F.gelu(h.float()), 1e-2, 1e-3, "gelu epilogue: activation")    # exact-erf GELU of the stored h
+    resid = rnd(M, N, seed=5)
+    out = torch.empty(M, N, device="cuda")
+    nat.call("csm_linear_fwd", x, w, b, out, resid, M, N, K, nat.EPI_RESID)
+    close(out, resid + ref.to(bf16).float(), 1e-2, 1e-2, "residual epilogue")
+    o32 = torch.empty(M, N, device="cuda")
+    nat.call("csm_linear_fwd", x, w, b, o32, None, M, N, K, nat.EPI_F32)
+    close(o32, ref, 1e-4, 1e-4, "f32 epilogue")          # only fp32 accumulation-order differences
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 128), (256, 384, 128), (200, 136, 72), (3200, 2304, 768),
+                                   (1000, 768, 3072), (394, 64, 64)])
+def test_linear_dgrad(nat, M, N, K):
+    dy, w = rnd(M, N, dtype=bf16), rnd(N, K, scale=N ** -0.5, dtype=bf16)
+    ref = dy.float() @ w.float()
+    dx = torch.empty(M, K, device="cuda")
+    nat.call("csm_linear_dgrad", dy, w, dx, None, M, N, K, nat.EPI_F32)
+    close(dx, ref, 1e-4, 1e-4, "dgrad f32")
+    dxb = torch.empty(M, K, device="cuda", dtype=bf16)
+    nat.call("csm_linear_dgrad", dy, w, dxb, None, M, N, K, nat.EPI_BF16)
+    close(dxb, ref, 1e-2, 1e-2, "dgrad bf16")
+    hpre = rnd(M, K, dtype=bf16, seed=9)
+    dh = torch.empty(M, K, device="cuda", dtype=bf16)
+    nat.call("csm_linear_dgrad", dy, w, dh, hpre, M, N, K, nat.EPI_DGELU)
+    hp = hpre.float().requires_grad_(True)
+    F.gelu(hp).backward(ref.to(bf16).float())
+    close(dh, hp.grad, 1e-2, 1e-2, "dgrad + dGELU")
+
+
+@pytest.mark.parametrize("rows,N,K", [(128, 128, 128), (1000, 256, 192), (6400, 2304, 768), (12608, 512, 2048),
+                                      (777, 64, 136), (50, 192, 64)])
+def test_linear_wgrad(nat, rows, N, K):
+    dy, x = rnd(rows, N, dtype=bf16), rnd(rows, K, dtype=bf16)
+    dw = torch.zeros(N, K, device="cuda")
+    nat.call("csm_linear_wgrad", dy, x, dw, rows, N, K, 148)
+    ref = dy.float().t() @ x.float()
+    close(dw, ref, 2e-4, 2e-3 * math.sqrt(rows / 128), "wgrad")   # fp32 split-K accumulation order
+    nat.call("csm_linear_wgrad", dy, x, dw, rows, N, K, 148)       # accumulates
+    close(dw, 2 * ref, 2e-4, 4e-3 * math.sqrt(rows / 128), "wgrad accumulate")
+
+
+def test_colsum(nat):
+    dy = rnd(1234, 768, dtype=bf16)
+    db = torch.zeros(768, device="cuda")
+    nat.call("csm_colsum_bf16", dy, db, 1234, 768, 0, 148)
+    close(db, dy.float().sum(0), 1e-4, 1e-3, "colsum")
+    db.zero_()
+    nat.call("csm_colsum_bf16", dy, db, 1234, 768, 50, 148)
+    keep = torch.arange(1234, device="cuda") % 50 != 0
+    close(db, dy.float()[keep].sum(0), 1e-4, 1e-3, "colsum skip")
+
+
+# ------------------------------------------------------------------------------------------------ masking
+@pytest.mark.parametrize("nimg,L,ratio", [(64, 196, 0.75), (16, 784, 0.75), (3, 16, 0.75), (5, 64, 0.9), (2, 36, 0.6)])
+def test_random_masking_bit_exact(nat, nimg, L, ratio):
+    torch.manual_seed(L)
+    noise = torch.rand(nimg, L, device="cuda")
+    noise[0, 3] = noise[0, 1]                 # force ties: stable-by-index order is the contract
+    noise[-1, :4] = 0.5
+    keep = int(L * (1 - ratio))
+    ids_restore = torch.empty(nimg, L, dtype=torch.int64, device="cuda")
+    ids_shuffle = torch.empty(nimg, L, dtype=torch.int32, device="cuda")
+    mask = torch.empty(nimg, L, device="cuda")
+    nat.call("csm_random_masking", noise, nimg, L, keep, ids_restore, ids_shuffle, mask)
+    sh = torch.argsort(noise, dim=1, stable=True)
+    rs = torch.argsort(sh, dim=1, stable=True)
+    m = torch.ones(nimg, L, device="cuda")
+    m[:, :keep] = 0
+    m = torch.gather(m, 1, rs)
+    assert torch.equal(ids_restore, rs)
+    assert torch.equal(ids_shuffle.long(), sh)
+    assert torch.equal(mask, m)
+
+
+def test_patch_gather_and_assemble(nat):
+    nimg, C, H, p, D, Dd = 5, 3, 64, 16, 64, 32
+    L, keep = 16, 4
+    Se, Sd = keep + 1, L + 1
+    imgs = rnd(nimg, C, H, H)
+    noise = torch.rand(nimg, L, device="cuda")
+    sh = torch.argsort(noise, dim=1, stable=True)
+    rs = torch.argsort(sh, dim=1, stable=True)
+    sh32 = sh.int().contiguous()
+    out = torch.full((nimg * Se, C * p * p), float("nan"), device="cuda", dtype=bf16)
+    nat.call("csm_patch_gather", imgs, sh32, out, nimg, C, H, p, L, keep)
+    # conv-order patches: [n, l, (c, py, px)]
+    pat = imgs.reshape(nimg, C, H // p, p, H // p, p).permute(0, 2, 4, 1, 3, 5).reshape(nimg, L, C * p * p)
+    ref = torch.gather(pat, 1, sh[:, :keep].unsqueeze(-1).expand(-1, -1, C * p * p))
+    o = out.view(nimg, Se, -1)
+    assert torch.equal(o[:, 0], torch.zeros_like(o[:, 0]))
+    assert torch.equal(o[:, 1:], ref.to(bf16))
+
+    emb = rnd(nimg * Se, D, dtype=bf16)
+    pos, cls = rnd(L + 1, D), rnd(D)
+    x = torch.empty(nimg * Se, D, device="cuda")
+    nat.call("csm_encoder_assemble", emb, sh32, pos, cls, x, nimg, L, keep, D)
+    xr = torch.empty(nimg, Se, D, device="cuda")
+    xr[:, 0] = cls + pos[0]
+    xr[:, 1:] = emb.view(nimg, Se, D)[:, 1:].float() + pos[1:][sh[:, :keep]]
+    assert torch.equal(x.view(nimg, Se, D), xr)
+
+    demb = rnd(nimg * Se, Dd, dtype=bf16)
+    mtok, dpos = rnd(Dd), rnd(Sd, Dd)
+    y = torch.empty(nimg * Sd, Dd, device="cuda")
+    nat.call("csm_decoder_assemble", demb, rs.contiguous(), mtok, dpos, y, nimg, L, keep, Dd)
+    de = demb.view(nimg, Se, Dd).float()
+    x_ = torch.cat([de[:, 1:], mtok.expand(nimg, L - keep, Dd)], 1)
+    x_ = torch.gather(x_, 1, rs.unsqueeze(-1).expand(-1, -1, Dd))
+    yr = torch.cat([de[:, :1], x_], 1) + dpos
+    assert torch.equal(y.view(nimg, Sd, Dd), yr)
+
+    dy = rnd(nimg * Sd, Dd)
+    d_demb = torch.empty(nimg * Se, Dd, device="cuda", dtype=bf16)
+    d_mtok = torch.zeros(Dd, device="cuda")
+    nat.call("csm_decoder_assemble_bwd", dy, sh32, d_demb, d_mtok, nimg, L, keep, Dd)
+    de_l = de.clone().requires_grad_(True)
+    mt_l = mtok.clone().requires_grad_(True)
+    x_ = torch.cat([de_l[:, 1:], mt_l.expand(nimg, L - keep, Dd)], 1)
+    x_ = torch.gather(x_, 1, rs.unsqueeze(-1).expand(-1, -1, Dd))
+    (torch.cat([de_l[:, :1], x_], 1) + dpos).backward(dy.view(nimg, Sd, Dd))
+    assert torch.equal(d_demb.view(nimg, Se, Dd), de_l.grad.to(bf16))
+    close(d_mtok, mt_l.grad, 1e-5, 1e-5, "mask_token grad")
+
+
+def test_encoder_out_grad_and_cls(nat):
+    nimg, Se, D = 6, 5, 64
+    d_enc, d_feat = rnd(nimg * Se, D, dtype=bf16), rnd(nimg, D)
+    dx = torch.empty(nimg * Se, D, device="cuda")
+    dx16 = torch.empty(nimg * Se, D, device="cuda", dtype=bf16)
+    nat.call("csm_encoder_out_grad", d_enc, d_feat, dx, dx16, nimg, Se, D)
+    ref = d_enc.float().view(nimg, Se, D).clone()
+    ref[:, 1:] += (d_feat / (Se - 1)).unsqueeze(1)
+    close(dx.view(nimg, Se, D), ref, 1e-6, 1e-6, "encoder_out_grad")
+    assert torch.equal(dx16, dx.to(bf16))
+    d_cls = torch.empty(D, device="cuda")
+    nat.call("csm_cls_grad", dx, d_cls, nimg, Se, D)
+    close(d_cls, dx.view(nimg, Se, D)[:, 0].sum(0), 1e-5, 1e-5, "cls grad")
+
+
+# ------------------------------------------------------------------------------------------------ LayerNorm
+@pytest.mark.parametrize("rows,D", [(3200, 768), (1000, 512), (300, 1024), (77, 64)])
+def test_layernorm_fwd_bwd(nat, rows, D):
+    x, g, b = rnd(rows, D, scale=2.0), 1 + 0.1 * rnd(D), 0.1 * rnd(D, seed=3)
+    o16 = torch.empty(rows, D, device="cuda", dtype=bf16)
+    o32 = torch.empty(rows, D, device="cuda")
+    mean, rstd = torch.empty(rows, device="cuda"), torch.empty(rows, device="cuda")
+    nat.call("csm_layernorm_fwd", x, g, b, o16, o32, mean, rstd, rows, D, 1e-6)
+    ref = F.layer_norm(x, (D,), g, b, 1e-6)
+    close(o32, ref, 1e-5, 1e-5, "LN fwd f32")
+    assert torch.equal(o16, o32.to(bf16))
+    dy16, dy2, dres_in = rnd(rows, D, dtype=bf16, seed=1), rnd(rows, D, seed=2), rnd(rows, D, seed=4)
+    dres = torch.empty(rows, D, device="cuda")
+    dres16 = torch.empty(rows, D, device="cuda", dtype=bf16)
+    dg, db = torch.zeros(D, device="cuda"), torch.zeros(D, device="cuda")
+    nat.call("csm_layernorm_bwd", dy16, dy2, x, mean, rstd, g, dres_in, dres, dres16, dg, db, rows, D, 148)
+    xl, gl, bl = x.clone().requires_grad_(True), g.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    F.layer_norm(xl, (D,), gl, bl, 1e-6).backward(dy16.float() + dy2)
+    close(dres, dres_in + xl.grad, 1e-4, 1e-4, "LN bwd dx")
+    assert torch.equal(dres16, dres.to(bf16))
+    close(dg, gl.grad, 1e-4, 1e-3 * math.sqrt(rows / 100), "LN dgamma")
+    close(db, bl.grad, 1e-4, 1e-3 * math.sqrt(rows / 100), "LN dbeta")
+    # in-place residual-gradient update + bf16-only incoming gradient
+    d2 = dres_in.clone()
+    nat.call("csm_layernorm_bwd", dy16, None, x, mean, rstd, g, d2, d2, dres16, dg, db, rows, D, 148)
+    xl.grad = None
+    F.layer_norm(xl, (D,), g, b, 1e-6).backward(dy16.float())
+    close(d2, dres_in + xl.grad, 1e-4, 1e-4, "LN bwd in place")
+
+
+def test_casts(nat):
+    a = rnd(1000003)
+    o = torch.empty(1000003, device="cuda", dtype=bf16)
+    nat.call("csm_cast_f32_bf16", a, o, a.numel())
+    assert torch.equal(o, a.to(bf16))
+    srcs = [rnd(n, seed=n) for n in (8, 768 * 768, 2304 * 768, 12)]
+    dsts = [torch.empty(s.numel(), device="cuda", dtype=bf16) for s in srcs]
+    table = []
+    for s, d in zip(srcs, dsts):
+        table += [s.data_ptr(), d.data_ptr(), s.numel()]
+    table = torch.tensor(table, dtype=torch.int64).cuda()
+    nat.call("csm_cast_multi", table, len(srcs), 32)
+    for s, d in zip(srcs, dsts):
+        assert torch.equal(d, s.to(bf16))
+
+
+# ------------------------------------------------------------------------------------------------ attention
+def attn_ref(qkv, B, S, H, d):
+    """timm 0.4.12 Attention core in fp32 on the bf16-rounded qkv (oracle/timm_shim.py)."""
+    q, k, v = qkv.float().view(B, S, 3, H, d).permute(2, 0, 3, 1, 4)
+    att = ((q @ k.transpose(-2, -1)) * d ** -0.5).softmax(-1)
+    return (att @ v).transpose(1, 2).reshape(B * S, H * d)
+
+
+@pytest.mark.parametrize("B,S,H,d", [(8, 50, 12, 64), (4, 197, 16, 32), (2, 785, 4, 32), (3, 197, 2, 64),
+                                     (5, 5, 1, 64), (3, 17, 2, 32), (2, 64, 2, 32), (2, 65, 1, 64)])
+def test_attention_fwd_bwd(nat, B, S, H, d):
+    Dm = H * d
+    qkv = rnd(B * S, 3 * Dm, dtype=bf16)
+    out = torch.full((B * S, Dm), float("nan"), device="cuda", dtype=bf16)
+    lse = torch.empty(B * H * S, device="cuda")
+    nat.call("csm_attention_fwd", qkv, out, lse, B, S, H, d)
+    ql = qkv.float().requires_grad_(True)
+    ref = attn_ref(ql, B, S, H, d)
+    # bf16 rounding of scores / probabilities / output: ~2^-8 relative per element
+    close(out, ref, 2e-2, 2e-2, "attention fwd")
+    d_out = rnd(B * S, Dm, dtype=bf16, seed=11)
+    ref.backward(d_out.float())
+    dqkv = torch.full((B * S, 3 * Dm), float("nan"), device="cuda", dtype=bf16)
+    delta = torch.empty(B * H * S, device="cuda")
+    nat.call("csm_attention_bwd", qkv, out, d_out, lse, delta, dqkv, B, S, H, d)
+    g = ql.grad
+    err = (dqkv.float() - g).abs().max().item()
+    assert err <= 3e-2 * g.abs().max().item() + 1e-3, f"attention bwd max err {err:.3e} vs max {g.abs().max():.3e}"
+    rel = ((dqkv.float() - g).norm() / g.norm()).item()
+    assert rel < 2e-2, f"attention bwd relative L2 error {rel:.3e}"
+
+
+# ------------------------------------------------------------------------------------------------ losses
+def patchify(imgs, p, c):
+    n, _, hh, _ = imgs.shape
+    g = hh // p
+    x = imgs.reshape(n, c, g, p, g, p)
+    return torch.einsum("nchpwq->nhwpqc", x).reshape(n, g * g, p * p * c)
+
+
+@pytest.mark.parametrize("norm_pix", [0, 1])
+def test_recon_loss(nat, norm_pix):
+    nimg, C, H, p = 6, 3, 64, 16
+    L, P = 16, 768
+    imgs = rnd(nimg, C, H, H)
+    pred_full = rnd(nimg * (L + 1), P, dtype=bf16)
+    mask = (torch.rand(nimg, L, device="cuda") < 0.75).float()
+    acc = torch.zeros(1, device="cuda")
+    nat.call("csm_recon_loss_fwd", pred_full, imgs, mask, acc, nimg, C, H, p, L, norm_pix)
+    pl = pred_full.float().view(nimg, L + 1, P)[:, 1:].clone().requires_grad_(True)
+    tgt = patchify(imgs, p, C)
+    if norm_pix:
+        tgt = (tgt - tgt.mean(-1, keepdim=True)) / (tgt.var(-1, keepdim=True) + 1e-6) ** 0.5
+        diff = pl - tgt
+    else:
+        diff = pl - tgt.to(bf16).float()          # autocast: einsum rounds the target to bf16
+    loss = ((diff ** 2).mean(-1) * mask).sum()
+    close(acc, loss.detach().reshape(1), 5e-3, 1e-3, "recon loss sum")       # bf16 rounding of (pred - target)
+    g = torch.tensor([3.0], device="cuda")
+    coef = 1.0 / (P * mask.sum().item())
+    dpred = torch.full((nimg * (L + 1), P), float("nan"), device="cuda", dtype=bf16)
+    nat.call("csm_recon_loss_bwd", pred_full, imgs, mask, dpred, g, coef, nimg, C, H, p, L, norm_pix)
+    (loss * 3.0 / mask.sum()).backward()
+    dp = dpred.float().view(nimg, L + 1, P)
+    assert torch.equal(dp[:, 0], torch.zeros_like(dp[:, 0]))
+    close(dp[:, 1:], pl.grad, 2e-2, 1e-6, "recon dpred")
+
+
+def test_cross_mse(nat):
+    N, Sd, Dd = 4, 17, 64
+    cp, tgt = rnd(N * Sd, Dd, dtype=bf16), rnd(N * Sd, Dd, seed=2)
+    acc = torch.zeros(1, device="cuda")
+    nat.call("csm_cross_mse_fwd", cp, tgt, acc, N * Sd, Sd, Dd)
+    d = (cp.float() - tgt).view(N, Sd, Dd)[:, 1:]
+    close(acc, (d ** 2).sum().reshape(1), 1e-4, 1e-3, "cross mse")
+    g = torch.tensor([2.0], device="cuda")
+    d_cp = torch.empty(N * Sd, Dd, device="cuda", dtype=bf16)
+    d_t = torch.empty(N * Sd, Dd, device="cuda")
+    coef = 1.0 / (N * (Sd - 1) * Dd)
+    nat.call("csm_cross_mse_bwd", cp, tgt, d_cp, d_t, g, coef, N * Sd, Sd, Dd)
+    ref = torch.zeros(N, Sd, Dd, device="cuda")
+    ref[:, 1:] = 2.0 * coef * 2 * d
+    close(d_t.view(N, Sd, Dd), -ref, 1e-5, 1e-7, "cross mse d_tgt")
+    close(d_cp.view(N, Sd, Dd), ref, 1e-2, 1e-7, "cross mse d_cp")
+
+
+def test_bn_patch(nat):
+    N, L, Hp = 8, 16, 128
+    Sd = L + 1
+    h = rnd(N * Sd, Hp, dtype=bf16, scale=2.0)
+    gamma, beta = 1 + 0.1 * rnd(L), 0.1 * rnd(L, seed=3)
+    rm, rv = torch.zeros(L, device="cuda"), torch.ones(L, device="cuda")
+    out = torch.full((N * Sd, Hp), float("nan"), device="cuda", dtype=bf16)
+    mean, rstd = torch.empty(L, device="cuda"), torch.empty(L, device="cuda")
+    nat.call("csm_bn_patch_fwd", h, gamma, beta, out, mean, rstd, rm, rv, N, L, Hp, 1e-5, 0.1, 1)
+    hl = h.float().view(N, Sd, Hp)[:, 1:].clone().requires_grad_(True)
+    gl, bl = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    rm_r, rv_r = torch.zeros(L, device="cuda"), torch.ones(L, device="cuda")
+    y = F.relu(F.batch_norm(hl, rm_r, rv_r, gl, bl, training=True, momentum=0.1, eps=1e-5))
+    o = out.float().view(N, Sd, Hp)
+    assert torch.equal(o[:, 0], torch.zeros_like(o[:, 0]))
+    close(o[:, 1:], y, 1e-2, 1e-2, "bn+relu fwd")
+    close(rm, rm_r, 1e-4, 1e-5, "running mean")
+    close(rv, rv_r, 1e-4, 1e-5, "running var")
+    d_out = rnd(N * Sd, Hp, dtype=bf16, seed=7)
+    dh = torch.full((N * Sd, Hp), float("nan"), device="cuda", dtype=bf16)
+    dg, db = torch.empty(L, device="cuda"), torch.empty(L, device="cuda")
+    nat.call("csm_bn_patch_bwd", h, out, d_out, gamma, mean, rstd, dh, dg, db, N, L, Hp)
+    y.backward(d_out.float().view(N, Sd, Hp)[:, 1:])
+    d = dh.float().view(N, Sd, Hp)
+    assert torch.equal(d[:, 0], torch.zeros_like(d[:, 0]))
+    close(d[:, 1:], hl.grad, 2e-2, 2e-3, "bn bwd dh")
+    close(dg, gl.grad, 1e-2, 5e-2, "bn dgamma")      # relu mask taken from the bf16-rounded output
+    close(db, bl.grad, 1e-2, 5e-2, "bn dbeta")
+    # eval mode uses the running statistics
+    nat.call("csm_bn_patch_fwd", h, gamma, beta, out, mean, rstd, rm, rv, N, L, Hp, 1e-5, 0.1, 0)
+    ye = F.relu(F.batch_norm(hl.detach(), rm, rv, gamma, beta, training=False, eps=1e-5))
+    close(out.float().view(N, Sd, Hp)[:, 1:], ye, 1e-2, 1e-2, "bn eval")
+
+
+@pytest.mark.parametrize("B,Se,D", [(64, 50, 768), (4, 5, 64), (32, 50, 1024)])
+def test_ntxent(nat, B, Se, D):
+    from oracle import restatement as R
+    x = rnd(2 * B * Se, D)
+    zhat, fnorm = torch.empty(2 * B, D, device="cuda"), torch.empty(2 * B, device="cuda")
+    neg, acc = torch.empty(2 * B, device="cuda"), torch.zeros(1, device="cuda")
+    nat.call("csm_ntxent_fwd", x, zhat, fnorm, neg, acc, B, Se, D, 0.5, 1e-8)
+    xl = x.clone().requires_grad_(True)
+    f = xl.view(2 * B, Se, D)[:, 1:].mean(1)
+    loss = R.ntxent(f[:B], f[B:])
+    close(acc, loss.detach().reshape(1), 1e-5, 1e-5, "ntxent loss")
+    g = torch.tensor([1.5], device="cuda")
+    d_feat = torch.empty(2 * B, D, device="cuda")
+    nat.call("csm_ntxent_bwd", zhat, fnorm, neg, g, d_feat, B, D, 0.5, 1e-8)
+    f2 = f.detach().clone().requires_grad_(True)
+    (R.ntxent(f2[:B], f2[B:]) * 1.5).backward()
+    close(d_feat, f2.grad, 1e-3, 1e-6 * f2.grad.abs().max().item() + 1e-9, "ntxent d_feat")
