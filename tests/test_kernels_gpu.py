@@ -61,7 +61,7 @@ def test_linear_fwd_gelu_resid_f32(nat, M, N, K):
     resid = rnd(M, N, seed=5)
     out = torch.empty(M, N, device="cuda")
     nat.call("csm_linear_fwd", x, w, b, out, resid, M, N, K, nat.EPI_RESID)
-    close(out, resid + ref.to(bf16).float(), 1e-2, 1e-2, "residual epilogue")
+    close(out - resid, ref, 1e-2, 1e-2, "residual epilogue")   # out = resid + bf16(acc + bias)
     o32 = torch.empty(M, N, device="cuda")
     nat.call("csm_linear_fwd", x, w, b, o32, None, M, N, K, nat.EPI_F32)
     close(o32, ref, 1e-4, 1e-4, "f32 epilogue")          # only fp32 accumulation-order differences
