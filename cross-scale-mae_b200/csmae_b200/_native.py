@@ -37,7 +37,7 @@ SIGNATURES = {
     "csm_encoder_out_grad": [_P, _P, _P, _P, _I, _I, _I, _P],
     "csm_cls_grad": [_P, _P, _I, _I, _I, _P],
     "csm_layernorm_fwd": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _F, _P],
-    "csm_layernorm_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P],
+    "csm_layernorm_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P],
     "csm_cast_multi": [_P, _I, _I, _P],
     "csm_cast_f32_bf16": [_P, _P, _L, _P],
     "csm_attention_fwd": [_P, _P, _P, _I, _I, _I, _I, _P],

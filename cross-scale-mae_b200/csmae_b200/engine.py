@@ -320,10 +320,13 @@ class HotPathEngine:
         y_final = B[f"dec.{len(m.decoder) - 1}.xout"] if len(m.decoder) else B["dec.x0"]
         dres = buf("b.dec.dres", (rows_d, Dd), f32)
         dres16 = buf("b.dec.dres16", (rows_d, Dd), bf16)
+        # the bf16 residual-stream gradient every LayerNorm backward emits is the dY of the Linear feeding
+        # that residual add, so its column sums (that Linear's bias gradient) are taken in the same pass
+        top_fc2_bias = G[f"decoder.{len(m.decoder) - 1}.mlp.fc2.bias"] if len(m.decoder) else None
         call("csm_layernorm_bwd", d_dec, dy2, y_final, B["dn_mean"], B["dn_rstd"], params["decoder_norm.weight"], None,
-             dres, dres16, G["decoder_norm.weight"], G["decoder_norm.bias"], rows_d, Dd, nsm)
+             dres, dres16, G["decoder_norm.weight"], G["decoder_norm.bias"], top_fc2_bias, rows_d, Dd, nsm)
         self._blocks_bwd("dec", "decoder", len(m.decoder), dres, dres16, NB, Sd, Dd, m.decoder_num_heads, params, w16,
-                         G, dev, nsm)
+                         G, dev, nsm, top_bias_done=True)
 
         # ---- un-shuffle backward, decoder_embed ---------------------------------------------------
         d_demb = buf("b.d_demb", (rows_e, Dd), bf16)
@@ -342,7 +345,7 @@ class HotPathEngine:
         eres16 = buf("b.enc.dres16", (rows_e, D), bf16)
         call("csm_encoder_out_grad", d_enc, d_feat, eres, eres16, NB, Se, D)
         self._blocks_bwd("enc", "encoder", len(m.encoder), eres, eres16, NB, Se, D, m.encoder_num_heads, params, w16,
-                         G, dev, nsm)
+                         G, dev, nsm, top_bias_done=False)
 
         # ---- cls token, patch embed (only the kept patches carry gradient; cls-slot rows are zero) -
         call("csm_cls_grad", eres, G["cls_token"], NB, Se, D)
@@ -351,7 +354,8 @@ class HotPathEngine:
         self._state = None
         return [G[n] for n in names]
 
-    def _blocks_bwd(self, tag, pname, nlayers, dres, dres16, NB, S, Dm, heads, params, w16, G, dev, nsm):
+    def _blocks_bwd(self, tag, pname, nlayers, dres, dres16, NB, S, Dm, heads, params, w16, G, dev, nsm,
+                    top_bias_done):
         bf16, f32 = torch.bfloat16, torch.float32
         rows = NB * S
         d = Dm // heads
@@ -363,7 +367,8 @@ class HotPathEngine:
             x_in = B[f"{tag}.{i - 1}.xout"] if i > 0 else B[f"{tag}.x0"]
             # MLP branch: x_out = x_mid + fc2(gelu(fc1(norm2(x_mid))))
             call("csm_linear_wgrad", dres16, B[t + "act"], G[q + "mlp.fc2.weight"], rows, Dm, hid, nsm)
-            call("csm_colsum_bf16", dres16, G[q + "mlp.fc2.bias"], rows, Dm, 0, nsm)
+            if i == nlayers - 1 and not top_bias_done:
+                call("csm_colsum_bf16", dres16, G[q + "mlp.fc2.bias"], rows, Dm, 0, nsm)
             dh = buf(f"b.{tag}.dh", (rows, hid), bf16)
             call("csm_linear_dgrad", dres16, w16[q + "mlp.fc2.weight"], dh, B[t + "h"], rows, Dm, hid, EPI_DGELU)
             call("csm_linear_wgrad", dh, B[t + "ln2"], G[q + "mlp.fc1.weight"], rows, hid, Dm, nsm)
@@ -372,10 +377,9 @@ class HotPathEngine:
             call("csm_linear_dgrad", dh, w16[q + "mlp.fc1.weight"], dln, None, rows, hid, Dm, EPI_BF16)
             call("csm_layernorm_bwd", dln, None, B[t + "xmid"], B[t + "mean2"], B[t + "rstd2"],
                  params[q + "norm2.weight"], dres, dres, dres16, G[q + "norm2.weight"], G[q + "norm2.bias"],
-                 rows, Dm, nsm)
+                 G[q + "attn.proj.bias"], rows, Dm, nsm)
             # attention branch: x_mid = x_in + proj(attn(qkv(norm1(x_in))))
             call("csm_linear_wgrad", dres16, B[t + "ao"], G[q + "attn.proj.weight"], rows, Dm, Dm, nsm)
-            call("csm_colsum_bf16", dres16, G[q + "attn.proj.bias"], rows, Dm, 0, nsm)
             d_ao = buf(f"b.{tag}.d_ao", (rows, Dm), bf16)
             call("csm_linear_dgrad", dres16, w16[q + "attn.proj.weight"], d_ao, None, rows, Dm, Dm, EPI_BF16)
             dqkv = buf(f"b.{tag}.dqkv", (rows, 3 * Dm), bf16)
@@ -384,8 +388,9 @@ class HotPathEngine:
             call("csm_linear_wgrad", dqkv, B[t + "ln1"], G[q + "attn.qkv.weight"], rows, 3 * Dm, Dm, nsm)
             call("csm_colsum_bf16", dqkv, G[q + "attn.qkv.bias"], rows, 3 * Dm, 0, nsm)
             call("csm_linear_dgrad", dqkv, w16[q + "attn.qkv.weight"], dln, None, rows, 3 * Dm, Dm, EPI_BF16)
+            below_fc2_bias = G[f"{pname}.{i - 1}.mlp.fc2.bias"] if i > 0 else None
             call("csm_layernorm_bwd", dln, None, x_in, B[t + "mean1"], B[t + "rstd1"], params[q + "norm1.weight"],
-                 dres, dres, dres16, G[q + "norm1.weight"], G[q + "norm1.bias"], rows, Dm, nsm)
+                 dres, dres, dres16, G[q + "norm1.weight"], G[q + "norm1.bias"], below_fc2_bias, rows, Dm, nsm)
 
 
 class CrossScaleStep(torch.autograd.Function):

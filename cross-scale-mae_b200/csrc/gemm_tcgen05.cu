@@ -4,20 +4,27 @@
 //   forward : Y[M,N]  = X[M,K] . W[N,K]^T          A K-major,  B K-major
 //   dgrad   : dX[M,K] = dY[M,N] . W[N,K]           A K-major,  B MN-major (W is read as stored: no
 //                                                  transposed weight copy exists anywhere)
-//   wgrad   : dW[N,K] = sum_r dY[r,N] . X[r,K]     A MN-major, B MN-major, reduction over the token
-//                                                  rows r, split over blockIdx.z and accumulated
-//                                                  with red.global.add.v4.f32
+//   wgrad   : dW[N,K] += sum_r dY[r,N] . X[r,K]    A MN-major, B MN-major, reduction over the token
+//                                                  rows r split into work units, TMA reduce-add (f32)
 //
-// One CTA computes one 128 x BN output tile:
-//   warp 0      TMA producer   (cp.async.bulk.tensor.2d -> 128B-swizzled smem ring, mbarrier tx)
-//   warp 1      TMEM allocator + single-thread tcgen05.mma issuer (accumulator in TMEM)
-//   warps 2..5  epilogue       (tcgen05.ld -> registers -> fused bias / GELU / residual / dGELU -> global)
-// Two CTAs are co-resident per SM (3-stage ring = 96 KB each) so one CTA's epilogue overlaps the
-// other's main loop.
+// Design (B200: 148 SMs = 74 SM pairs, L2 -> SM feed ~43 B/clk/SM is the binding resource for bf16
+// GEMM): a PERSISTENT kernel of 2-CTA clusters.  A cluster owns a 256 x BN output tile
+// (BN <= 256, chosen per problem): each CTA TMA-loads its own 128 rows of A and its own half of the B
+// tile (so a k-block costs 128 + BN/2 rows of traffic per SM instead of 128 + BN), the leader CTA issues
+// tcgen05.mma.cta_group::2 (M = 256) into TMEM accumulators that live in both SMs.
+//   warp 0      TMA producer (both CTAs; completion signalled on the LEADER's full barrier)
+//   warp 1      TMEM allocator; in the leader CTA the single-thread MMA issuer
+//   warps 2..9  epilogue: tcgen05.ld -> registers -> fused bias / GELU / residual / dGELU ->
+//               128B-swizzled staging tile in shared memory -> TMA store (or TMA reduce-add);
+//               residual / pre-activation inputs arrive by TMA load into the same staging tile
+// The accumulator is double-buffered in TMEM (2 x 256 columns), so the epilogue of tile i overlaps
+// the main loop of tile i+1; the smem ring is 5 stages of 32 KB.
 //
 // Rounding points follow the reference's CUDA-autocast graph (SURVEY.md 8a'): a Linear's output
 // is rounded to bf16 before it is added to the fp32 residual stream; GELU is evaluated in fp32 on
-// the bf16-rounded fc1 output and rounded again.
+// the bf16-rounded fc1 output and rounded again.  The fc1 epilogue stores gelu'(h) (bf16) instead of h:
+// it is the only thing the backward needs from h, and the exp it shares with gelu(h) is already there,
+// so the fc2-dgrad epilogue is a single multiply (one extra bf16 rounding on dh, documented in DESIGN.md).
 #include "common.cuh"
 
 #include <mutex>
@@ -27,243 +34,461 @@ namespace {
 
 using namespace csm;
 
-constexpr int BM = 128;
-constexpr int BK = 64;     // 64 bf16 = 128 bytes = one swizzle row
+constexpr int BM = 128;            // rows per CTA; the cluster tile is 2 * BM = 256 rows
+constexpr int BK = 64;             // 64 bf16 = 128 bytes = one swizzle row
 constexpr int UMMA_K = 16;
-constexpr int GEMM_THREADS = 192;
+constexpr int MAX_BN = 256;
+constexpr int STAGES = 5;
+constexpr int EPI_WARPS = 8;
+constexpr int GEMM_THREADS = 32 * (2 + EPI_WARPS);
+constexpr int A_BYTES = BM * BK * 2;                 // 16 KB
+constexpr int B_BYTES_MAX = (MAX_BN / 2) * BK * 2;   // 16 KB (each CTA holds half of the B tile)
+constexpr int STAGE_BYTES = A_BYTES + B_BYTES_MAX;
+constexpr int STG_BYTES = 4096;                      // one staging tile: 32 rows x 128 B
+constexpr int STG_BUFS = 2;
+constexpr int SMEM_RING = STAGES * STAGE_BYTES;
+constexpr int SMEM_STG = EPI_WARPS * STG_BUFS * STG_BYTES;
+constexpr int SMEM_BAR_OFFSET = SMEM_RING + SMEM_STG;
+constexpr int SMEM_TOTAL = SMEM_BAR_OFFSET + 512 + 1024;   // + barriers + 1024 B alignment slack
+constexpr int ACC_COLS = 256;                        // TMEM columns per accumulator buffer
 
 enum Epi : int {
   EPI_BF16 = 0,        // out_bf16 = bf16(acc + bias)
-  EPI_GELU = 1,        // out_bf16 = h = bf16(acc + bias); out2_bf16 = bf16(gelu(h))
+  EPI_GELU = 1,        // h = bf16(acc + bias); out_bf16 = bf16(gelu'(h)); out2_bf16 = bf16(gelu(h))
   EPI_RESID = 2,       // out_f32 = aux_f32 + bf16(acc + bias)              (residual stream)
-  EPI_DGELU = 3,       // out_bf16 = bf16(bf16(acc) * gelu'(aux_bf16))
-  EPI_F32_ATOMIC = 4,  // out_f32 += acc                                    (red.global.add)
+  EPI_DGELU = 3,       // out_bf16 = bf16(bf16(acc) * aux_bf16),  aux = the gelu'(h) stored by EPI_GELU
+  EPI_F32_ATOMIC = 4,  // out_f32 += acc                                    (TMA reduce-add)
   EPI_F32 = 5          // out_f32 = acc + bias
 };
 
 struct GemmParams {
-  int M, N, K;           // output rows, output cols, reduction length
-  int kb_per_split;      // k-blocks handled by one blockIdx.z
-  void* out;             // bf16 or f32 [M, ldo]
-  void* out2;            // bf16 [M, ldo]      (EPI_GELU)
+  int M, N;              // output rows / cols
+  int num_kb;            // k-blocks of the whole reduction
+  int kb_per_split;      // k-blocks handled by one work unit
+  int splits;
+  int bn;                // cluster tile width (multiple of 64, <= 256)
+  int tiles_m, tiles_n;  // 256-row tiles, bn-col tiles
   const float* bias;     // [N] or nullptr
-  const void* aux;       // EPI_DGELU: bf16 pre-activation h; EPI_RESID: f32 residual input
-  int ldo;               // leading dimension (elements) of out/out2/aux
 };
 
-template <int BN, int STAGES>
-struct SmemLayout {
-  static constexpr int A_BYTES = BM * BK * 2;
-  static constexpr int B_BYTES = BN * BK * 2;
-  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
-  static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;  // + barriers + 1024B alignment slack
-};
+// ---------------------------------------------------------------------------------------------
+// cluster / 2-CTA PTX helpers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t local_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t* smem_result, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)),
+               "r"(ncols)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish2() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem, both CTAs] (+)= A (128 rows from each CTA) * B (bn/2 rows from each CTA)
+__device__ __forceinline__ void umma2_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive (once) on the mbarrier at this shared-memory offset in BOTH CTAs of the pair when all previously
+// issued tcgen05.mma of this thread have completed
+__device__ __forceinline__ void umma2_commit_mc(uint64_t* bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"(static_cast<uint16_t>(3))
+      : "memory");
+}
+// TMA load whose completion bytes are signalled on an mbarrier that may live in the peer CTA
+__device__ __forceinline__ void tma2_load_2d(void* smem_dst, const CUtensorMap* map, uint32_t bar_cluster_addr, int c0,
+                                             int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], "
+      "[%2];" ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(map)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, const void* smem_src, int c0, int c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(map)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
-template <int BN, int STAGES, bool A_MN, bool B_MN, int EPI>
-__global__ void __launch_bounds__(GEMM_THREADS)
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint4 v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+
+struct WorkUnit {
+  int m_tile, n_tile, kb0, nkb;
+};
+__device__ __forceinline__ WorkUnit decode_unit(const GemmParams& p, int u) {
+  WorkUnit w;
+  w.n_tile = u % p.tiles_n;
+  const int r = u / p.tiles_n;
+  w.m_tile = r % p.tiles_m;
+  const int split = r / p.tiles_m;
+  w.kb0 = split * p.kb_per_split;
+  w.nkb = min(p.kb_per_split, p.num_kb - w.kb0);
+  return w;
+}
+
+// ---------------------------------------------------------------------------------------------
+template <bool A_MN, bool B_MN, int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+            const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_aux,
             const GemmParams p) {
-  using L = SmemLayout<BN, STAGES>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + SMEM_BAR_OFFSET);
   uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* accum_bar = empty_bar + STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+  uint64_t* tmem_full = empty_bar + STAGES;        // [2]
+  uint64_t* tmem_empty = tmem_full + 2;            // [2]
+  uint64_t* aux_bar = tmem_empty + 2;              // [EPI_WARPS][STG_BUFS]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux_bar + EPI_WARPS * STG_BUFS);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int n_tile = blockIdx.x;
-  const int m_tile = blockIdx.y;
-  const int num_kb_total = (p.K + BK - 1) / BK;
-  const int kb0 = blockIdx.z * p.kb_per_split;
-  const int kb1 = min(num_kb_total, kb0 + p.kb_per_split);
-  const int num_kb = kb1 - kb0;
+  const uint32_t rank = cluster_ctarank();
+  const int cluster_id = blockIdx.x >> 1;
+  const int num_clusters = gridDim.x >> 1;
+  const int total_units = p.tiles_m * p.tiles_n * p.splits;
+  const int half_bn = p.bn >> 1;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
+    tma_prefetch_desc(&tmap_out);
+    if (EPI == EPI_GELU || EPI == EPI_RESID || EPI == EPI_DGELU) tma_prefetch_desc(&tmap_aux);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(accum_bar, 1);
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full[a], 1);
+      mbar_init(&tmem_empty[a], 2 * EPI_WARPS);
+    }
+    for (int i = 0; i < EPI_WARPS * STG_BUFS; ++i) mbar_init(&aux_bar[i], 1);
     fence_mbar_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, BN);
-    tmem_relinquish();
+    tmem_alloc2(tmem_slot, 2 * ACC_COLS);
+    tmem_relinquish2();
   }
   tc_fence_before();
-  __syncthreads();
+  cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ------------------------------ TMA producer ------------------------------
+    // ------------------------------ TMA producer (both CTAs) ------------------------------
     if (lane == 0) {
-      for (int i = 0; i < num_kb; ++i) {
-        const int s = i % STAGES;
-        const uint32_t ph = (i / STAGES) & 1;
-        mbar_wait(&empty_bar[s], ph ^ 1);
-        uint8_t* sa = smem + s * L::STAGE_BYTES;
-        uint8_t* sb = sa + L::A_BYTES;
-        mbar_expect_tx(&full_bar[s], L::STAGE_BYTES);
-        const int k = (kb0 + i) * BK;
-        // K-major operand : one box {64 k, rows}.
-        // MN-major operand: boxes {64 mn, 64 k}; each 64-wide MN group is its own [64 k][128 B] slab.
-        if (!A_MN) {
-          tma_load_2d(sa, &tmap_a, &full_bar[s], k, m_tile * BM);
-        } else {
+      const uint32_t stage_tx = 2u * static_cast<uint32_t>(A_BYTES + half_bn * BK * 2);
+      uint32_t it = 0;
+      for (int u = cluster_id; u < total_units; u += num_clusters) {
+        const WorkUnit w = decode_unit(p, u);
+        const int m0 = w.m_tile * (2 * BM) + static_cast<int>(rank) * BM;
+        const int n0 = w.n_tile * p.bn + static_cast<int>(rank) * half_bn;
+        for (int i = 0; i < w.nkb; ++i, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          uint8_t* sa = smem + s * STAGE_BYTES;
+          uint8_t* sb = sa + A_BYTES;
+          const uint32_t full_leader = mapa_u32(smem_u32(&full_bar[s]), 0);
+          if (rank == 0) mbar_expect_tx(&full_bar[s], stage_tx);
+          const int k = (w.kb0 + i) * BK;
+          // K-major operand : one box {64 k, rows}.
+          // MN-major operand: boxes {64 mn, 64 k}; each 64-wide MN group is its own [64 k][128 B] slab.
+          if (!A_MN) {
+            tma2_load_2d(sa, &tmap_a, full_leader, k, m0);
+          } else {
 #pragma unroll
-          for (int g = 0; g < BM / 64; ++g)
-            tma_load_2d(sa + g * (BK * 128), &tmap_a, &full_bar[s], m_tile * BM + g * 64, k);
-        }
-        if (!B_MN) {
-          tma_load_2d(sb, &tmap_b, &full_bar[s], k, n_tile * BN);
-        } else {
-#pragma unroll
-          for (int g = 0; g < BN / 64; ++g)
-            tma_load_2d(sb + g * (BK * 128), &tmap_b, &full_bar[s], n_tile * BN + g * 64, k);
+            for (int g = 0; g < BM / 64; ++g) tma2_load_2d(sa + g * (BK * 128), &tmap_a, full_leader, m0 + g * 64, k);
+          }
+          if (!B_MN) {
+            tma2_load_2d(sb, &tmap_b, full_leader, k, n0);
+          } else {
+            for (int g = 0; g < half_bn / 64; ++g)
+              tma2_load_2d(sb + g * (BK * 128), &tmap_b, full_leader, n0 + g * 64, k);
+          }
         }
       }
     }
   } else if (warp == 1) {
-    // ------------------------------ MMA issuer --------------------------------
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
-      for (int i = 0; i < num_kb; ++i) {
-        const int s = i % STAGES;
-        const uint32_t ph = (i / STAGES) & 1;
-        mbar_wait(&full_bar[s], ph);
+    // ------------------------------ MMA issuer (leader CTA, one thread) --------------------
+    if (rank == 0 && lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16(2 * BM, p.bn, A_MN ? 1 : 0, B_MN ? 1 : 0);
+      uint32_t it = 0, tile_it = 0;
+      for (int u = cluster_id; u < total_units; u += num_clusters, ++tile_it) {
+        const WorkUnit w = decode_unit(p, u);
+        const uint32_t acc = tile_it & 1;
+        const uint32_t acc_ph = (tile_it >> 1) & 1;
+        mbar_wait(&tmem_empty[acc], acc_ph ^ 1);      // both CTAs' epilogues have drained this buffer
         tc_fence_after();
-        const uint32_t sa = smem_u32(smem + s * L::STAGE_BYTES);
-        const uint32_t sb = sa + L::A_BYTES;
+        const uint32_t tmem_d = tmem_base + acc * ACC_COLS;
+        for (int i = 0; i < w.nkb; ++i, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
+          const uint32_t sb = sa + A_BYTES;
 #pragma unroll
-        for (int k = 0; k < BK / UMMA_K; ++k) {
-          // K-major, 128B swizzle : 8-row groups are 1024 B apart (SBO); a K step of 16 is 32 B inside the row.
-          // MN-major, 128B swizzle: 64-wide MN groups are BK*128 B apart (LBO), 8-deep K groups 1024 B (SBO);
-          //                         a K step of 16 is 16 rows = 2048 B.
-          const uint64_t da = A_MN ? umma_smem_desc_sw128(sa + k * (UMMA_K * 128), BK * 128, 1024)
-                                   : umma_smem_desc_sw128(sa + k * (UMMA_K * 2), 16, 1024);
-          const uint64_t db = B_MN ? umma_smem_desc_sw128(sb + k * (UMMA_K * 128), BK * 128, 1024)
-                                   : umma_smem_desc_sw128(sb + k * (UMMA_K * 2), 16, 1024);
-          umma_f16(tmem_base, da, db, idesc, (i > 0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            // K-major, 128B swizzle : 8-row groups are 1024 B apart (SBO); a K step of 16 is 32 B inside the row.
+            // MN-major, 128B swizzle: 64-wide MN groups are BK*128 B apart (LBO), 8-deep K groups 1024 B (SBO);
+            //                         a K step of 16 is 16 rows = 2048 B.
+            const uint64_t da = A_MN ? umma_smem_desc_sw128(sa + k * (UMMA_K * 128), BK * 128, 1024)
+                                     : umma_smem_desc_sw128(sa + k * (UMMA_K * 2), 16, 1024);
+            const uint64_t db = B_MN ? umma_smem_desc_sw128(sb + k * (UMMA_K * 128), BK * 128, 1024)
+                                     : umma_smem_desc_sw128(sb + k * (UMMA_K * 2), 16, 1024);
+            umma2_f16(tmem_d, da, db, idesc, (i > 0 || k > 0) ? 1u : 0u);
+          }
+          umma2_commit_mc(&empty_bar[s]);   // frees this smem slot in both CTAs once the MMAs have read it
         }
-        umma_commit(&empty_bar[s]);   // frees the smem slot once these MMAs have read it
+        umma2_commit_mc(&tmem_full[acc]);   // accumulator complete: wakes the epilogue warps of both CTAs
       }
-      umma_commit(accum_bar);         // accumulator complete
     }
   } else {
-    // ------------------------------ epilogue ----------------------------------
-    const int q = warp & 3;                      // TMEM lane quarter this warp may access
-    const int row = m_tile * BM + q * 32 + lane;
-    const bool row_ok = row < p.M;
-    if (num_kb > 0) {
-      mbar_wait(accum_bar, 0);
-      tc_fence_after();
-    }
-#pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
-      const int col0 = n_tile * BN + c * 32;
-      if (col0 >= p.N) break;
-      uint32_t r[32];
-      if (num_kb > 0) {
-        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c * 32, r);
-        tmem_ld_wait();
-      } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) r[j] = 0;
-      }
-      float v[32];
-#pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+    // ------------------------------ epilogue (both CTAs, 8 warps) --------------------------
+    const int ew = warp - 2;
+    const int q = warp & 3;                        // TMEM lane quarter this warp may access
+    const int half = ew >> 2;                      // which chunks of the tile this warp takes
+    constexpr bool OUT_F32 = (EPI == EPI_RESID || EPI == EPI_F32 || EPI == EPI_F32_ATOMIC);
+    constexpr bool HAS_AUX = (EPI == EPI_RESID || EPI == EPI_DGELU);
+    constexpr int CW = OUT_F32 ? 32 : 64;          // columns per staging tile (128 bytes per row)
+    uint8_t* stg = smem + SMEM_RING + ew * (STG_BUFS * STG_BYTES);
+    uint64_t* my_aux_bar = aux_bar + ew * STG_BUFS;
+    const uint32_t tmem_empty_leader0 = mapa_u32(smem_u32(&tmem_empty[0]), 0);
+    const uint32_t tmem_empty_leader1 = mapa_u32(smem_u32(&tmem_empty[1]), 0);
+    const int nchunks = p.bn / CW;
+    const uint32_t sw = static_cast<uint32_t>(lane & 7);
+    uint32_t seq = 0;        // staging-buffer sequence number (continues across tiles)
+    uint32_t aux_seq = 0;    // aux loads issued so far
+    uint32_t tile_it = 0;
 
-      if (EPI != EPI_DGELU && EPI != EPI_F32_ATOMIC) {
-        if (p.bias != nullptr) {
+    // first aux prefetch of the first tile
+    auto issue_aux = [&](const WorkUnit& w, int c) {
+      const uint32_t b = aux_seq & 1;
+      mbar_expect_tx(&my_aux_bar[b], STG_BYTES);
+      tma_load_2d(stg + b * STG_BYTES, &tmap_aux, &my_aux_bar[b], w.n_tile * p.bn + c * CW,
+                  w.m_tile * (2 * BM) + static_cast<int>(rank) * BM + q * 32);
+      ++aux_seq;
+    };
+
+    for (int u = cluster_id; u < total_units; u += num_clusters, ++tile_it) {
+      const WorkUnit w = decode_unit(p, u);
+      const uint32_t acc = tile_it & 1;
+      const uint32_t acc_ph = (tile_it >> 1) & 1;
+      const int row0 = w.m_tile * (2 * BM) + static_cast<int>(rank) * BM + q * 32;
+      const int col_tile = w.n_tile * p.bn;
+      if (HAS_AUX && lane == 0 && half < nchunks) {
+        // the staging buffer the load lands in must have been read out by its previous TMA store
+        bulk_wait_read<0>();
+        issue_aux(w, half);
+      }
+      mbar_wait(&tmem_full[acc], acc_ph);
+      tc_fence_after();
+      if (half >= nchunks) {     // narrow tile: this warp has no chunk, it only releases the accumulator
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(acc ? tmem_empty_leader1 : tmem_empty_leader0);
+      }
+      const uint32_t tmem_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * ACC_COLS;
+
+#pragma unroll 1
+      for (int c = half; c < nchunks; c += 2) {
+        const int col0 = col_tile + c * CW;
+        const bool last = (c + 2 >= nchunks);
+        // ---- accumulator chunk -> registers ----
+        uint32_t r[CW];
+        tmem_ld_32x32(tmem_row + c * CW, *reinterpret_cast<uint32_t(*)[32]>(&r[0]));
+        if (CW == 64) tmem_ld_32x32(tmem_row + c * CW + 32, *reinterpret_cast<uint32_t(*)[32]>(&r[CW - 32]));
+        tmem_ld_wait();
+        if (last) {
+          // all TMEM reads of this tile by this warp are done: hand the buffer back to the MMA issuer
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(acc ? tmem_empty_leader1 : tmem_empty_leader0);
+        }
+        float v[CW];
 #pragma unroll
-          for (int g = 0; g < 8; ++g) {
-            if (col0 + g * 4 + 4 <= p.N) {
+        for (int j = 0; j < CW; ++j) v[j] = __uint_as_float(r[j]);
+        if (EPI != EPI_DGELU && EPI != EPI_F32_ATOMIC && p.bias != nullptr) {
+#pragma unroll
+          for (int g = 0; g < CW / 4; ++g) {
+            if (col0 + g * 4 < p.N) {       // N % 8 == 0, so a group of 4 is all-in or all-out
               const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + g * 4));
               v[g * 4 + 0] += b.x; v[g * 4 + 1] += b.y; v[g * 4 + 2] += b.z; v[g * 4 + 3] += b.w;
             }
           }
         }
-      }
-      if (!row_ok) continue;
-      const size_t off = static_cast<size_t>(row) * p.ldo + col0;
 
-      if (EPI == EPI_BF16 || EPI == EPI_GELU || EPI == EPI_DGELU) {
-        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + off;
+        if (!HAS_AUX) {
+          // ---- plain / GELU / f32 / reduce: registers -> staging tile -> TMA store ----
+          const uint32_t b = seq & 1;
+          if (lane == 0) bulk_wait_read<1>();     // the store that last used this buffer has read it out
+          __syncwarp();
+          const uint32_t sbase = smem_u32(stg + b * STG_BYTES) + lane * 128;
+          if (OUT_F32) {
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          if (col0 + g * 8 + 8 > p.N) break;
-          float x[8];
+            for (int g = 0; g < 8; ++g) {
+              uint4 o;
+              o.x = __float_as_uint(v[g * 4 + 0]); o.y = __float_as_uint(v[g * 4 + 1]);
+              o.z = __float_as_uint(v[g * 4 + 2]); o.w = __float_as_uint(v[g * 4 + 3]);
+              st_shared_v4(sbase + ((static_cast<uint32_t>(g) ^ sw) << 4), o);
+            }
+          } else if (EPI == EPI_GELU) {
+            // one pass: h rounded to bf16 (the reference's fc1 output), gelu(h) -> v, gelu'(h) -> first staging tile
 #pragma unroll
-          for (int j = 0; j < 8; ++j) x[j] = v[g * 8 + j];
-          if (EPI == EPI_DGELU) {
-            const uint4 hv = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.aux) + off + g * 8);
-            const uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w};
+            for (int g = 0; g < 8; ++g) {
+              uint4 o;
+              uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float2 h2 = unpack_bf16x2(hw[j]);
-              x[2 * j] = bf16_round(x[2 * j]) * gelu_erf_grad(h2.x);
-              x[2 * j + 1] = bf16_round(x[2 * j + 1]) * gelu_erf_grad(h2.y);
+              for (int j = 0; j < 4; ++j) {
+                float ga, gpa, gb, gpb;
+                gelu_and_grad(bf16_round(v[g * 8 + 2 * j]), ga, gpa);
+                gelu_and_grad(bf16_round(v[g * 8 + 2 * j + 1]), gb, gpb);
+                ow[j] = pack_bf16x2(gpa, gpb);
+                r[g * 4 + j] = pack_bf16x2(ga, gb);
+              }
+              st_shared_v4(sbase + ((static_cast<uint32_t>(g) ^ sw) << 4), o);
+            }
+          } else {
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+              uint4 o;
+              o.x = pack_bf16x2(v[g * 8 + 0], v[g * 8 + 1]); o.y = pack_bf16x2(v[g * 8 + 2], v[g * 8 + 3]);
+              o.z = pack_bf16x2(v[g * 8 + 4], v[g * 8 + 5]); o.w = pack_bf16x2(v[g * 8 + 6], v[g * 8 + 7]);
+              st_shared_v4(sbase + ((static_cast<uint32_t>(g) ^ sw) << 4), o);
             }
           }
-          uint4 pk;
-          pk.x = pack_bf16x2(x[0], x[1]); pk.y = pack_bf16x2(x[2], x[3]);
-          pk.z = pack_bf16x2(x[4], x[5]); pk.w = pack_bf16x2(x[6], x[7]);
-          *reinterpret_cast<uint4*>(o + g * 8) = pk;
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            if (EPI == EPI_F32_ATOMIC) tma_reduce_add_2d(&tmap_out, stg + b * STG_BYTES, col0, row0);
+            else tma_store_2d(&tmap_out, stg + b * STG_BYTES, col0, row0);
+            bulk_commit();
+          }
+          ++seq;
           if (EPI == EPI_GELU) {
-            const uint32_t hw[4] = {pk.x, pk.y, pk.z, pk.w};
-            uint32_t aw[4];
+            const uint32_t b2 = seq & 1;
+            if (lane == 0) bulk_wait_read<1>();
+            __syncwarp();
+            const uint32_t sbase2 = smem_u32(stg + b2 * STG_BYTES) + lane * 128;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float2 h2 = unpack_bf16x2(hw[j]);
-              aw[j] = pack_bf16x2(gelu_erf(h2.x), gelu_erf(h2.y));
+            for (int g = 0; g < 8; ++g)
+              st_shared_v4(sbase2 + ((static_cast<uint32_t>(g) ^ sw) << 4),
+                           make_uint4(r[g * 4 + 0], r[g * 4 + 1], r[g * 4 + 2], r[g * 4 + 3]));
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(&tmap_aux, stg + b2 * STG_BYTES, col0, row0);
+              bulk_commit();
             }
-            *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out2) + off + g * 8) =
-                make_uint4(aw[0], aw[1], aw[2], aw[3]);
+            ++seq;
           }
-        }
-      } else if (EPI == EPI_RESID) {
-        float* o = reinterpret_cast<float*>(p.out) + off;
-        const float* ri = reinterpret_cast<const float*>(p.aux) + off;
+        } else {
+          // ---- residual / dGELU: the aux tile was TMA-loaded into the staging buffer; combine in place ----
+          const uint32_t b = seq & 1;
+          // prefetch the aux tile of the next chunk (or of the next tile's first chunk) into the other buffer
+          if (lane == 0) {
+            bulk_wait_read<0>();                    // the other buffer's last store has read it out
+            if (!last) {
+              issue_aux(w, c + 2);
+            }
+          }
+          mbar_wait(&my_aux_bar[b], (seq >> 1) & 1);
+          const uint32_t sbase = smem_u32(stg + b * STG_BYTES) + lane * 128;
+          if (EPI == EPI_RESID) {
 #pragma unroll
-        for (int g = 0; g < 8; ++g) {
-          if (col0 + g * 4 + 4 > p.N) break;
-          float4 x = *reinterpret_cast<const float4*>(ri + g * 4);
-          x.x += bf16_round(v[g * 4 + 0]); x.y += bf16_round(v[g * 4 + 1]);
-          x.z += bf16_round(v[g * 4 + 2]); x.w += bf16_round(v[g * 4 + 3]);
-          *reinterpret_cast<float4*>(o + g * 4) = x;
-        }
-      } else if (EPI == EPI_F32) {
-        float* o = reinterpret_cast<float*>(p.out) + off;
+            for (int g = 0; g < 8; ++g) {
+              const uint32_t a = sbase + ((static_cast<uint32_t>(g) ^ sw) << 4);
+              uint4 x = ld_shared_v4(a);
+              x.x = __float_as_uint(__uint_as_float(x.x) + bf16_round(v[g * 4 + 0]));
+              x.y = __float_as_uint(__uint_as_float(x.y) + bf16_round(v[g * 4 + 1]));
+              x.z = __float_as_uint(__uint_as_float(x.z) + bf16_round(v[g * 4 + 2]));
+              x.w = __float_as_uint(__uint_as_float(x.w) + bf16_round(v[g * 4 + 3]));
+              st_shared_v4(a, x);
+            }
+          } else {   // EPI_DGELU
 #pragma unroll
-        for (int g = 0; g < 8; ++g) {
-          if (col0 + g * 4 + 4 > p.N) break;
-          *reinterpret_cast<float4*>(o + g * 4) = make_float4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
-        }
-      } else {  // EPI_F32_ATOMIC
-        float* o = reinterpret_cast<float*>(p.out) + off;
+            for (int g = 0; g < 8; ++g) {
+              const uint32_t a = sbase + ((static_cast<uint32_t>(g) ^ sw) << 4);
+              const uint4 hv = ld_shared_v4(a);
+              const uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w};
+              uint4 o;
+              uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
 #pragma unroll
-        for (int g = 0; g < 8; ++g) {
-          if (col0 + g * 4 + 4 > p.N) break;
-          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o + g * 4), "f"(v[g * 4]),
-                       "f"(v[g * 4 + 1]), "f"(v[g * 4 + 2]), "f"(v[g * 4 + 3])
-                       : "memory");
+              for (int j = 0; j < 4; ++j) {
+                const float2 h2 = unpack_bf16x2(hw[j]);
+                ow[j] = pack_bf16x2(bf16_round(v[g * 8 + 2 * j]) * h2.x, bf16_round(v[g * 8 + 2 * j + 1]) * h2.y);
+              }
+              st_shared_v4(a, o);
+            }
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&tmap_out, stg + b * STG_BYTES, col0, row0);
+            bulk_commit();
+          }
+          ++seq;
         }
       }
     }
+    if (lane == 0) bulk_wait_all();
   }
 
+  __syncwarp();
   tc_fence_before();
-  __syncthreads();
+  cluster_sync_all();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, BN);
+    tmem_dealloc2(tmem_base, 2 * ACC_COLS);
   }
 }
 
@@ -290,10 +515,10 @@ PFN_encodeTiled get_encode_fn() {
 struct MapKey {
   const void* ptr;
   uint64_t inner, outer, ld;
-  uint32_t box_inner, box_outer;
+  uint32_t box_inner, box_outer, elem_bytes;
   bool operator==(const MapKey& o) const {
     return ptr == o.ptr && inner == o.inner && outer == o.outer && ld == o.ld && box_inner == o.box_inner &&
-           box_outer == o.box_outer;
+           box_outer == o.box_outer && elem_bytes == o.elem_bytes;
   }
 };
 struct MapKeyHash {
@@ -301,17 +526,18 @@ struct MapKeyHash {
     size_t h = reinterpret_cast<size_t>(k.ptr);
     h ^= k.inner * 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2);
     h ^= k.outer * 0xC2B2AE3D27D4EB4Full + (h << 6) + (h >> 2);
-    h ^= (k.ld * 31 + k.box_inner * 131 + k.box_outer) + (h << 6) + (h >> 2);
+    h ^= (k.ld * 31 + k.box_inner * 131 + k.box_outer * 7 + k.elem_bytes) + (h << 6) + (h >> 2);
     return h;
   }
 };
 
-// bf16 row-major matrix [outer, inner] with leading dimension ld (elements); 128B-swizzled boxes.
+// Row-major matrix [outer, inner] of bf16 (elem_bytes 2) or f32 (4) with leading dimension ld (elements);
+// 128B-swizzled boxes {box_inner, box_outer}.
 int get_tensor_map(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld,
-                   uint32_t box_inner, uint32_t box_outer) {
+                   uint32_t box_inner, uint32_t box_outer, uint32_t elem_bytes = 2) {
   static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
   static std::mutex mu;
-  MapKey key{ptr, inner, outer, ld, box_inner, box_outer};
+  MapKey key{ptr, inner, outer, ld, box_inner, box_outer, elem_bytes};
   {
     std::lock_guard<std::mutex> lock(mu);
     auto it = cache.find(key);
@@ -325,19 +551,19 @@ int get_tensor_map(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t o
     csm_set_error("cuTensorMapEncodeTiled not available from the driver");
     return CSM_ERR_CUDA;
   }
-  if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0 || (ld * 2) % 16 != 0) {
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0 || (ld * elem_bytes) % 16 != 0) {
     csm_set_error("tensor map: base pointer and row pitch must be 16-byte aligned (ptr=%p ld=%llu)", ptr,
                   (unsigned long long)ld);
     return CSM_ERR_ARG;
   }
   cuuint64_t dims[2] = {inner, outer};
-  cuuint64_t strides[1] = {ld * 2};
+  cuuint64_t strides[1] = {ld * elem_bytes};
   cuuint32_t box[2] = {box_inner, box_outer};
   cuuint32_t estr[2] = {1, 1};
   CUtensorMap m;
-  CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = enc(&m, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                   const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     csm_set_error("cuTensorMapEncodeTiled failed with CUresult %d (inner=%llu outer=%llu ld=%llu box=%ux%u)", (int)r,
                   (unsigned long long)inner, (unsigned long long)outer, (unsigned long long)ld, box_inner, box_outer);
@@ -352,27 +578,105 @@ int get_tensor_map(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t o
   return CSM_OK;
 }
 
-template <int BN, int STAGES, bool A_MN, bool B_MN, int EPI>
-int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int splits, cudaStream_t stream) {
-  using L = SmemLayout<BN, STAGES>;
-  auto kern = gemm_kernel<BN, STAGES, A_MN, B_MN, EPI>;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
+// number of 2-CTA clusters of this kernel that can be co-resident on the device (<= SMs / 2)
+template <typename Kern>
+int max_clusters(Kern kern, int num_sms) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * 74, 1, 1);
+  cfg.blockDim = dim3(GEMM_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = SMEM_TOTAL;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess || n < 1) {
+    cudaGetLastError();
+    n = num_sms > 1 ? num_sms / 2 : 1;
+  }
+  return n;
+}
+
+// BN for a [M, N] output: the k-block time of a 256 x bn cluster tile is bound by the L2 -> SM feed
+// (~ 128 + bn/2 rows per SM), so the cost model is rounds(bn) * (256 + bn).
+int choose_bn(int M, int N, int num_clusters, bool b_mn) {
+  const int tiles_m = csm_cdiv(M, 2 * BM);
+  int best_bn = 256;
+  long long best_cost = -1;
+  const int cands_k[4] = {256, 192, 128, 64};
+  for (int i = 0; i < 4; ++i) {
+    const int bn = cands_k[i];
+    if (b_mn && (bn % 128) != 0) continue;     // MN-major B is loaded in 64-wide groups per CTA
+    const long long tiles = static_cast<long long>(tiles_m) * csm_cdiv(N, bn);
+    const long long rounds = (tiles + num_clusters - 1) / num_clusters;
+    const long long cost = rounds * (256 + bn);
+    if (best_cost < 0 || cost < best_cost) {
+      best_cost = cost;
+      best_bn = bn;
+    }
+  }
+  return best_bn;
+}
+
+template <bool A_MN, bool B_MN, int EPI>
+int launch_gemm(const void* a, uint64_t a_inner, uint64_t a_outer, const void* b, uint64_t b_inner, uint64_t b_outer,
+                void* out, const void* aux, const float* bias, int M, int N, int red_len, int num_sms,
+                cudaStream_t stream) {
+  auto kern = gemm_kernel<A_MN, B_MN, EPI>;
+  static int clusters = 0;
+  if (clusters == 0) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL);
     if (e != cudaSuccess) {
-      csm_set_error("gemm: cudaFuncSetAttribute(smem=%d) failed: %s", L::TOTAL, cudaGetErrorString(e));
+      csm_set_error("gemm: cudaFuncSetAttribute(smem=%d) failed: %s", SMEM_TOTAL, cudaGetErrorString(e));
       return CSM_ERR_CUDA;
     }
-    configured = true;
+    clusters = max_clusters(kern, num_sms > 0 ? num_sms : 148);
   }
-  dim3 grid(csm_cdiv(p.N, BN), csm_cdiv(p.M, BM), splits);
-  kern<<<grid, GEMM_THREADS, L::TOTAL, stream>>>(ta, tb, p);
+  constexpr bool OUT_F32 = (EPI == EPI_RESID || EPI == EPI_F32 || EPI == EPI_F32_ATOMIC);
+  GemmParams p{};
+  p.M = M; p.N = N;
+  p.num_kb = csm_cdiv(red_len, BK);
+  p.bias = bias;
+  p.tiles_m = csm_cdiv(M, 2 * BM);
+  if (EPI == EPI_F32_ATOMIC) {
+    // wgrad: few output tiles, long reduction -> split the reduction so that every cluster has work
+    p.bn = (N > 128 || B_MN) ? (N > 128 ? 256 : 128) : 64;
+    if (B_MN && p.bn < 128) p.bn = 128;
+    p.tiles_n = csm_cdiv(N, p.bn);
+    const int tiles = p.tiles_m * p.tiles_n;
+    int splits = (clusters + tiles - 1) / tiles;
+    int max_splits = p.num_kb / 4;               // keep >= 4 k-blocks per unit
+    if (max_splits < 1) max_splits = 1;
+    if (splits > max_splits) splits = max_splits;
+    if (splits < 1) splits = 1;
+    p.kb_per_split = csm_cdiv(p.num_kb, splits);
+    p.splits = csm_cdiv(p.num_kb, p.kb_per_split);
+  } else {
+    p.bn = choose_bn(M, N, clusters, B_MN);
+    p.tiles_n = csm_cdiv(N, p.bn);
+    p.kb_per_split = p.num_kb;
+    p.splits = 1;
+  }
+  CUtensorMap ta, tb, to, tx;
+  int rc;
+  // A: K-major [M, red] box {64, 128};  MN-major [red, M] box {64, 64}
+  rc = A_MN ? get_tensor_map(&ta, a, a_inner, a_outer, a_inner, 64, BK) : get_tensor_map(&ta, a, a_inner, a_outer, a_inner, BK, BM);
+  if (rc) return rc;
+  rc = B_MN ? get_tensor_map(&tb, b, b_inner, b_outer, b_inner, 64, BK)
+            : get_tensor_map(&tb, b, b_inner, b_outer, b_inner, BK, p.bn / 2);
+  if (rc) return rc;
+  rc = get_tensor_map(&to, out, N, M, N, OUT_F32 ? 32 : 64, 32, OUT_F32 ? 4 : 2);
+  if (rc) return rc;
+  tx = to;
+  if (EPI == EPI_GELU || EPI == EPI_DGELU) {
+    rc = get_tensor_map(&tx, aux, N, M, N, 64, 32, 2);
+    if (rc) return rc;
+  } else if (EPI == EPI_RESID) {
+    rc = get_tensor_map(&tx, aux, N, M, N, 32, 32, 4);
+    if (rc) return rc;
+  }
+  const int units = p.tiles_m * p.tiles_n * p.splits;
+  const int grid = 2 * (units < clusters ? units : clusters);
+  kern<<<grid, GEMM_THREADS, SMEM_TOTAL, stream>>>(ta, tb, to, tx, p);
   CSM_CHECK_LAUNCH("gemm_tcgen05");
   return CSM_OK;
 }
-
-constexpr int kBN = 128;
-constexpr int kStages = 3;
 
 }  // namespace
 
@@ -383,24 +687,17 @@ extern "C" int csm_linear_fwd(const void* x_bf16, const void* w_bf16, const floa
                               int M, int N, int K, int epilogue, cudaStream_t stream) {
   CSM_CHECK_ARG(M > 0 && N > 0 && K > 0, "csm_linear_fwd: empty problem M=%d N=%d K=%d", M, N, K);
   CSM_CHECK_ARG(N % 8 == 0 && K % 8 == 0, "csm_linear_fwd: N and K must be multiples of 8 (N=%d K=%d)", N, K);
-  CUtensorMap ta, tb;
-  int rc = get_tensor_map(&ta, x_bf16, K, M, K, BK, BM);
-  if (rc) return rc;
-  rc = get_tensor_map(&tb, w_bf16, K, N, K, BK, kBN);
-  if (rc) return rc;
-  GemmParams p{};
-  p.M = M; p.N = N; p.K = K;
-  p.kb_per_split = csm_cdiv(K, BK);
-  p.out = out; p.out2 = aux; p.bias = bias; p.aux = aux; p.ldo = N;
   switch (epilogue) {
-    case EPI_BF16: return launch_gemm<kBN, kStages, false, false, EPI_BF16>(ta, tb, p, 1, stream);
+    case EPI_BF16:
+      return launch_gemm<false, false, EPI_BF16>(x_bf16, K, M, w_bf16, K, N, out, nullptr, bias, M, N, K, 0, stream);
     case EPI_GELU:
       CSM_CHECK_ARG(aux != nullptr, "csm_linear_fwd: GELU epilogue needs aux (activation output)");
-      return launch_gemm<kBN, kStages, false, false, EPI_GELU>(ta, tb, p, 1, stream);
+      return launch_gemm<false, false, EPI_GELU>(x_bf16, K, M, w_bf16, K, N, out, aux, bias, M, N, K, 0, stream);
     case EPI_RESID:
       CSM_CHECK_ARG(aux != nullptr, "csm_linear_fwd: residual epilogue needs aux (f32 residual input)");
-      return launch_gemm<kBN, kStages, false, false, EPI_RESID>(ta, tb, p, 1, stream);
-    case EPI_F32: return launch_gemm<kBN, kStages, false, false, EPI_F32>(ta, tb, p, 1, stream);
+      return launch_gemm<false, false, EPI_RESID>(x_bf16, K, M, w_bf16, K, N, out, aux, bias, M, N, K, 0, stream);
+    case EPI_F32:
+      return launch_gemm<false, false, EPI_F32>(x_bf16, K, M, w_bf16, K, N, out, nullptr, bias, M, N, K, 0, stream);
     default:
       csm_set_error("csm_linear_fwd: unsupported epilogue %d", epilogue);
       return CSM_ERR_ARG;
@@ -412,21 +709,14 @@ extern "C" int csm_linear_dgrad(const void* dy_bf16, const void* w_bf16, void* d
   // dX[M,K] = dY[M,N] . W[N,K]; reduction over N, W consumed MN-major straight from its [N,K] storage.
   CSM_CHECK_ARG(M > 0 && N > 0 && K > 0, "csm_linear_dgrad: empty problem M=%d N=%d K=%d", M, N, K);
   CSM_CHECK_ARG(N % 8 == 0 && K % 8 == 0, "csm_linear_dgrad: N and K must be multiples of 8 (N=%d K=%d)", N, K);
-  CUtensorMap ta, tb;
-  int rc = get_tensor_map(&ta, dy_bf16, N, M, N, BK, BM);
-  if (rc) return rc;
-  rc = get_tensor_map(&tb, w_bf16, K, N, K, 64, BK);
-  if (rc) return rc;
-  GemmParams p{};
-  p.M = M; p.N = K; p.K = N;
-  p.kb_per_split = csm_cdiv(N, BK);
-  p.out = dx; p.aux = aux; p.ldo = K;
   switch (epilogue) {
-    case EPI_BF16: return launch_gemm<kBN, kStages, false, true, EPI_BF16>(ta, tb, p, 1, stream);
+    case EPI_BF16:
+      return launch_gemm<false, true, EPI_BF16>(dy_bf16, N, M, w_bf16, K, N, dx, nullptr, nullptr, M, K, N, 0, stream);
     case EPI_DGELU:
       CSM_CHECK_ARG(aux != nullptr, "csm_linear_dgrad: dGELU epilogue needs aux (bf16 pre-activation)");
-      return launch_gemm<kBN, kStages, false, true, EPI_DGELU>(ta, tb, p, 1, stream);
-    case EPI_F32: return launch_gemm<kBN, kStages, false, true, EPI_F32>(ta, tb, p, 1, stream);
+      return launch_gemm<false, true, EPI_DGELU>(dy_bf16, N, M, w_bf16, K, N, dx, aux, nullptr, M, K, N, 0, stream);
+    case EPI_F32:
+      return launch_gemm<false, true, EPI_F32>(dy_bf16, N, M, w_bf16, K, N, dx, nullptr, nullptr, M, K, N, 0, stream);
     default:
       csm_set_error("csm_linear_dgrad: unsupported epilogue %d", epilogue);
       return CSM_ERR_ARG;
@@ -437,23 +727,7 @@ extern "C" int csm_linear_wgrad(const void* dy_bf16, const void* x_bf16, float* 
                                 int num_sms, cudaStream_t stream) {
   CSM_CHECK_ARG(rows > 0 && N > 0 && K > 0, "csm_linear_wgrad: empty problem rows=%d N=%d K=%d", rows, N, K);
   CSM_CHECK_ARG(N % 8 == 0 && K % 8 == 0, "csm_linear_wgrad: N and K must be multiples of 8 (N=%d K=%d)", N, K);
-  CUtensorMap ta, tb;
-  int rc = get_tensor_map(&ta, dy_bf16, N, rows, N, 64, BK);
-  if (rc) return rc;
-  rc = get_tensor_map(&tb, x_bf16, K, rows, K, 64, BK);
-  if (rc) return rc;
-  GemmParams p{};
-  p.M = N; p.N = K; p.K = rows;
-  const int tiles = csm_cdiv(N, BM) * csm_cdiv(K, kBN);
-  const int num_kb = csm_cdiv(rows, BK);
-  if (num_sms <= 0) num_sms = 148;
-  int splits = (2 * num_sms + tiles - 1) / tiles;     // two co-resident CTAs per SM
-  splits = splits < 1 ? 1 : splits;
-  int max_splits = num_kb / 4;                        // keep >= 4 k-blocks per split
-  if (max_splits < 1) max_splits = 1;
-  if (splits > max_splits) splits = max_splits;
-  p.kb_per_split = csm_cdiv(num_kb, splits);
-  splits = csm_cdiv(num_kb, p.kb_per_split);
-  p.out = dw; p.ldo = K;
-  return launch_gemm<kBN, kStages, true, true, EPI_F32_ATOMIC>(ta, tb, p, splits, stream);
+  // dW[N,K] : GEMM "M" = N, "N" = K, reduction over the token rows; both operands MN-major
+  return launch_gemm<true, true, EPI_F32_ATOMIC>(dy_bf16, N, rows, x_bf16, K, rows, dw, nullptr, nullptr, N, K, rows,
+                                                 num_sms, stream);
 }

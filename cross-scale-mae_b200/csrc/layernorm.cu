@@ -8,6 +8,11 @@ using namespace csm;
 
 constexpr int LN_MAX_VEC = 8;  // float4 per lane -> D <= 1024
 
+__device__ __forceinline__ void red_add_v4(float* addr, const float4 v) {   // 16-byte aligned address
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+               : "memory");
+}
+
 // One warp per row.  Statistics in fp32 (two-pass: mean, then centred variance), output rounded once.
 __global__ void layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                                      const float* __restrict__ beta, __nv_bfloat16* __restrict__ out_bf16,
@@ -67,23 +72,157 @@ __global__ void layernorm_fwd_kernel(const float* __restrict__ x, const float* _
 
 // dy = float(dy_bf16) + dy2_f32 (either may be null).  dx_ln = rstd * (g - mean(g) - xhat * mean(g * xhat)),
 // g = dy * gamma.  dres_out = (dres_in ? dres_in : 0) + dx_ln, plus a bf16 copy for the following GEMMs.
-// dgamma / dbeta: every lane owns fixed columns, accumulates over the rows its warp visits, then the
-// CTA reduces through shared memory and issues one atomicAdd per column.
+// Column sums accumulated on the way: dgamma += sum_r dy*xhat, dbeta += sum_r dy and (optional)
+// dcolsum += sum_r bf16(dres_out) -- the bias gradient of the Linear whose output gradient dres_bf16 is
+// (attn.proj / mlp.fc2: their dY IS the residual-stream gradient), so no separate column-sum pass.
+//
+// Layout: a row is spread over TPR = D/4 threads (one float4 each), a CTA handles blockDim/TPR rows per
+// iteration; the two row statistics cross the row's warps through shared memory (one __syncthreads per
+// iteration, double-buffered).  Every thread owns 4 fixed columns, so the three column sums cost 12
+// registers and the kernel runs at full occupancy (HBM-latency hiding by many resident rows).
+__host__ __device__ constexpr int ln_tile_threads(int tpr) { return (tpr == 96 || tpr == 192) ? 384 : (tpr == 256 ? 512 : 256); }
+
+template <int TPR>
+__global__ void __launch_bounds__(ln_tile_threads(TPR))
+layernorm_bwd_tile_kernel(const __nv_bfloat16* __restrict__ dy_bf16, const float* __restrict__ dy2,
+                          const float* __restrict__ x, const float* __restrict__ mean_in,
+                          const float* __restrict__ rstd_in, const float* __restrict__ gamma,
+                          const float* __restrict__ dres_in, float* __restrict__ dres_out,
+                          __nv_bfloat16* __restrict__ dres_bf16, float* __restrict__ dgamma,
+                          float* __restrict__ dbeta, float* __restrict__ dcolsum, int rows) {
+  constexpr int D = TPR * 4;
+  constexpr int WPR = TPR / 32;                       // warps per row
+  constexpr int THREADS = ln_tile_threads(TPR);
+  constexpr int RPI = THREADS / TPR;                  // rows per iteration
+  static_assert(THREADS % TPR == 0 && TPR % 32 == 0, "a row must be a whole number of warps");
+  __shared__ float2 s_part[2][RPI][WPR];
+  __shared__ float4 s_col[3][RPI > 1 ? RPI - 1 : 1][TPR];
+  const int rsub = threadIdx.x / TPR;
+  const int ct = threadIdx.x % TPR;
+  const int wir = ct >> 5;                            // warp index inside the row
+  const int lane = threadIdx.x & 31;
+  const int col = ct * 4;
+  const float4 gm = *reinterpret_cast<const float4*>(gamma + col);
+  float4 ag = make_float4(0.f, 0.f, 0.f, 0.f), ab = ag, ac = ag;
+
+  struct RowIn {
+    float4 xv, d, rin;
+    float mean, rstd;
+  };
+  auto load_row = [&](int row) {
+    RowIn r;
+    r.xv = make_float4(0.f, 0.f, 0.f, 0.f);
+    r.d = r.xv;
+    r.rin = r.xv;
+    r.mean = 0.f;
+    r.rstd = 0.f;
+    if (row < rows) {
+      const size_t base = static_cast<size_t>(row) * D + col;
+      r.xv = *reinterpret_cast<const float4*>(x + base);
+      if (dy_bf16 != nullptr) {
+        const uint2 ev = *reinterpret_cast<const uint2*>(dy_bf16 + base);
+        const float2 e0 = unpack_bf16x2(ev.x), e1 = unpack_bf16x2(ev.y);
+        r.d = make_float4(e0.x, e0.y, e1.x, e1.y);
+      }
+      if (dy2 != nullptr) {
+        const float4 d2 = *reinterpret_cast<const float4*>(dy2 + base);
+        r.d.x += d2.x; r.d.y += d2.y; r.d.z += d2.z; r.d.w += d2.w;
+      }
+      if (dres_in != nullptr) r.rin = *reinterpret_cast<const float4*>(dres_in + base);
+      r.mean = mean_in[row];
+      r.rstd = rstd_in[row];
+    }
+    return r;
+  };
+
+  int buf = 0;
+  const int step = gridDim.x * RPI;
+  int row = blockIdx.x * RPI + rsub;
+  RowIn cur = load_row(row);
+  for (int row0 = blockIdx.x * RPI; row0 < rows; row0 += step, row += step, buf ^= 1) {
+    // software pipeline: the next row's loads are in flight while this row is reduced and written
+    const RowIn nxt = load_row(row0 + step < rows ? row + step : rows);
+    const bool valid = row < rows;
+    const float4 xv = cur.xv, d = cur.d, rin = cur.rin;
+    const float mean = cur.mean, rstd = cur.rstd;
+    const float4 xh = make_float4((xv.x - mean) * rstd, (xv.y - mean) * rstd, (xv.z - mean) * rstd,
+                                  (xv.w - mean) * rstd);
+    const float4 g = make_float4(d.x * gm.x, d.y * gm.y, d.z * gm.z, d.w * gm.w);
+    float c1 = g.x + g.y + g.z + g.w;
+    float c2 = g.x * xh.x + g.y * xh.y + g.z * xh.z + g.w * xh.w;
+    c1 = warp_sum(c1);
+    c2 = warp_sum(c2);
+    if (lane == 0) s_part[buf][rsub][wir] = make_float2(c1, c2);
+    __syncthreads();
+    c1 = 0.f; c2 = 0.f;
+#pragma unroll
+    for (int w = 0; w < WPR; ++w) {
+      const float2 pr = s_part[buf][rsub][w];
+      c1 += pr.x; c2 += pr.y;
+    }
+    c1 *= (1.0f / D);
+    c2 *= (1.0f / D);
+    if (valid) {
+      const size_t base = static_cast<size_t>(row) * D + col;
+      float4 o;
+      o.x = rstd * (g.x - c1 - xh.x * c2) + rin.x;
+      o.y = rstd * (g.y - c1 - xh.y * c2) + rin.y;
+      o.z = rstd * (g.z - c1 - xh.z * c2) + rin.z;
+      o.w = rstd * (g.w - c1 - xh.w * c2) + rin.w;
+      *reinterpret_cast<float4*>(dres_out + base) = o;
+      uint2 pk;
+      pk.x = pack_bf16x2(o.x, o.y);
+      pk.y = pack_bf16x2(o.z, o.w);
+      if (dres_bf16 != nullptr) *reinterpret_cast<uint2*>(dres_bf16 + base) = pk;
+      const float2 r0 = unpack_bf16x2(pk.x), r1 = unpack_bf16x2(pk.y);
+      ac.x += r0.x; ac.y += r0.y; ac.z += r1.x; ac.w += r1.y;
+      ag.x += d.x * xh.x; ag.y += d.y * xh.y; ag.z += d.z * xh.z; ag.w += d.w * xh.w;
+      ab.x += d.x; ab.y += d.y; ab.z += d.z; ab.w += d.w;
+    }
+    cur = nxt;
+  }
+  // fold the RPI row slots, then one vector atomic per thread and sum
+  if (RPI > 1) {
+    if (rsub > 0) {
+      s_col[0][rsub - 1][ct] = ag;
+      s_col[1][rsub - 1][ct] = ab;
+      s_col[2][rsub - 1][ct] = ac;
+    }
+    __syncthreads();
+    if (rsub == 0) {
+#pragma unroll
+      for (int r = 0; r < RPI - 1; ++r) {
+        const float4 a = s_col[0][r][ct], b = s_col[1][r][ct], c = s_col[2][r][ct];
+        ag.x += a.x; ag.y += a.y; ag.z += a.z; ag.w += a.w;
+        ab.x += b.x; ab.y += b.y; ab.z += b.z; ab.w += b.w;
+        ac.x += c.x; ac.y += c.y; ac.z += c.z; ac.w += c.w;
+      }
+    }
+  }
+  if (rsub == 0) {
+    red_add_v4(dgamma + col, ag);
+    red_add_v4(dbeta + col, ab);
+    if (dcolsum != nullptr) red_add_v4(dcolsum + col, ac);
+  }
+}
+
+// Generic-D fallback (D not a multiple of 128, D <= 1024): one warp per row, register-resident row.
 __global__ void layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy_bf16, const float* __restrict__ dy2,
                                      const float* __restrict__ x, const float* __restrict__ mean_in,
                                      const float* __restrict__ rstd_in, const float* __restrict__ gamma,
                                      const float* __restrict__ dres_in, float* __restrict__ dres_out,
                                      __nv_bfloat16* __restrict__ dres_bf16, float* __restrict__ dgamma,
-                                     float* __restrict__ dbeta, int rows, int D) {
-  extern __shared__ float s_red[];  // [2][warps][D]
+                                     float* __restrict__ dbeta, float* __restrict__ dcolsum, int rows, int D) {
+  extern __shared__ float s_red[];  // [3][warps][D]
   const int warps = blockDim.x >> 5;
   const int w = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  float4 ag[LN_MAX_VEC], ab[LN_MAX_VEC];
+  float4 ag[LN_MAX_VEC], ab[LN_MAX_VEC], ac[LN_MAX_VEC];
 #pragma unroll
   for (int k = 0; k < LN_MAX_VEC; ++k) {
     ag[k] = make_float4(0.f, 0.f, 0.f, 0.f);
     ab[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    ac[k] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
   for (int row = blockIdx.x * warps + w; row < rows; row += gridDim.x * warps) {
     const size_t base = static_cast<size_t>(row) * D;
@@ -130,34 +269,38 @@ __global__ void layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy_bf16, 
           o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
         }
         *reinterpret_cast<float4*>(dres_out + base + i) = o;
-        if (dres_bf16 != nullptr) {
-          uint2 pk;
-          pk.x = pack_bf16x2(o.x, o.y);
-          pk.y = pack_bf16x2(o.z, o.w);
-          *reinterpret_cast<uint2*>(dres_bf16 + base + i) = pk;
-        }
+        uint2 pk;
+        pk.x = pack_bf16x2(o.x, o.y);
+        pk.y = pack_bf16x2(o.z, o.w);
+        if (dres_bf16 != nullptr) *reinterpret_cast<uint2*>(dres_bf16 + base + i) = pk;
+        const float2 r0 = unpack_bf16x2(pk.x), r1 = unpack_bf16x2(pk.y);
+        ac[k].x += r0.x; ac[k].y += r0.y; ac[k].z += r1.x; ac[k].w += r1.y;
       }
     }
   }
   float* sg = s_red;
   float* sb = s_red + warps * D;
+  float* sc = s_red + 2 * warps * D;
 #pragma unroll
   for (int k = 0; k < LN_MAX_VEC; ++k) {
     const int i = (k * 32 + lane) * 4;
     if (i < D) {
       *reinterpret_cast<float4*>(sg + w * D + i) = ag[k];
       *reinterpret_cast<float4*>(sb + w * D + i) = ab[k];
+      *reinterpret_cast<float4*>(sc + w * D + i) = ac[k];
     }
   }
   __syncthreads();
   for (int i = threadIdx.x; i < D; i += blockDim.x) {
-    float a = 0.f, b = 0.f;
+    float a = 0.f, b = 0.f, c = 0.f;
     for (int ww = 0; ww < warps; ++ww) {
       a += sg[ww * D + i];
       b += sb[ww * D + i];
+      c += sc[ww * D + i];
     }
     atomicAdd(dgamma + i, a);
     atomicAdd(dbeta + i, b);
+    if (dcolsum != nullptr) atomicAdd(dcolsum + i, c);
   }
 }
 
@@ -171,15 +314,24 @@ __global__ void colsum_bf16_kernel(const __nv_bfloat16* __restrict__ dy, float* 
 #pragma unroll
   for (int j = 0; j < 8; ++j) acc[j] = 0.f;
   if (col < N) {
-    for (int r = blockIdx.y * 8 + ty; r < rows; r += gridDim.y * 8) {
-      if (skip_period > 0 && (r % skip_period) == 0) continue;
-      const uint4 v = *reinterpret_cast<const uint4*>(dy + static_cast<size_t>(r) * N + col);
-      const uint32_t wv[4] = {v.x, v.y, v.z, v.w};
+    const int stride = gridDim.y * 8;
+    for (int r0 = blockIdx.y * 8 + ty; r0 < rows; r0 += 4 * stride) {
+      uint4 v[4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float2 f = unpack_bf16x2(wv[j]);
-        acc[2 * j] += f.x;
-        acc[2 * j + 1] += f.y;
+      for (int u = 0; u < 4; ++u) {     // four independent 16-byte loads in flight per thread
+        const int r = r0 + u * stride;
+        const bool ok = r < rows && !(skip_period > 0 && (r % skip_period) == 0);
+        v[u] = ok ? *reinterpret_cast<const uint4*>(dy + static_cast<size_t>(r) * N + col) : make_uint4(0, 0, 0, 0);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const uint32_t wv[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = unpack_bf16x2(wv[j]);
+          acc[2 * j] += f.x;
+          acc[2 * j + 1] += f.y;
+        }
       }
     }
   }
@@ -249,28 +401,64 @@ extern "C" int csm_layernorm_fwd(const float* x, const float* gamma, const float
   return CSM_OK;
 }
 
+template <int TPR>
+void launch_ln_bwd_tile(const void* dy_bf16, const float* dy2_f32, const float* x, const float* mean, const float* rstd,
+                        const float* gamma, const float* dres_in, float* dres_out, void* dres_bf16, float* dgamma,
+                        float* dbeta, float* dcolsum, int rows, int num_sms, cudaStream_t stream) {
+  constexpr int THREADS = ln_tile_threads(TPR);
+  constexpr int RPI = THREADS / TPR;
+  static int ctas_per_sm = 0;
+  if (ctas_per_sm == 0) {
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, layernorm_bwd_tile_kernel<TPR>, THREADS, 0) != cudaSuccess ||
+        occ < 1)
+      occ = 1;
+    ctas_per_sm = occ;
+  }
+  int grid = csm_cdiv(rows, RPI);
+  const int cap = num_sms * ctas_per_sm;               // exactly one resident wave
+  if (grid > cap) grid = cap;
+  layernorm_bwd_tile_kernel<TPR><<<grid, THREADS, 0, stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(dy_bf16), dy2_f32, x, mean, rstd, gamma, dres_in, dres_out,
+      reinterpret_cast<__nv_bfloat16*>(dres_bf16), dgamma, dbeta, dcolsum, rows);
+}
+
 extern "C" int csm_layernorm_bwd(const void* dy_bf16, const float* dy2_f32, const float* x, const float* mean,
                                  const float* rstd, const float* gamma, const float* dres_in, float* dres_out,
-                                 void* dres_bf16, float* dgamma, float* dbeta, int rows, int D, int num_sms,
-                                 cudaStream_t stream) {
+                                 void* dres_bf16, float* dgamma, float* dbeta, float* dcolsum, int rows, int D,
+                                 int num_sms, cudaStream_t stream) {
   CSM_CHECK_ARG(rows > 0 && D > 0 && D % 4 == 0 && D <= LN_MAX_VEC * 128,
                 "csm_layernorm_bwd: D must be a multiple of 4 and <= %d (rows=%d D=%d)", LN_MAX_VEC * 128, rows, D);
   CSM_CHECK_ARG(dy_bf16 != nullptr || dy2_f32 != nullptr, "csm_layernorm_bwd: no incoming gradient");
-  const int wpb = 8;
   if (num_sms <= 0) num_sms = 148;
-  int grid = csm_cdiv(rows, wpb);
-  if (grid > num_sms * 2) grid = num_sms * 2;
-  const size_t smem = static_cast<size_t>(2) * wpb * D * sizeof(float);
-  static bool configured = false;
-  if (!configured) {
-    cudaFuncSetAttribute(layernorm_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         2 * wpb * LN_MAX_VEC * 128 * (int)sizeof(float));
-    configured = true;
+#define CSM_LN_TILE(TPR)                                                                                         \
+  launch_ln_bwd_tile<TPR>(dy_bf16, dy2_f32, x, mean, rstd, gamma, dres_in, dres_out, dres_bf16, dgamma, dbeta, \
+                          dcolsum, rows, num_sms, stream)
+  switch (D) {
+    case 128: CSM_LN_TILE(32); break;
+    case 256: CSM_LN_TILE(64); break;
+    case 384: CSM_LN_TILE(96); break;
+    case 512: CSM_LN_TILE(128); break;
+    case 768: CSM_LN_TILE(192); break;
+    case 1024: CSM_LN_TILE(256); break;
+    default: {
+      const int wpb = 8;
+      int grid = csm_cdiv(rows, wpb);
+      if (grid > num_sms * 2) grid = num_sms * 2;
+      const size_t smem = static_cast<size_t>(3) * wpb * D * sizeof(float);
+      static bool configured = false;
+      if (!configured) {
+        cudaFuncSetAttribute(layernorm_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             3 * wpb * LN_MAX_VEC * 128 * (int)sizeof(float));
+        configured = true;
+      }
+      layernorm_bwd_kernel<<<grid, wpb * 32, smem, stream>>>(reinterpret_cast<const __nv_bfloat16*>(dy_bf16), dy2_f32,
+                                                             x, mean, rstd, gamma, dres_in, dres_out,
+                                                             reinterpret_cast<__nv_bfloat16*>(dres_bf16), dgamma,
+                                                             dbeta, dcolsum, rows, D);
+    }
   }
-  layernorm_bwd_kernel<<<grid, wpb * 32, smem, stream>>>(reinterpret_cast<const __nv_bfloat16*>(dy_bf16), dy2_f32, x,
-                                                         mean, rstd, gamma, dres_in, dres_out,
-                                                         reinterpret_cast<__nv_bfloat16*>(dres_bf16), dgamma, dbeta,
-                                                         rows, D);
+#undef CSM_LN_TILE
   CSM_CHECK_LAUNCH("layernorm_bwd");
   return CSM_OK;
 }

@@ -81,9 +81,11 @@ int csm_cls_grad(const float* dx, float* d_cls, int nimg, int Se, int D, csm_str
 /* ---- LayerNorm (eps 1e-6, MAE_ViT_Baseline.py:43-45) and casts -------------------------------- */
 int csm_layernorm_fwd(const float* x, const float* gamma, const float* beta, void* out_bf16, float* out_f32,
                       float* mean, float* rstd, int rows, int D, float eps, csm_stream_t stream);
+/* dres_out = dres_in + LN'(dy_bf16 + dy2_f32); dgamma/dbeta accumulate; dcolsum (nullable) accumulates the column
+ * sums of the bf16 copy dres_bf16 = the bias gradient of the Linear (attn.proj / mlp.fc2) whose dY it is */
 int csm_layernorm_bwd(const void* dy_bf16, const float* dy2_f32, const float* x, const float* mean, const float* rstd,
                       const float* gamma, const float* dres_in, float* dres_out, void* dres_bf16, float* dgamma,
-                      float* dbeta, int rows, int D, int num_sms, csm_stream_t stream);
+                      float* dbeta, float* dcolsum, int rows, int D, int num_sms, csm_stream_t stream);
 int csm_cast_multi(const void* table_dev, int num_tensors, int blocks_per_tensor, csm_stream_t stream);
 int csm_cast_f32_bf16(const float* src, void* dst_bf16, long long n, csm_stream_t stream);
 

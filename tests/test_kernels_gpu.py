@@ -197,7 +197,7 @@ def test_encoder_out_grad_and_cls(nat):
 
 
 # ------------------------------------------------------------------------------------------------ LayerNorm
-@pytest.mark.parametrize("rows,D", [(3200, 768), (1000, 512), (300, 1024), (77, 64)])
+@pytest.mark.parametrize("rows,D", [(3200, 768), (1000, 512), (300, 1024), (77, 64), (25216, 512), (131, 128), (3, 384)])
 def test_layernorm_fwd_bwd(nat, rows, D):
     x, g, b = rnd(rows, D, scale=2.0), 1 + 0.1 * rnd(D), 0.1 * rnd(D, seed=3)
     o16 = torch.empty(rows, D, device="cuda", dtype=bf16)
@@ -211,16 +211,19 @@ def test_layernorm_fwd_bwd(nat, rows, D):
     dres = torch.empty(rows, D, device="cuda")
     dres16 = torch.empty(rows, D, device="cuda", dtype=bf16)
     dg, db = torch.zeros(D, device="cuda"), torch.zeros(D, device="cuda")
-    nat.call("csm_layernorm_bwd", dy16, dy2, x, mean, rstd, g, dres_in, dres, dres16, dg, db, rows, D, 148)
+    dcs = torch.zeros(D, device="cuda")
+    nat.call("csm_layernorm_bwd", dy16, dy2, x, mean, rstd, g, dres_in, dres, dres16, dg, db, dcs, rows, D, 148)
     xl, gl, bl = x.clone().requires_grad_(True), g.clone().requires_grad_(True), b.clone().requires_grad_(True)
     F.layer_norm(xl, (D,), gl, bl, 1e-6).backward(dy16.float() + dy2)
     close(dres, dres_in + xl.grad, 1e-4, 1e-4, "LN bwd dx")
     assert torch.equal(dres16, dres.to(bf16))
     close(dg, gl.grad, 1e-4, 1e-3 * math.sqrt(rows / 100), "LN dgamma")
     close(db, bl.grad, 1e-4, 1e-3 * math.sqrt(rows / 100), "LN dbeta")
+    # fused bias gradient of the Linear whose dY is dres16: column sums of the bf16 copy
+    close(dcs, dres16.float().sum(0), 1e-4, 1e-3 * math.sqrt(rows / 100), "LN bwd fused column sum")
     # in-place residual-gradient update + bf16-only incoming gradient
     d2 = dres_in.clone()
-    nat.call("csm_layernorm_bwd", dy16, None, x, mean, rstd, g, d2, d2, dres16, dg, db, rows, D, 148)
+    nat.call("csm_layernorm_bwd", dy16, None, x, mean, rstd, g, d2, d2, dres16, dg, db, None, rows, D, 148)
     xl.grad = None
     F.layer_norm(xl, (D,), g, b, 1e-6).backward(dy16.float())
     close(d2, dres_in + xl.grad, 1e-4, 1e-4, "LN bwd in place")

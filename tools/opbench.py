@@ -161,7 +161,7 @@ def main():
             dres = rnd(rows, Dm, dt=f32)
             dres16 = torch.empty(rows, Dm, device=dev, dtype=bf16)
             dg_, db_ = torch.zeros(Dm, device=dev), torch.zeros(Dm, device=dev)
-            us = timeit(lambda: nat.call("csm_layernorm_bwd", dy, None, x, mean, rstd, gam, dres, dres, dres16, dg_, db_,
+            us = timeit(lambda: nat.call("csm_layernorm_bwd", dy, None, x, mean, rstd, gam, dres, dres, dres16, dg_, db_, dg_,
                                          rows, Dm, nsm), args.iters, flush)
             report("ln", f"layernorm_bwd {name}", [rows, Dm], us, nbytes=rows * Dm * (2 + 4 + 4 + 4 + 2) + rows * 8)
             for N in (Dm, 3 * Dm, 4 * Dm):
