@@ -248,9 +248,10 @@ class HotPathEngine:
             mean2, rstd2 = buf(t + "mean2", (rows,), f32), buf(t + "rstd2", (rows,), f32)
             call("csm_layernorm_fwd", xmid, params[q + "norm2.weight"], params[q + "norm2.bias"], ln2, None, mean2,
                  rstd2, rows, Dm, LN_EPS)
-            h = buf(t + "h", (rows, hid), bf16)
+            # fc1 + GELU in one epilogue; what is kept for the backward is gelu'(h), not h
+            gp = buf(t + "gp", (rows, hid), bf16)
             act = buf(t + "act", (rows, hid), bf16)
-            call("csm_linear_fwd", ln2, w16[q + "mlp.fc1.weight"], params[q + "mlp.fc1.bias"], h, act,
+            call("csm_linear_fwd", ln2, w16[q + "mlp.fc1.weight"], params[q + "mlp.fc1.bias"], gp, act,
                  rows, hid, Dm, EPI_GELU)
             xout = buf(t + "xout", (rows, Dm), f32)
             call("csm_linear_fwd", act, w16[q + "mlp.fc2.weight"], params[q + "mlp.fc2.bias"], xout, xmid,
@@ -370,7 +371,7 @@ class HotPathEngine:
             if i == nlayers - 1 and not top_bias_done:
                 call("csm_colsum_bf16", dres16, G[q + "mlp.fc2.bias"], rows, Dm, 0, nsm)
             dh = buf(f"b.{tag}.dh", (rows, hid), bf16)
-            call("csm_linear_dgrad", dres16, w16[q + "mlp.fc2.weight"], dh, B[t + "h"], rows, Dm, hid, EPI_DGELU)
+            call("csm_linear_dgrad", dres16, w16[q + "mlp.fc2.weight"], dh, B[t + "gp"], rows, Dm, hid, EPI_DGELU)
             call("csm_linear_wgrad", dh, B[t + "ln2"], G[q + "mlp.fc1.weight"], rows, hid, Dm, nsm)
             call("csm_colsum_bf16", dh, G[q + "mlp.fc1.bias"], rows, hid, 0, nsm)
             dln = buf(f"b.{tag}.dln", (rows, Dm), bf16)

@@ -40,9 +40,9 @@ int csm_device_check(int device);
  * timm Block qkv/proj/fc1/fc2 (MAE_ViT_Baseline.py:160-188), patch_embed.proj as a GEMM (:75-77,245),
  * decoder_embed (:270), decoder_pred (:295), predictor Linears (MLP.py:6,9).
  * epilogue codes: 0 out_bf16 = bf16(acc + bias)
- *                 1 out_bf16 = h = bf16(acc + bias), aux_bf16 = bf16(gelu_erf(h))          (fc1 + nn.GELU)
+ *                 1 h = bf16(acc + bias); out_bf16 = bf16(gelu'(h)), aux_bf16 = bf16(gelu(h)) (fc1 + nn.GELU, erf form)
  *                 2 out_f32  = aux_f32 + bf16(acc + bias)                                  (x = x + proj/fc2)
- *                 3 out_bf16 = bf16(bf16(acc) * gelu'(aux_bf16))                           (dgrad only)
+ *                 3 out_bf16 = bf16(bf16(acc) * aux_bf16), aux = the gelu'(h) kept by epilogue 1   (dgrad only)
  *                 5 out_f32  = acc + bias
  */
 int csm_linear_fwd(const void* x_bf16, const void* w_bf16, const float* bias, void* out, void* aux, int M, int N,
