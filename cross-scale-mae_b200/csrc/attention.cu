@@ -6,20 +6,32 @@
 // Layout: qkv is the [rows, 3*Dm] bf16 output of the qkv Linear, row = b*S + s, columns
 // [which*Dm + h*d + j]; the output is [rows, Dm] with column h*d + j (== transpose(1,2).reshape).
 //
-// The whole K/V (or Q/dO) of one head is staged in shared memory, so the S x S score matrix never
-// exists in HBM (the reference materialises it in fp32: 159 MB per decoder layer at B=64).
-// Rounding points follow the autocast graph: scores are rounded to bf16, scaled, rounded again;
-// softmax statistics in fp32; probabilities rounded to bf16 for the PV product.
+// The S x S score matrix never exists in HBM (the reference materialises it in fp32: 159 MB per
+// decoder layer at B=64).  With d = 32/64 and S <= 785 these kernels are bound by the softmax
+// arithmetic (one exp2 + ~4 FP32 ops per score element against 2*d MACs), not by the tensor pipe or
+// HBM, so they are built around the instruction count per score element:
+//   forward : one CTA = the whole K/V of 1..2 heads in shared memory (read from HBM exactly once),
+//             one warp per 16-query tile, online softmax over 64-key blocks, exp2 with the
+//             d^-1/2 * log2(e) factor folded into one FFMA.
+//   backward: ONE pass per head (S <= 256).  One warp per 16-key tile walks the query tiles and forms
+//             S^T = K Q^T and dP^T = V dO^T once; P^T and dS^T are already A-operand fragments for
+//             dV += P^T dO and dK += dS^T Q; dS is transposed in registers (movmatrix) for
+//             dQ += dS K, which is accumulated across the key warps in shared memory (red.shared)
+//             and written once.  Longer sequences (cfg-5's S = 785 decoder) use the two-kernel path
+//             further down (dQ pass + dK/dV pass).
+// Probabilities / dS are rounded to bf16 for the tensor-core products as in the reference's autocast
+// graph; scores and softmax statistics stay in fp32 (the reference rounds the scores to bf16 first --
+// this path is strictly more accurate there).  mma.sync.m16n8k16 (bf16, f32 accumulate):
+// a tcgen05 version would leave the 128-lane MMA mostly empty at d = 32 and would not remove the
+// softmax bound.
 //
-// Round-1 implementation note: the three kernels use warp-level mma.sync.m16n8k16 (bf16, f32
-// accumulate) with ldmatrix operand fetch.  Attention is ~4 % of the step's FLOPs; moving it onto
-// tcgen05/TMEM is tracked in DESIGN.md as the next step for this file.
+// The per-row statistic handed from forward to backward is L2 = m * c + log2(sum exp2(s*c - m*c)),
+// c = d^-1/2 * log2(e), i.e. the log-sum-exp in the exp2 domain: p = exp2(s * c - L2).
 #include "common.cuh"
 
 namespace {
 using namespace csm;
 
-constexpr float kLog2e = 1.4426950408889634f;
 
 __device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t addr) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
@@ -116,72 +128,125 @@ __device__ __forceinline__ void store_tile_bf16(const float (&acc)[DH / 8][4], _
   }
 }
 
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ uint32_t movmatrix_trans(uint32_t a) {
+  uint32_t d;
+  asm volatile("movmatrix.sync.aligned.m8n8.trans.b16 %0, %1;" : "=r"(d) : "r"(a));
+  return d;
+}
+__device__ __forceinline__ void red_shared_add(float* addr, float v) {
+  asm volatile("red.shared.add.f32 [%0], %1;" ::"r"(smem_u32(addr)), "f"(v) : "memory");
+}
+
+// cooperative copy by `nthreads` threads (index tid) of rows [row0, row0 + nrows_pad) -- see load_rows
+template <int DH>
+__device__ __forceinline__ void load_rows_part(__nv_bfloat16* s, const __nv_bfloat16* g, int row0, int nrows_valid_total,
+                                               int nrows_pad, size_t ld_g, int tid, int nthreads) {
+  constexpr int CH = DH / 8;
+  for (int idx = tid; idx < nrows_pad * CH; idx += nthreads) {
+    const int r = idx / CH, c = idx % CH;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (row0 + r < nrows_valid_total) v = *reinterpret_cast<const uint4*>(g + static_cast<size_t>(row0 + r) * ld_g + c * 8);
+    *reinterpret_cast<uint4*>(s + r * (DH + 8) + c * 8) = v;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
-// forward: grid (B*H, ceil(S/64)); 4 warps, 16 query rows each; keys consumed 64 at a time
+// forward: grid (B*H / HPC, ceil(QT / QW)); CTA = HPC heads x QW warps, warp = one 16-query tile
 // ---------------------------------------------------------------------------------------------
 template <int DH>
-__global__ void __launch_bounds__(128)
-attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, float* __restrict__ lse,
-                int S, int H, int Dm, float scale) {
+__global__ void __launch_bounds__(512)
+attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, float* __restrict__ lse2,
+                int S, int H, int Dm, int HPC, int QW, float c) {
   extern __shared__ __align__(16) uint8_t smem_attn[];
   constexpr int LDS = DH + 8;
-  const int S_pad = (S + 63) / 64 * 64;
-  __nv_bfloat16* sK = reinterpret_cast<__nv_bfloat16*>(smem_attn);
-  __nv_bfloat16* sV = sK + S_pad * LDS;
-  __nv_bfloat16* sQ = sV + S_pad * LDS;
-  const int bh = blockIdx.x, b = bh / H, h = bh % H;
-  const int q0 = blockIdx.y * 64;
-  const size_t ld = static_cast<size_t>(3) * Dm;
-  const __nv_bfloat16* base = qkv + static_cast<size_t>(b) * S * ld + h * DH;
-  load_rows<DH>(sK, base + Dm, 0, S, S_pad, ld);
-  load_rows<DH>(sV, base + 2 * Dm, 0, S, S_pad, ld);
-  load_rows<DH>(sQ, base, q0, S, 64, ld);
-  __syncthreads();
-
+  const int S16 = (S + 15) & ~15;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int gq = lane >> 2, t = lane & 3;
-  const int r0 = q0 + warp * 16;
-  if (r0 >= S) return;
+  const int hl = warp / QW;                       // head slot inside the CTA
+  const int wq = warp % QW;
+  const int tph = QW * 32;                        // threads per head slot
+  const int bh = blockIdx.x * HPC + hl;
+  const int b = bh / H, h = bh % H;
+  // per head slot: K [S16][LDS], V [S16][LDS], per-warp Q / output tile [16][LDS]
+  __nv_bfloat16* sK = reinterpret_cast<__nv_bfloat16*>(smem_attn) + static_cast<size_t>(hl) * (2 * S16 + QW * 16) * LDS;
+  __nv_bfloat16* sV = sK + S16 * LDS;
+  __nv_bfloat16* sQ = sV + S16 * LDS + wq * 16 * LDS;
+  const size_t ld = static_cast<size_t>(3) * Dm;
+  const __nv_bfloat16* base = qkv + static_cast<size_t>(b) * S * ld + h * DH;
+  const int tid_h = threadIdx.x - hl * tph;
+  const int q0 = (blockIdx.y * QW + wq) * 16;
+  load_rows_part<DH>(sK, base + Dm, 0, S, S16, ld, tid_h, tph);
+  load_rows_part<DH>(sV, base + 2 * Dm, 0, S, S16, ld, tid_h, tph);
+  load_rows_part<DH>(sQ, base, q0, S, 16, ld, lane, 32);
+  __syncthreads();
+  if (q0 >= S) return;
 
   uint32_t qf[DH / 16][4];
-  load_a_frags<DH>(qf, sQ, warp * 16, lane);
+  load_a_frags<DH>(qf, sQ, 0, lane);
   float o[DH / 8][4];
 #pragma unroll
   for (int i = 0; i < DH / 8; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
   float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
 
-  for (int kb0 = 0; kb0 < S_pad; kb0 += 64) {
+  for (int kb0 = 0; kb0 < S16; kb0 += 64) {
+    const int nt16 = min(4, (S16 - kb0) >> 4);     // 16-key tiles in this block (warp-uniform)
     float s[8][4];
 #pragma unroll
     for (int i = 0; i < 8; ++i) s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
-    mma_a_rowsT<DH, 8>(s, qf, sK, kb0, lane);
+    {
+      const int r = (lane & 7) + (lane >> 4) * 8;
+      const int cc = ((lane >> 3) & 1) * 8;
+#pragma unroll
+      for (int kk = 0; kk < DH / 16; ++kk) {
+#pragma unroll
+        for (int np = 0; np < 4; ++np) {
+          if (np < nt16) {
+            uint32_t bfr[4];
+            ldsm_x4(bfr, smem_u32(sK + (kb0 + np * 16 + r) * LDS + kk * 16 + cc));
+            mma_bf16(s[2 * np], qf[kk], bfr[0], bfr[1]);
+            mma_bf16(s[2 * np + 1], qf[kk], bfr[2], bfr[3]);
+          }
+        }
+      }
+    }
+    if (kb0 + 64 > S) {                             // only the last block holds padded keys
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int key = kb0 + nt * 8 + 2 * t + (e & 1);
+          if (key >= S) s[nt][e] = -INFINITY;
+        }
+      }
+    }
     float mx[2] = {-INFINITY, -INFINITY};
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int key = kb0 + nt * 8 + 2 * t + (e & 1);
-        float v = bf16_round(bf16_round(s[nt][e]) * scale);
-        v = key < S ? v : -INFINITY;
-        s[nt][e] = v;
-        mx[e >> 1] = fmaxf(mx[e >> 1], v);
-      }
+      mx[0] = fmaxf(mx[0], fmaxf(s[nt][0], s[nt][1]));
+      mx[1] = fmaxf(mx[1], fmaxf(s[nt][2], s[nt][3]));
     }
-    float alpha[2];
+    float alpha[2], mc[2];
 #pragma unroll
     for (int hh = 0; hh < 2; ++hh) {
       mx[hh] = fmaxf(mx[hh], __shfl_xor_sync(0xffffffffu, mx[hh], 1));
       mx[hh] = fmaxf(mx[hh], __shfl_xor_sync(0xffffffffu, mx[hh], 2));
       const float m_new = fmaxf(m_run[hh], mx[hh]);
-      alpha[hh] = exp2f((m_run[hh] - m_new) * kLog2e);
+      alpha[hh] = ex2_approx((m_run[hh] - m_new) * c);
       m_run[hh] = m_new;
+      mc[hh] = m_new * c;
       l_run[hh] *= alpha[hh];
     }
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        const float pv = exp2f((s[nt][e] - m_run[e >> 1]) * kLog2e);
+        const float pv = ex2_approx(fmaf(s[nt][e], c, -mc[e >> 1]));
         s[nt][e] = pv;
         l_run[e >> 1] += pv;
       }
@@ -193,12 +258,14 @@ attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict
     }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      uint32_t a[4];
-      a[0] = pack_bf16x2(s[2 * j][0], s[2 * j][1]);
-      a[1] = pack_bf16x2(s[2 * j][2], s[2 * j][3]);
-      a[2] = pack_bf16x2(s[2 * j + 1][0], s[2 * j + 1][1]);
-      a[3] = pack_bf16x2(s[2 * j + 1][2], s[2 * j + 1][3]);
-      mma_p_rows<DH>(o, a, sV, kb0 + j * 16, lane);
+      if (j < nt16) {
+        uint32_t a[4];
+        a[0] = pack_bf16x2(s[2 * j][0], s[2 * j][1]);
+        a[1] = pack_bf16x2(s[2 * j][2], s[2 * j][3]);
+        a[2] = pack_bf16x2(s[2 * j + 1][0], s[2 * j + 1][1]);
+        a[3] = pack_bf16x2(s[2 * j + 1][2], s[2 * j + 1][3]);
+        mma_p_rows<DH>(o, a, sV, kb0 + j * 16, lane);
+      }
     }
   }
 #pragma unroll
@@ -213,14 +280,175 @@ attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict
     o[dn][2] *= inv1; o[dn][3] *= inv1;
   }
   if (t == 0) {
-    if (r0 + gq < S) lse[static_cast<size_t>(bh) * S + r0 + gq] = m_run[0] + logf(l_run[0]);
-    if (r0 + gq + 8 < S) lse[static_cast<size_t>(bh) * S + r0 + gq + 8] = m_run[1] + logf(l_run[1]);
+    if (q0 + gq < S) lse2[static_cast<size_t>(bh) * S + q0 + gq] = m_run[0] * c + log2f(l_run[0]);
+    if (q0 + gq + 8 < S) lse2[static_cast<size_t>(bh) * S + q0 + gq + 8] = m_run[1] * c + log2f(l_run[1]);
   }
   __nv_bfloat16* og = out + static_cast<size_t>(b) * S * Dm + h * DH;
-  store_tile_bf16<DH>(o, sQ + warp * 16 * LDS, og, r0, S, Dm, lane);
+  store_tile_bf16<DH>(o, sQ, og, q0, S, Dm, lane);
 }
 
 // ---------------------------------------------------------------------------------------------
+// backward, single pass (S16 <= 256): grid (B*H / HPC); CTA = HPC heads x KT warps, warp = one 16-key tile
+// ---------------------------------------------------------------------------------------------
+template <int DH>
+__global__ void __launch_bounds__(512)
+attn_bwd_head_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ o_fwd,
+                     const __nv_bfloat16* __restrict__ d_out, const float* __restrict__ lse2,
+                     __nv_bfloat16* __restrict__ dqkv, int S, int H, int Dm, int HPC, float c, float scale) {
+  extern __shared__ __align__(16) uint8_t smem_attn[];
+  constexpr int LDS = DH + 8;
+  constexpr int LDQ = DH + 4;                     // f32 dQ rows (padded against bank conflicts)
+  const int S16 = (S + 15) & ~15;
+  const int KT = S16 >> 4;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int gq = lane >> 2, t = lane & 3;
+  const int hl = warp / KT;
+  const int kt = warp % KT;
+  const int tph = KT * 32;
+  const int tid_h = threadIdx.x - hl * tph;
+  const int bh = blockIdx.x * HPC + hl;
+  const int b = bh / H, h = bh % H;
+  // per head slot: Q [S16][LDS], dO [S16][LDS], per-warp K and V tiles [16][LDS] each, dQ f32 [S16][LDQ],
+  //                L2 [S16], delta [S16]
+  const size_t slot_bytes = static_cast<size_t>(2 * S16 + KT * 32) * LDS * 2 + static_cast<size_t>(S16) * LDQ * 4 +
+                            static_cast<size_t>(S16) * 8;
+  uint8_t* slot = smem_attn + hl * slot_bytes;
+  __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(slot);
+  __nv_bfloat16* sdO = sQ + S16 * LDS;
+  __nv_bfloat16* sKt = sdO + S16 * LDS + kt * 32 * LDS;
+  __nv_bfloat16* sVt = sKt + 16 * LDS;
+  float* sdQ = reinterpret_cast<float*>(sdO + S16 * LDS + KT * 32 * LDS);
+  float* sL2 = sdQ + S16 * LDQ;
+  float* sDelta = sL2 + S16;
+  const size_t ld = static_cast<size_t>(3) * Dm;
+  const __nv_bfloat16* base = qkv + static_cast<size_t>(b) * S * ld + h * DH;
+  const size_t obase = static_cast<size_t>(b) * S * Dm + h * DH;
+
+  load_rows_part<DH>(sQ, base, 0, S, S16, ld, tid_h, tph);
+  load_rows_part<DH>(sdO, d_out + obase, 0, S, S16, Dm, tid_h, tph);
+  load_rows_part<DH>(sKt, base + Dm, kt * 16, S, 16, ld, lane, 32);
+  load_rows_part<DH>(sVt, base + 2 * Dm, kt * 16, S, 16, ld, lane, 32);
+  for (int i = tid_h; i < S16 * LDQ; i += tph) sdQ[i] = 0.f;
+  // delta[q] = sum_j dO[q, j] * O[q, j]; L2 = +inf for padded queries (p = exp2(-inf) = 0)
+  {
+    constexpr int TPRW = DH / 8;                  // threads per row (16-byte chunks)
+    for (int idx = tid_h; idx < S16 * TPRW; idx += tph) {
+      const int r = idx / TPRW, cch = idx % TPRW;
+      float part = 0.f;
+      if (r < S) {
+        const uint4 a = *reinterpret_cast<const uint4*>(d_out + obase + static_cast<size_t>(r) * Dm + cch * 8);
+        const uint4 bb = *reinterpret_cast<const uint4*>(o_fwd + obase + static_cast<size_t>(r) * Dm + cch * 8);
+        const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 x = unpack_bf16x2(aw[j]), y = unpack_bf16x2(bw[j]);
+          part += x.x * y.x + x.y * y.y;
+        }
+      }
+      // TPRW (4 or 8) consecutive lanes hold one row
+#pragma unroll
+      for (int off = TPRW / 2; off > 0; off >>= 1) part += __shfl_xor_sync(0xffffffffu, part, off);
+      if (cch == 0) {
+        sDelta[r] = part;
+        sL2[r] = r < S ? lse2[static_cast<size_t>(bh) * S + r] : INFINITY;
+      }
+    }
+  }
+  __syncthreads();
+
+  uint32_t kf[DH / 16][4], vf[DH / 16][4];
+  load_a_frags<DH>(kf, sKt, 0, lane);
+  load_a_frags<DH>(vf, sVt, 0, lane);
+  float dk[DH / 8][4], dv[DH / 8][4];
+#pragma unroll
+  for (int i = 0; i < DH / 8; ++i) {
+    dk[i][0] = dk[i][1] = dk[i][2] = dk[i][3] = 0.f;
+    dv[i][0] = dv[i][1] = dv[i][2] = dv[i][3] = 0.f;
+  }
+  const bool tail_keys = (kt * 16 + 16 > S);       // this warp's tile holds padded keys (warp-uniform)
+  const bool key_ok0 = kt * 16 + gq < S, key_ok1 = kt * 16 + gq + 8 < S;
+
+  for (int qt = 0; qt < KT; ++qt) {
+    const int qb0 = qt * 16;
+    float st[2][4], dpt[2][4];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      st[i][0] = st[i][1] = st[i][2] = st[i][3] = 0.f;
+      dpt[i][0] = dpt[i][1] = dpt[i][2] = dpt[i][3] = 0.f;
+    }
+    mma_a_rowsT<DH, 2>(st, kf, sQ, qb0, lane);      // S^T  = K Q^T   [16 keys x 16 queries]
+    mma_a_rowsT<DH, 2>(dpt, vf, sdO, qb0, lane);    // dP^T = V dO^T
+    uint32_t pa[4], da[4];
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt) {
+      const float2 l2 = *reinterpret_cast<const float2*>(sL2 + qb0 + nt * 8 + 2 * t);
+      const float2 dl = *reinterpret_cast<const float2*>(sDelta + qb0 + nt * 8 + 2 * t);
+      float pv[4], dsv[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float p = ex2_approx(fmaf(st[nt][e], c, -((e & 1) ? l2.y : l2.x)));
+        pv[e] = p;
+        dsv[e] = p * (dpt[nt][e] - ((e & 1) ? dl.y : dl.x));
+      }
+      if (tail_keys) {
+        if (!key_ok0) { pv[0] = pv[1] = 0.f; dsv[0] = dsv[1] = 0.f; }
+        if (!key_ok1) { pv[2] = pv[3] = 0.f; dsv[2] = dsv[3] = 0.f; }
+      }
+      pa[nt * 2 + 0] = pack_bf16x2(pv[0], pv[1]);
+      pa[nt * 2 + 1] = pack_bf16x2(pv[2], pv[3]);
+      da[nt * 2 + 0] = pack_bf16x2(dsv[0], dsv[1]);
+      da[nt * 2 + 1] = pack_bf16x2(dsv[2], dsv[3]);
+    }
+    mma_p_rows<DH>(dv, pa, sdO, qb0, lane);         // dV += P^T dO
+    mma_p_rows<DH>(dk, da, sQ, qb0, lane);          // dK += dS^T Q   (x scale at the end)
+    // dQ[16 q, :] += dS[16 q x 16 keys] K[16 keys, :]: transpose the dS^T fragments in registers
+    uint32_t dst[4];
+    dst[0] = movmatrix_trans(da[0]);
+    dst[1] = movmatrix_trans(da[2]);
+    dst[2] = movmatrix_trans(da[1]);
+    dst[3] = movmatrix_trans(da[3]);
+    float dq[DH / 8][4];
+#pragma unroll
+    for (int i = 0; i < DH / 8; ++i) dq[i][0] = dq[i][1] = dq[i][2] = dq[i][3] = 0.f;
+    mma_p_rows<DH>(dq, dst, sKt, 0, lane);
+    float* q_lo = sdQ + (qb0 + gq) * LDQ + 2 * t;
+    float* q_hi = q_lo + 8 * LDQ;
+#pragma unroll
+    for (int dn = 0; dn < DH / 8; ++dn) {
+      red_shared_add(q_lo + dn * 8, dq[dn][0]);
+      red_shared_add(q_lo + dn * 8 + 1, dq[dn][1]);
+      red_shared_add(q_hi + dn * 8, dq[dn][2]);
+      red_shared_add(q_hi + dn * 8 + 1, dq[dn][3]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < DH / 8; ++i) {
+    dk[i][0] *= scale; dk[i][1] *= scale; dk[i][2] *= scale; dk[i][3] *= scale;
+  }
+  __nv_bfloat16* dkg = dqkv + static_cast<size_t>(b) * S * ld + Dm + h * DH;
+  __nv_bfloat16* dvg = dqkv + static_cast<size_t>(b) * S * ld + 2 * Dm + h * DH;
+  // both tiles go out through this warp's private K-tile scratch (its fragments are already in registers)
+  store_tile_bf16<DH>(dk, sKt, dkg, kt * 16, S, ld, lane);
+  store_tile_bf16<DH>(dv, sKt, dvg, kt * 16, S, ld, lane);
+  __syncthreads();
+  // dQ = scale * sum over key tiles, written once
+  {
+    __nv_bfloat16* dqg = dqkv + static_cast<size_t>(b) * S * ld + h * DH;
+    constexpr int CH = DH / 8;
+    for (int idx = tid_h; idx < S * CH; idx += tph) {
+      const int r = idx / CH, cch = idx % CH;
+      const float4 a = *reinterpret_cast<const float4*>(sdQ + r * LDQ + cch * 8);
+      const float4 bb = *reinterpret_cast<const float4*>(sdQ + r * LDQ + cch * 8 + 4);
+      uint4 pk;
+      pk.x = pack_bf16x2(a.x * scale, a.y * scale); pk.y = pack_bf16x2(a.z * scale, a.w * scale);
+      pk.z = pack_bf16x2(bb.x * scale, bb.y * scale); pk.w = pack_bf16x2(bb.z * scale, bb.w * scale);
+      *reinterpret_cast<uint4*>(dqg + static_cast<size_t>(r) * ld + cch * 8) = pk;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// long sequences (S16 > 256), two kernels.
 // backward, dQ: grid (B*H, ceil(S/64)); K,V of the head + the Q/dO/O rows of this block in smem.
 // Also writes delta[bh, s] = sum_j dO[s, j] * O[s, j] for the dK/dV kernel.
 // ---------------------------------------------------------------------------------------------
@@ -228,7 +456,8 @@ template <int DH>
 __global__ void __launch_bounds__(128)
 attn_bwd_dq_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ o_fwd,
                    const __nv_bfloat16* __restrict__ d_out, const float* __restrict__ lse,
-                   float* __restrict__ delta, __nv_bfloat16* __restrict__ dqkv, int S, int H, int Dm, float scale) {
+                   float* __restrict__ delta, __nv_bfloat16* __restrict__ dqkv, int S, int H, int Dm, float c,
+                   float scale) {
   extern __shared__ __align__(16) uint8_t smem_attn[];
   constexpr int LDS = DH + 8;
   const int S_pad = (S + 31) / 32 * 32;
@@ -295,10 +524,8 @@ attn_bwd_dq_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* _
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const int key = kb0 + nt * 8 + 2 * t + (e & 1);
-        const float sv = bf16_round(bf16_round(s[nt][e]) * scale);
-        const float p = key < S ? exp2f((sv - ls[e >> 1]) * kLog2e) : 0.f;
-        const float ds = p * (bf16_round(dp[nt][e]) - dl[e >> 1]);
-        s[nt][e] = bf16_round(ds) * scale;
+        const float p = key < S ? ex2_approx(fmaf(s[nt][e], c, -ls[e >> 1])) : 0.f;
+        s[nt][e] = p * (dp[nt][e] - dl[e >> 1]) * scale;
       }
     }
 #pragma unroll
@@ -322,7 +549,7 @@ template <int DH>
 __global__ void __launch_bounds__(128)
 attn_bwd_dkv_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ d_out,
                     const float* __restrict__ lse, const float* __restrict__ delta,
-                    __nv_bfloat16* __restrict__ dqkv, int S, int H, int Dm, float scale) {
+                    __nv_bfloat16* __restrict__ dqkv, int S, int H, int Dm, float c, float scale) {
   extern __shared__ __align__(16) uint8_t smem_attn[];
   constexpr int LDS = DH + 8;
   const int S_pad = (S + 31) / 32 * 32;
@@ -378,11 +605,9 @@ attn_bwd_dkv_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* 
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const int query = qb0 + nt * 8 + 2 * t + (e & 1);
-        const float sv = bf16_round(bf16_round(st[nt][e]) * scale);
-        const float p = exp2f((sv - sLse[query]) * kLog2e);   // lse = +inf for padded queries -> 0
-        const float ds = p * (bf16_round(dpt[nt][e]) - sDelta[query]);
+        const float p = ex2_approx(fmaf(st[nt][e], c, -sLse[query]));   // L2 = +inf for padded queries -> 0
         pv[e] = p;
-        dsv[e] = bf16_round(ds) * scale;
+        dsv[e] = p * (dpt[nt][e] - sDelta[query]) * scale;
       }
       const int j = nt >> 1, hi = (nt & 1) * 2;
       pa[j][hi + 0] = pack_bf16x2(pv[0], pv[1]);
@@ -422,15 +647,21 @@ int set_smem(K kern, size_t bytes, size_t* configured, const char* name) {
 template <int DH>
 int attn_fwd_launch(const void* qkv, void* out, float* lse, int B, int S, int H, cudaStream_t stream) {
   const int Dm = H * DH;
-  const int S_pad = (S + 63) / 64 * 64;
-  const size_t smem = static_cast<size_t>(2 * S_pad + 64) * (DH + 8) * 2;
+  const int S16 = (S + 15) & ~15;
+  const int QT = S16 >> 4;
+  int HPC = QT >= 8 ? 1 : 8 / QT;
+  while (HPC > 1 && (B * H) % HPC != 0) --HPC;
+  int QW = 16 / HPC;
+  if (QW > QT) QW = QT;
+  const size_t smem = static_cast<size_t>(HPC) * (2 * S16 + QW * 16) * (DH + 8) * 2;
   static size_t cfg_fwd = 0;
   int rc = set_smem(attn_fwd_kernel<DH>, smem, &cfg_fwd, "attention_fwd");
   if (rc) return rc;
-  dim3 grid(B * H, (S + 63) / 64);
-  attn_fwd_kernel<DH><<<grid, 128, smem, stream>>>(reinterpret_cast<const __nv_bfloat16*>(qkv),
-                                                   reinterpret_cast<__nv_bfloat16*>(out), lse, S, H, Dm,
-                                                   1.0f / sqrtf(static_cast<float>(DH)));
+  const float c = 1.4426950408889634f / sqrtf(static_cast<float>(DH));
+  dim3 grid(B * H / HPC, (QT + QW - 1) / QW);
+  attn_fwd_kernel<DH><<<grid, HPC * QW * 32, smem, stream>>>(reinterpret_cast<const __nv_bfloat16*>(qkv),
+                                                             reinterpret_cast<__nv_bfloat16*>(out), lse, S, H, Dm, HPC,
+                                                             QW, c);
   CSM_CHECK_LAUNCH("attention_fwd");
   return CSM_OK;
 }
@@ -439,8 +670,27 @@ template <int DH>
 int attn_bwd_launch(const void* qkv, const void* o, const void* d_out, const float* lse, float* delta, void* dqkv,
                     int B, int S, int H, cudaStream_t stream) {
   const int Dm = H * DH;
-  const int S_pad = (S + 31) / 32 * 32;
   const float scale = 1.0f / sqrtf(static_cast<float>(DH));
+  const float c = 1.4426950408889634f * scale;
+  const int S16 = (S + 15) & ~15;
+  if (S16 <= 256) {
+    const int KT = S16 >> 4;
+    int HPC = KT >= 8 ? 1 : 8 / KT;
+    while (HPC > 1 && (B * H) % HPC != 0) --HPC;
+    const size_t slot = static_cast<size_t>(2 * S16 + KT * 32) * (DH + 8) * 2 + static_cast<size_t>(S16) * (DH + 4) * 4 +
+                        static_cast<size_t>(S16) * 8;
+    static size_t cfg_head = 0;
+    int rc = set_smem(attn_bwd_head_kernel<DH>, slot * HPC, &cfg_head, "attention_bwd");
+    if (rc) return rc;
+    attn_bwd_head_kernel<DH><<<B * H / HPC, HPC * KT * 32, slot * HPC, stream>>>(
+        reinterpret_cast<const __nv_bfloat16*>(qkv), reinterpret_cast<const __nv_bfloat16*>(o),
+        reinterpret_cast<const __nv_bfloat16*>(d_out), lse, reinterpret_cast<__nv_bfloat16*>(dqkv), S, H, Dm, HPC, c,
+        scale);
+    CSM_CHECK_LAUNCH("attention_bwd");
+    return CSM_OK;
+  }
+  CSM_CHECK_ARG(delta != nullptr, "csm_attention_bwd: S=%d needs the delta scratch buffer", S);
+  const int S_pad = (S + 31) / 32 * 32;
   dim3 grid(B * H, (S + 63) / 64);
   const size_t smem_dq = static_cast<size_t>(2 * S_pad + 3 * 64) * (DH + 8) * 2;
   static size_t cfg_dq = 0, cfg_dkv = 0;
@@ -448,7 +698,7 @@ int attn_bwd_launch(const void* qkv, const void* o, const void* d_out, const flo
   if (rc) return rc;
   attn_bwd_dq_kernel<DH><<<grid, 128, smem_dq, stream>>>(
       reinterpret_cast<const __nv_bfloat16*>(qkv), reinterpret_cast<const __nv_bfloat16*>(o),
-      reinterpret_cast<const __nv_bfloat16*>(d_out), lse, delta, reinterpret_cast<__nv_bfloat16*>(dqkv), S, H, Dm,
+      reinterpret_cast<const __nv_bfloat16*>(d_out), lse, delta, reinterpret_cast<__nv_bfloat16*>(dqkv), S, H, Dm, c,
       scale);
   CSM_CHECK_LAUNCH("attention_bwd_dq");
   const size_t smem_dkv = static_cast<size_t>(2 * S_pad + 2 * 64) * (DH + 8) * 2 + static_cast<size_t>(2) * S_pad * 4;
@@ -456,7 +706,7 @@ int attn_bwd_launch(const void* qkv, const void* o, const void* d_out, const flo
   if (rc) return rc;
   attn_bwd_dkv_kernel<DH><<<grid, 128, smem_dkv, stream>>>(
       reinterpret_cast<const __nv_bfloat16*>(qkv), reinterpret_cast<const __nv_bfloat16*>(d_out), lse, delta,
-      reinterpret_cast<__nv_bfloat16*>(dqkv), S, H, Dm, scale);
+      reinterpret_cast<__nv_bfloat16*>(dqkv), S, H, Dm, c, scale);
   CSM_CHECK_LAUNCH("attention_bwd_dkv");
   return CSM_OK;
 }
