@@ -16,8 +16,9 @@
 //   backward: ONE pass per head (S <= 256).  One warp per 16-key tile walks the query tiles and forms
 //             S^T = K Q^T and dP^T = V dO^T once; P^T and dS^T are already A-operand fragments for
 //             dV += P^T dO and dK += dS^T Q; dS is transposed in registers (movmatrix) for
-//             dQ += dS K, which is accumulated across the key warps in shared memory (red.shared)
-//             and written once.  Longer sequences (cfg-5's S = 785 decoder) use the two-kernel path
+//             dQ += dS K, which is accumulated across the key warps in shared memory and written once
+//             (the warps walk the query tiles in rotated order, one barrier per step, so the
+//             accumulation needs no atomics -- red.shared.add.f32 compiles to a CAS loop).  Longer sequences (cfg-5's S = 785 decoder) use the two-kernel path
 //             further down (dQ pass + dK/dV pass).
 // Probabilities / dS are rounded to bf16 for the tensor-core products as in the reference's autocast
 // graph; scores and softmax statistics stay in fp32 (the reference rounds the scores to bf16 first --
@@ -139,8 +140,19 @@ __device__ __forceinline__ uint32_t movmatrix_trans(uint32_t a) {
   asm volatile("movmatrix.sync.aligned.m8n8.trans.b16 %0, %1;" : "=r"(d) : "r"(a));
   return d;
 }
-__device__ __forceinline__ void red_shared_add(float* addr, float v) {
-  asm volatile("red.shared.add.f32 [%0], %1;" ::"r"(smem_u32(addr)), "f"(v) : "memory");
+
+__device__ __forceinline__ uint4 ld_shared_u4(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ float2 ld_shared_f2(uint32_t addr) {
+  float2 v;
+  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void st_shared_f2(uint32_t addr, float2 v) {
+  asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(v.x), "f"(v.y) : "memory");
 }
 
 // cooperative copy by `nthreads` threads (index tid) of rows [row0, row0 + nrows_pad) -- see load_rows
@@ -156,16 +168,37 @@ __device__ __forceinline__ void load_rows_part(__nv_bfloat16* s, const __nv_bflo
   }
 }
 
+// Same copy with cp.async (16 bytes per request, zero-fill for rows past the end): nothing waits on the
+// loads until cp_async_wait_all(), so a CTA exposes one memory latency for everything it stages.
+template <int DH>
+__device__ __forceinline__ void load_rows_async(__nv_bfloat16* s, const __nv_bfloat16* g, int row0, int nrows_valid_total,
+                                                int nrows_pad, size_t ld_g, int tid, int nthreads) {
+  constexpr int CH = DH / 8;
+  for (int idx = tid; idx < nrows_pad * CH; idx += nthreads) {
+    const int r = idx / CH, c = idx % CH;
+    const bool ok = row0 + r < nrows_valid_total;
+    const __nv_bfloat16* src = g + static_cast<size_t>(ok ? row0 + r : 0) * ld_g + c * 8;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(s + r * (DH + 8) + c * 8)), "l"(src),
+                 "r"(ok ? 16 : 0)
+                 : "memory");
+  }
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+
 // ---------------------------------------------------------------------------------------------
 // forward: grid (B*H / HPC, ceil(QT / QW)); CTA = HPC heads x QW warps, warp = one 16-query tile
 // ---------------------------------------------------------------------------------------------
 template <int DH>
-__global__ void __launch_bounds__(512)
+__global__ void __launch_bounds__(256, DH == 32 ? 3 : 2)
 attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, float* __restrict__ lse2,
-                int S, int H, int Dm, int HPC, int QW, float c) {
+                int S, int H, int Dm, int HPC, int QW, int QPW, float c) {
   extern __shared__ __align__(16) uint8_t smem_attn[];
   constexpr int LDS = DH + 8;
   const int S16 = (S + 15) & ~15;
+  const int QT = S16 >> 4;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int gq = lane >> 2, t = lane & 3;
   const int hl = warp / QW;                       // head slot inside the CTA
@@ -173,131 +206,142 @@ attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict
   const int tph = QW * 32;                        // threads per head slot
   const int bh = blockIdx.x * HPC + hl;
   const int b = bh / H, h = bh % H;
-  // per head slot: K [S16][LDS], V [S16][LDS], per-warp Q / output tile [16][LDS]
-  __nv_bfloat16* sK = reinterpret_cast<__nv_bfloat16*>(smem_attn) + static_cast<size_t>(hl) * (2 * S16 + QW * 16) * LDS;
+  // per head slot: K [S16][LDS], V [S16][LDS], per-warp Q / output tiles [QPW][16][LDS]
+  __nv_bfloat16* sK = reinterpret_cast<__nv_bfloat16*>(smem_attn) +
+                      static_cast<size_t>(hl) * (2 * S16 + QW * QPW * 16) * LDS;
   __nv_bfloat16* sV = sK + S16 * LDS;
-  __nv_bfloat16* sQ = sV + S16 * LDS + wq * 16 * LDS;
+  __nv_bfloat16* sQw = sV + S16 * LDS + wq * QPW * 16 * LDS;
   const size_t ld = static_cast<size_t>(3) * Dm;
   const __nv_bfloat16* base = qkv + static_cast<size_t>(b) * S * ld + h * DH;
+  __nv_bfloat16* og = out + static_cast<size_t>(b) * S * Dm + h * DH;
   const int tid_h = threadIdx.x - hl * tph;
-  const int q0 = (blockIdx.y * QW + wq) * 16;
-  load_rows_part<DH>(sK, base + Dm, 0, S, S16, ld, tid_h, tph);
-  load_rows_part<DH>(sV, base + 2 * Dm, 0, S, S16, ld, tid_h, tph);
-  load_rows_part<DH>(sQ, base, q0, S, 16, ld, lane, 32);
+  const int qt_begin = blockIdx.y * QW * QPW;
+  const int qt_end = min(QT, qt_begin + QW * QPW);
+  load_rows_async<DH>(sK, base + Dm, 0, S, S16, ld, tid_h, tph);
+  load_rows_async<DH>(sV, base + 2 * Dm, 0, S, S16, ld, tid_h, tph);
+  for (int qt = qt_begin + wq, i = 0; qt < qt_end; qt += QW, ++i)
+    load_rows_async<DH>(sQw + i * 16 * LDS, base, qt * 16, S, 16, ld, lane, 32);
+  cp_async_wait_all();
   __syncthreads();
-  if (q0 >= S) return;
 
-  uint32_t qf[DH / 16][4];
-  load_a_frags<DH>(qf, sQ, 0, lane);
-  float o[DH / 8][4];
+  for (int qt = qt_begin + wq, qi = 0; qt < qt_end; qt += QW, ++qi) {
+    const int q0 = qt * 16;
+    __nv_bfloat16* sQ = sQw + qi * 16 * LDS;
+    uint32_t qf[DH / 16][4];
+    load_a_frags<DH>(qf, sQ, 0, lane);
+    float o[DH / 8][4];
 #pragma unroll
-  for (int i = 0; i < DH / 8; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
-  float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
+    for (int i = 0; i < DH / 8; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
+    float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
 
-  for (int kb0 = 0; kb0 < S16; kb0 += 64) {
-    const int nt16 = min(4, (S16 - kb0) >> 4);     // 16-key tiles in this block (warp-uniform)
-    float s[8][4];
+    for (int kb0 = 0; kb0 < S16; kb0 += 64) {
+      const int nt16 = min(4, (S16 - kb0) >> 4);     // 16-key tiles in this block (warp-uniform)
+      float s[8][4];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
-    {
-      const int r = (lane & 7) + (lane >> 4) * 8;
-      const int cc = ((lane >> 3) & 1) * 8;
+      for (int i = 0; i < 8; ++i) s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
+      {
+        const int r = (lane & 7) + (lane >> 4) * 8;
+        const int cc = ((lane >> 3) & 1) * 8;
 #pragma unroll
-      for (int kk = 0; kk < DH / 16; ++kk) {
+        for (int kk = 0; kk < DH / 16; ++kk) {
 #pragma unroll
-        for (int np = 0; np < 4; ++np) {
-          if (np < nt16) {
-            uint32_t bfr[4];
-            ldsm_x4(bfr, smem_u32(sK + (kb0 + np * 16 + r) * LDS + kk * 16 + cc));
-            mma_bf16(s[2 * np], qf[kk], bfr[0], bfr[1]);
-            mma_bf16(s[2 * np + 1], qf[kk], bfr[2], bfr[3]);
+          for (int np = 0; np < 4; ++np) {
+            if (np < nt16) {
+              uint32_t bfr[4];
+              ldsm_x4(bfr, smem_u32(sK + (kb0 + np * 16 + r) * LDS + kk * 16 + cc));
+              mma_bf16(s[2 * np], qf[kk], bfr[0], bfr[1]);
+              mma_bf16(s[2 * np + 1], qf[kk], bfr[2], bfr[3]);
+            }
           }
         }
       }
-    }
-    if (kb0 + 64 > S) {                             // only the last block holds padded keys
+      if (kb0 + nt16 * 16 > S) {                      // only the last 16-key tile holds padded keys
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int key = kb0 + nt * 8 + 2 * t + (e & 1);
+            if (key >= S) s[nt][e] = -INFINITY;
+          }
+        }
+      }
+      float mx[2] = {-INFINITY, -INFINITY};
 #pragma unroll
       for (int nt = 0; nt < 8; ++nt) {
+        if (nt < 2 * nt16) {
+          mx[0] = fmaxf(mx[0], fmaxf(s[nt][0], s[nt][1]));
+          mx[1] = fmaxf(mx[1], fmaxf(s[nt][2], s[nt][3]));
+        }
+      }
+      float alpha[2], mc[2];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int key = kb0 + nt * 8 + 2 * t + (e & 1);
-          if (key >= S) s[nt][e] = -INFINITY;
+      for (int hh = 0; hh < 2; ++hh) {
+        mx[hh] = fmaxf(mx[hh], __shfl_xor_sync(0xffffffffu, mx[hh], 1));
+        mx[hh] = fmaxf(mx[hh], __shfl_xor_sync(0xffffffffu, mx[hh], 2));
+        const float m_new = fmaxf(m_run[hh], mx[hh]);
+        alpha[hh] = ex2_approx((m_run[hh] - m_new) * c);
+        m_run[hh] = m_new;
+        mc[hh] = m_new * c;
+        l_run[hh] *= alpha[hh];
+      }
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        if (nt < 2 * nt16) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float pv = ex2_approx(fmaf(s[nt][e], c, -mc[e >> 1]));
+            s[nt][e] = pv;
+            l_run[e >> 1] += pv;
+          }
+        }
+      }
+#pragma unroll
+      for (int dn = 0; dn < DH / 8; ++dn) {
+        o[dn][0] *= alpha[0]; o[dn][1] *= alpha[0];
+        o[dn][2] *= alpha[1]; o[dn][3] *= alpha[1];
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (j < nt16) {
+          uint32_t a[4];
+          a[0] = pack_bf16x2(s[2 * j][0], s[2 * j][1]);
+          a[1] = pack_bf16x2(s[2 * j][2], s[2 * j][3]);
+          a[2] = pack_bf16x2(s[2 * j + 1][0], s[2 * j + 1][1]);
+          a[3] = pack_bf16x2(s[2 * j + 1][2], s[2 * j + 1][3]);
+          mma_p_rows<DH>(o, a, sV, kb0 + j * 16, lane);
         }
       }
     }
-    float mx[2] = {-INFINITY, -INFINITY};
-#pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
-      mx[0] = fmaxf(mx[0], fmaxf(s[nt][0], s[nt][1]));
-      mx[1] = fmaxf(mx[1], fmaxf(s[nt][2], s[nt][3]));
-    }
-    float alpha[2], mc[2];
 #pragma unroll
     for (int hh = 0; hh < 2; ++hh) {
-      mx[hh] = fmaxf(mx[hh], __shfl_xor_sync(0xffffffffu, mx[hh], 1));
-      mx[hh] = fmaxf(mx[hh], __shfl_xor_sync(0xffffffffu, mx[hh], 2));
-      const float m_new = fmaxf(m_run[hh], mx[hh]);
-      alpha[hh] = ex2_approx((m_run[hh] - m_new) * c);
-      m_run[hh] = m_new;
-      mc[hh] = m_new * c;
-      l_run[hh] *= alpha[hh];
+      l_run[hh] += __shfl_xor_sync(0xffffffffu, l_run[hh], 1);
+      l_run[hh] += __shfl_xor_sync(0xffffffffu, l_run[hh], 2);
     }
-#pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float pv = ex2_approx(fmaf(s[nt][e], c, -mc[e >> 1]));
-        s[nt][e] = pv;
-        l_run[e >> 1] += pv;
-      }
-    }
+    const float inv0 = 1.f / l_run[0], inv1 = 1.f / l_run[1];
 #pragma unroll
     for (int dn = 0; dn < DH / 8; ++dn) {
-      o[dn][0] *= alpha[0]; o[dn][1] *= alpha[0];
-      o[dn][2] *= alpha[1]; o[dn][3] *= alpha[1];
+      o[dn][0] *= inv0; o[dn][1] *= inv0;
+      o[dn][2] *= inv1; o[dn][3] *= inv1;
     }
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      if (j < nt16) {
-        uint32_t a[4];
-        a[0] = pack_bf16x2(s[2 * j][0], s[2 * j][1]);
-        a[1] = pack_bf16x2(s[2 * j][2], s[2 * j][3]);
-        a[2] = pack_bf16x2(s[2 * j + 1][0], s[2 * j + 1][1]);
-        a[3] = pack_bf16x2(s[2 * j + 1][2], s[2 * j + 1][3]);
-        mma_p_rows<DH>(o, a, sV, kb0 + j * 16, lane);
-      }
+    if (t == 0) {
+      if (q0 + gq < S) lse2[static_cast<size_t>(bh) * S + q0 + gq] = m_run[0] * c + log2f(l_run[0]);
+      if (q0 + gq + 8 < S) lse2[static_cast<size_t>(bh) * S + q0 + gq + 8] = m_run[1] * c + log2f(l_run[1]);
     }
+    store_tile_bf16<DH>(o, sQ, og, q0, S, Dm, lane);
   }
-#pragma unroll
-  for (int hh = 0; hh < 2; ++hh) {
-    l_run[hh] += __shfl_xor_sync(0xffffffffu, l_run[hh], 1);
-    l_run[hh] += __shfl_xor_sync(0xffffffffu, l_run[hh], 2);
-  }
-  const float inv0 = 1.f / l_run[0], inv1 = 1.f / l_run[1];
-#pragma unroll
-  for (int dn = 0; dn < DH / 8; ++dn) {
-    o[dn][0] *= inv0; o[dn][1] *= inv0;
-    o[dn][2] *= inv1; o[dn][3] *= inv1;
-  }
-  if (t == 0) {
-    if (q0 + gq < S) lse2[static_cast<size_t>(bh) * S + q0 + gq] = m_run[0] * c + log2f(l_run[0]);
-    if (q0 + gq + 8 < S) lse2[static_cast<size_t>(bh) * S + q0 + gq + 8] = m_run[1] * c + log2f(l_run[1]);
-  }
-  __nv_bfloat16* og = out + static_cast<size_t>(b) * S * Dm + h * DH;
-  store_tile_bf16<DH>(o, sQ, og, q0, S, Dm, lane);
 }
 
 // ---------------------------------------------------------------------------------------------
 // backward, single pass (S16 <= 256): grid (B*H / HPC); CTA = HPC heads x KT warps, warp = one 16-key tile
 // ---------------------------------------------------------------------------------------------
 template <int DH>
-__global__ void __launch_bounds__(512)
+__global__ void __launch_bounds__(DH == 64 ? 256 : 512, DH == 64 ? 2 : 1)
 attn_bwd_head_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ o_fwd,
                      const __nv_bfloat16* __restrict__ d_out, const float* __restrict__ lse2,
                      __nv_bfloat16* __restrict__ dqkv, int S, int H, int Dm, int HPC, float c, float scale) {
   extern __shared__ __align__(16) uint8_t smem_attn[];
   constexpr int LDS = DH + 8;
-  constexpr int LDQ = DH + 4;                     // f32 dQ rows (padded against bank conflicts)
+  constexpr int LDQ = DH + 8;                     // f32 dQ rows: 64-bit accesses of a half-warp hit 32 distinct banks
   const int S16 = (S + 15) & ~15;
   const int KT = S16 >> 4;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -309,26 +353,27 @@ attn_bwd_head_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16*
   const int bh = blockIdx.x * HPC + hl;
   const int b = bh / H, h = bh % H;
   // per head slot: Q [S16][LDS], dO [S16][LDS], per-warp K and V tiles [16][LDS] each, dQ f32 [S16][LDQ],
-  //                L2 [S16], delta [S16]
+  //                {L2, delta} [S16], per-query-tile step counters [16]
   const size_t slot_bytes = static_cast<size_t>(2 * S16 + KT * 32) * LDS * 2 + static_cast<size_t>(S16) * LDQ * 4 +
-                            static_cast<size_t>(S16) * 8;
+                            static_cast<size_t>(S16) * 8 + 64;
   uint8_t* slot = smem_attn + hl * slot_bytes;
   __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(slot);
   __nv_bfloat16* sdO = sQ + S16 * LDS;
   __nv_bfloat16* sKt = sdO + S16 * LDS + kt * 32 * LDS;
   __nv_bfloat16* sVt = sKt + 16 * LDS;
   float* sdQ = reinterpret_cast<float*>(sdO + S16 * LDS + KT * 32 * LDS);
-  float* sL2 = sdQ + S16 * LDQ;
-  float* sDelta = sL2 + S16;
+  float* sLD = sdQ + S16 * LDQ;                   // interleaved {L2, delta} per query
+  int* sFlag = reinterpret_cast<int*>(sLD + 2 * S16);
   const size_t ld = static_cast<size_t>(3) * Dm;
   const __nv_bfloat16* base = qkv + static_cast<size_t>(b) * S * ld + h * DH;
   const size_t obase = static_cast<size_t>(b) * S * Dm + h * DH;
 
-  load_rows_part<DH>(sQ, base, 0, S, S16, ld, tid_h, tph);
-  load_rows_part<DH>(sdO, d_out + obase, 0, S, S16, Dm, tid_h, tph);
-  load_rows_part<DH>(sKt, base + Dm, kt * 16, S, 16, ld, lane, 32);
-  load_rows_part<DH>(sVt, base + 2 * Dm, kt * 16, S, 16, ld, lane, 32);
+  load_rows_async<DH>(sQ, base, 0, S, S16, ld, tid_h, tph);
+  load_rows_async<DH>(sdO, d_out + obase, 0, S, S16, Dm, tid_h, tph);
+  load_rows_async<DH>(sKt, base + Dm, kt * 16, S, 16, ld, lane, 32);
+  load_rows_async<DH>(sVt, base + 2 * Dm, kt * 16, S, 16, ld, lane, 32);
   for (int i = tid_h; i < S16 * LDQ; i += tph) sdQ[i] = 0.f;
+  if (tid_h < 16) sFlag[tid_h] = 0;
   // delta[q] = sum_j dO[q, j] * O[q, j]; L2 = +inf for padded queries (p = exp2(-inf) = 0)
   {
     constexpr int TPRW = DH / 8;                  // threads per row (16-byte chunks)
@@ -348,17 +393,24 @@ attn_bwd_head_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16*
       // TPRW (4 or 8) consecutive lanes hold one row
 #pragma unroll
       for (int off = TPRW / 2; off > 0; off >>= 1) part += __shfl_xor_sync(0xffffffffu, part, off);
-      if (cch == 0) {
-        sDelta[r] = part;
-        sL2[r] = r < S ? lse2[static_cast<size_t>(bh) * S + r] : INFINITY;
-      }
+      if (cch == 0)
+        *reinterpret_cast<float2*>(sLD + 2 * r) =
+            make_float2(r < S ? lse2[static_cast<size_t>(bh) * S + r] : INFINITY, part);
     }
   }
+  cp_async_wait_all();
   __syncthreads();
 
   uint32_t kf[DH / 16][4], vf[DH / 16][4];
   load_a_frags<DH>(kf, sKt, 0, lane);
   load_a_frags<DH>(vf, sVt, 0, lane);
+  // the K tile as the B operand of dQ += dS K (k = key, n = feature): loop invariant
+  uint32_t kb[DH / 16][4];
+  {
+    const int r = (lane & 7) + ((lane >> 3) & 1) * 8, cc = (lane >> 4) * 8;
+#pragma unroll
+    for (int dp = 0; dp < DH / 16; ++dp) ldsm_x4_trans(kb[dp], smem_u32(sKt + r * LDS + dp * 16 + cc));
+  }
   float dk[DH / 8][4], dv[DH / 8][4];
 #pragma unroll
   for (int i = 0; i < DH / 8; ++i) {
@@ -368,27 +420,52 @@ attn_bwd_head_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16*
   const bool tail_keys = (kt * 16 + 16 > S);       // this warp's tile holds padded keys (warp-uniform)
   const bool key_ok0 = kt * 16 + gq < S, key_ok1 = kt * 16 + gq + 8 < S;
 
-  for (int qt = 0; qt < KT; ++qt) {
-    const int qb0 = qt * 16;
+  // per-lane shared-memory addresses; a step only adds its query-tile offset
+  const uint32_t rowsT = ((lane & 7) + (lane >> 4) * 8) * LDS + ((lane >> 3) & 1) * 8;   // B operand, n = row
+  const uint32_t rowsP = ((lane & 7) + ((lane >> 3) & 1) * 8) * LDS + (lane >> 4) * 8;   // B operand, k = row (.trans)
+  const uint32_t aQ = smem_u32(sQ + rowsT), adO = smem_u32(sdO + rowsT);
+  const uint32_t pQ = smem_u32(sQ + rowsP), pdO = smem_u32(sdO + rowsP);
+  const uint32_t aLD = smem_u32(sLD + 4 * t);          // float2 {L2, delta} of query 2t
+  const uint32_t aDQ = smem_u32(sdQ + gq * LDQ + 2 * t);
+  const uint32_t aFlag = smem_u32(sFlag);
+
+  // Step i: the warp of key tile kt works on query tile (kt + i) % KT, so within a step no two warps of a
+  // head touch the same dQ rows and the accumulation is a plain read-modify-write (no shared atomics --
+  // red.shared.add.f32 compiles to a CAS loop).  Tile q was last updated by warp kt+1 in step i-1: a per-tile
+  // step counter (release / acquire in shared memory) orders the two, no CTA-wide barrier in the loop.
+  int qt = kt;
+#pragma unroll 1
+  for (int step = 0; step < KT; ++step) {
+    const uint32_t qoff = static_cast<uint32_t>(qt) * (16 * LDS * 2);
     float st[2][4], dpt[2][4];
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
       st[i][0] = st[i][1] = st[i][2] = st[i][3] = 0.f;
       dpt[i][0] = dpt[i][1] = dpt[i][2] = dpt[i][3] = 0.f;
     }
-    mma_a_rowsT<DH, 2>(st, kf, sQ, qb0, lane);      // S^T  = K Q^T   [16 keys x 16 queries]
-    mma_a_rowsT<DH, 2>(dpt, vf, sdO, qb0, lane);    // dP^T = V dO^T
+#pragma unroll
+    for (int kk = 0; kk < DH / 16; ++kk) {
+      uint32_t bq[4], bo[4];
+      ldsm_x4(bq, aQ + qoff + kk * 32);
+      ldsm_x4(bo, adO + qoff + kk * 32);
+      mma_bf16(st[0], kf[kk], bq[0], bq[1]);        // S^T  = K Q^T   [16 keys x 16 queries]
+      mma_bf16(st[1], kf[kk], bq[2], bq[3]);
+      mma_bf16(dpt[0], vf[kk], bo[0], bo[1]);       // dP^T = V dO^T
+      mma_bf16(dpt[1], vf[kk], bo[2], bo[3]);
+    }
     uint32_t pa[4], da[4];
 #pragma unroll
     for (int nt = 0; nt < 2; ++nt) {
-      const float2 l2 = *reinterpret_cast<const float2*>(sL2 + qb0 + nt * 8 + 2 * t);
-      const float2 dl = *reinterpret_cast<const float2*>(sDelta + qb0 + nt * 8 + 2 * t);
+      // {L2, delta} of queries 2t and 2t+1 of this 8-query group
+      const uint4 ldv = ld_shared_u4(aLD + static_cast<uint32_t>(qt * 16 + nt * 8) * 8);
+      const float l2a = __uint_as_float(ldv.x), dla = __uint_as_float(ldv.y);
+      const float l2b = __uint_as_float(ldv.z), dlb = __uint_as_float(ldv.w);
       float pv[4], dsv[4];
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        const float p = ex2_approx(fmaf(st[nt][e], c, -((e & 1) ? l2.y : l2.x)));
+        const float p = ex2_approx(fmaf(st[nt][e], c, -((e & 1) ? l2b : l2a)));
         pv[e] = p;
-        dsv[e] = p * (dpt[nt][e] - ((e & 1) ? dl.y : dl.x));
+        dsv[e] = p * (dpt[nt][e] - ((e & 1) ? dlb : dla));
       }
       if (tail_keys) {
         if (!key_ok0) { pv[0] = pv[1] = 0.f; dsv[0] = dsv[1] = 0.f; }
@@ -399,8 +476,16 @@ attn_bwd_head_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16*
       da[nt * 2 + 0] = pack_bf16x2(dsv[0], dsv[1]);
       da[nt * 2 + 1] = pack_bf16x2(dsv[2], dsv[3]);
     }
-    mma_p_rows<DH>(dv, pa, sdO, qb0, lane);         // dV += P^T dO
-    mma_p_rows<DH>(dk, da, sQ, qb0, lane);          // dK += dS^T Q   (x scale at the end)
+#pragma unroll
+    for (int dp = 0; dp < DH / 16; ++dp) {
+      uint32_t bo[4], bq[4];
+      ldsm_x4_trans(bo, pdO + qoff + dp * 32);
+      ldsm_x4_trans(bq, pQ + qoff + dp * 32);
+      mma_bf16(dv[2 * dp], pa, bo[0], bo[1]);       // dV += P^T dO
+      mma_bf16(dv[2 * dp + 1], pa, bo[2], bo[3]);
+      mma_bf16(dk[2 * dp], da, bq[0], bq[1]);       // dK += dS^T Q   (x scale at the end)
+      mma_bf16(dk[2 * dp + 1], da, bq[2], bq[3]);
+    }
     // dQ[16 q, :] += dS[16 q x 16 keys] K[16 keys, :]: transpose the dS^T fragments in registers
     uint32_t dst[4];
     dst[0] = movmatrix_trans(da[0]);
@@ -410,17 +495,35 @@ attn_bwd_head_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16*
     float dq[DH / 8][4];
 #pragma unroll
     for (int i = 0; i < DH / 8; ++i) dq[i][0] = dq[i][1] = dq[i][2] = dq[i][3] = 0.f;
-    mma_p_rows<DH>(dq, dst, sKt, 0, lane);
-    float* q_lo = sdQ + (qb0 + gq) * LDQ + 2 * t;
-    float* q_hi = q_lo + 8 * LDQ;
 #pragma unroll
-    for (int dn = 0; dn < DH / 8; ++dn) {
-      red_shared_add(q_lo + dn * 8, dq[dn][0]);
-      red_shared_add(q_lo + dn * 8 + 1, dq[dn][1]);
-      red_shared_add(q_hi + dn * 8, dq[dn][2]);
-      red_shared_add(q_hi + dn * 8 + 1, dq[dn][3]);
+    for (int dp = 0; dp < DH / 16; ++dp) {
+      mma_bf16(dq[2 * dp], dst, kb[dp][0], kb[dp][1]);
+      mma_bf16(dq[2 * dp + 1], dst, kb[dp][2], kb[dp][3]);
     }
+    // wait until the previous owner of this query tile (step - 1) has published its update
+    {
+      const uint32_t fa = aFlag + qt * 4;
+      uint32_t seen;
+      do {
+        asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(seen) : "r"(fa) : "memory");
+      } while (static_cast<int>(seen) < step);
+      const uint32_t qlo = aDQ + static_cast<uint32_t>(qt) * (16 * LDQ * 4);
+      const uint32_t qhi = qlo + 8 * LDQ * 4;
+#pragma unroll
+      for (int dn = 0; dn < DH / 8; ++dn) {
+        float2 lo = ld_shared_f2(qlo + dn * 32);
+        float2 hi = ld_shared_f2(qhi + dn * 32);
+        lo.x += dq[dn][0]; lo.y += dq[dn][1];
+        hi.x += dq[dn][2]; hi.y += dq[dn][3];
+        st_shared_f2(qlo + dn * 32, lo);
+        st_shared_f2(qhi + dn * 32, hi);
+      }
+      __syncwarp();
+      if (lane == 0) asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(fa), "r"(step + 1) : "memory");
+    }
+    qt = (qt + 1 == KT) ? 0 : qt + 1;
   }
+  __syncthreads();      // every dQ tile has received all KT updates
 #pragma unroll
   for (int i = 0; i < DH / 8; ++i) {
     dk[i][0] *= scale; dk[i][1] *= scale; dk[i][2] *= scale; dk[i][3] *= scale;
@@ -430,8 +533,7 @@ attn_bwd_head_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16*
   // both tiles go out through this warp's private K-tile scratch (its fragments are already in registers)
   store_tile_bf16<DH>(dk, sKt, dkg, kt * 16, S, ld, lane);
   store_tile_bf16<DH>(dv, sKt, dvg, kt * 16, S, ld, lane);
-  __syncthreads();
-  // dQ = scale * sum over key tiles, written once
+  // dQ = scale * sum over key tiles, written once (the last step's barrier already ordered the accumulation)
   {
     __nv_bfloat16* dqg = dqkv + static_cast<size_t>(b) * S * ld + h * DH;
     constexpr int CH = DH / 8;
@@ -631,6 +733,8 @@ attn_bwd_dkv_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* 
 template <typename K>
 int set_smem(K kern, size_t bytes, size_t* configured, const char* name) {
   if (bytes <= *configured) return CSM_OK;
+  // these kernels want as many co-resident CTAs as shared memory allows: ask for the full carve-out
+  cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   if (bytes > 227 * 1024) {
     csm_set_error("%s: sequence too long for the whole-head-in-shared-memory kernel (%zu bytes needed)", name, bytes);
     return CSM_ERR_ARG;
@@ -649,19 +753,24 @@ int attn_fwd_launch(const void* qkv, void* out, float* lse, int B, int S, int H,
   const int Dm = H * DH;
   const int S16 = (S + 15) & ~15;
   const int QT = S16 >> 4;
-  int HPC = QT >= 8 ? 1 : 8 / QT;
+  // CTAs of at most 8 warps (so that 2-3 of them co-reside and one CTA's staging overlaps another's math):
+  // HPC heads per CTA for short sequences, QPW query tiles per warp for long ones
+  int HPC = QT >= 8 ? 1 : (QT >= 4 ? 2 : 4);
   while (HPC > 1 && (B * H) % HPC != 0) --HPC;
-  int QW = 16 / HPC;
-  if (QW > QT) QW = QT;
-  const size_t smem = static_cast<size_t>(HPC) * (2 * S16 + QW * 16) * (DH + 8) * 2;
+  const int wmax = 8 / HPC;
+  int QPW = (QT + wmax - 1) / wmax;
+  if (QPW > 4) QPW = 4;
+  int QW = (QT + QPW - 1) / QPW;
+  if (QW > wmax) QW = wmax;
+  const size_t smem = static_cast<size_t>(HPC) * (2 * S16 + QW * QPW * 16) * (DH + 8) * 2;
   static size_t cfg_fwd = 0;
   int rc = set_smem(attn_fwd_kernel<DH>, smem, &cfg_fwd, "attention_fwd");
   if (rc) return rc;
   const float c = 1.4426950408889634f / sqrtf(static_cast<float>(DH));
-  dim3 grid(B * H / HPC, (QT + QW - 1) / QW);
+  dim3 grid(B * H / HPC, (QT + QW * QPW - 1) / (QW * QPW));
   attn_fwd_kernel<DH><<<grid, HPC * QW * 32, smem, stream>>>(reinterpret_cast<const __nv_bfloat16*>(qkv),
                                                              reinterpret_cast<__nv_bfloat16*>(out), lse, S, H, Dm, HPC,
-                                                             QW, c);
+                                                             QW, QPW, c);
   CSM_CHECK_LAUNCH("attention_fwd");
   return CSM_OK;
 }
@@ -673,12 +782,15 @@ int attn_bwd_launch(const void* qkv, const void* o, const void* d_out, const flo
   const float scale = 1.0f / sqrtf(static_cast<float>(DH));
   const float c = 1.4426950408889634f * scale;
   const int S16 = (S + 15) & ~15;
-  if (S16 <= 256) {
+  if (S16 <= (DH == 64 ? 128 : 256)) {
     const int KT = S16 >> 4;
-    int HPC = KT >= 8 ? 1 : 8 / KT;
-    while (HPC > 1 && (B * H) % HPC != 0) --HPC;
-    const size_t slot = static_cast<size_t>(2 * S16 + KT * 32) * (DH + 8) * 2 + static_cast<size_t>(S16) * (DH + 4) * 4 +
-                        static_cast<size_t>(S16) * 8;
+    const int max_warps = DH == 64 ? 8 : 16;       // the kernel's launch bound
+    int HPC = 8 / KT;                               // heads per CTA for short sequences (<= 8 warps)
+    if (HPC < 1) HPC = 1;
+    if (HPC > 4) HPC = 4;
+    while (HPC > 1 && ((B * H) % HPC != 0 || HPC * KT > max_warps)) --HPC;
+    const size_t slot = static_cast<size_t>(2 * S16 + KT * 32) * (DH + 8) * 2 + static_cast<size_t>(S16) * (DH + 8) * 4 +
+                        static_cast<size_t>(S16) * 8 + 64;
     static size_t cfg_head = 0;
     int rc = set_smem(attn_bwd_head_kernel<DH>, slot * HPC, &cfg_head, "attention_bwd");
     if (rc) return rc;

@@ -640,12 +640,26 @@ int launch_gemm(const void* a, uint64_t a_inner, uint64_t a_outer, const void* b
     if (B_MN && p.bn < 128) p.bn = 128;
     p.tiles_n = csm_cdiv(N, p.bn);
     const int tiles = p.tiles_m * p.tiles_n;
-    int splits = (clusters + tiles - 1) / tiles;
-    int max_splits = p.num_kb / 4;               // keep >= 4 k-blocks per unit
+    // split the reduction so that the units fill whole rounds of `clusters`: best fill wins, fewer splits
+    // (less reduce-add traffic) break ties; at least 4 k-blocks per unit
+    int max_splits = p.num_kb / 4;
     if (max_splits < 1) max_splits = 1;
-    if (splits > max_splits) splits = max_splits;
-    if (splits < 1) splits = 1;
-    p.kb_per_split = csm_cdiv(p.num_kb, splits);
+    int best_splits = 1;
+    double best_fill = -1.0;
+    for (int sp = 1; sp <= max_splits && tiles * sp <= 4 * clusters; ++sp) {
+      const int kbs = csm_cdiv(p.num_kb, sp);
+      const int real = csm_cdiv(p.num_kb, kbs);
+      const long long units = static_cast<long long>(tiles) * real;
+      const long long rounds = (units + clusters - 1) / clusters;
+      // time ~ rounds * k-blocks per unit (+ a fixed cost per unit for prologue / epilogue ~ 6 k-blocks)
+      const double t = static_cast<double>(rounds) * (kbs + 6);
+      const double fill = 1.0 / t;
+      if (fill > best_fill * 1.03) {
+        best_fill = fill;
+        best_splits = real;
+      }
+    }
+    p.kb_per_split = csm_cdiv(p.num_kb, best_splits);
     p.splits = csm_cdiv(p.num_kb, p.kb_per_split);
   } else {
     p.bn = choose_bn(M, N, clusters, B_MN);
