@@ -259,17 +259,41 @@ def main():
         l_.backward()
     ms_fwd_bwd = timed(fwd_bwd, max(3, args.steps // 2))
 
-    # end to end: host batch -> H2D -> step -> loss.item()
-    def e2e_step():
-        x1 = host1.to(dev, non_blocking=True)
-        x2 = host2.to(dev, non_blocking=True)
-        return step(x1, x2).item()
-    for _ in range(2):
-        e2e_step()
-    ms_e2e = timed(e2e_step, args.steps)
+    # host-side cost of enqueueing one step (no synchronisation inside): if this approaches ms_per_step the
+    # path is launch-bound on the CPU
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(5):
+        step(imgs1, imgs2)
+    host_ms = (time.perf_counter() - t0) / 5 * 1e3
+    torch.cuda.synchronize()
+
+    # end to end through the public API: every step's batch starts in pinned HOST memory, is copied to the
+    # device (csmae_b200.DevicePrefetcher: the copy of step i+1 runs on a side stream while step i trains),
+    # trains, and the loss is read back to the host
+    from csmae_b200 import DevicePrefetcher
+
+    def e2e_run(k):
+        last = None
+        for x1, x2 in DevicePrefetcher(((host1, host2) for _ in range(k)), dev):
+            last = step(x1, x2).item()
+        return last
+    e2e_run(3)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    e2e_run(args.steps)
+    e1.record()
+    barrier()
+    ms_e2e = e0.elapsed_time(e1) / args.steps
+    if world > 1:
+        t = torch.tensor([ms_e2e], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_e2e = t.item()
     sampler.stop_flag.set()
 
     # per-kernel breakdown of one step with CUDA events on the launching stream (outside the timed region)
+    model._engine.use_graphs = False          # the breakdown times each C-ABI call eagerly
     breakdown = kernel_breakdown(_native, lambda: step(imgs1, imgs2)) if rank == 0 else None
 
     if rank != 0:
@@ -293,7 +317,7 @@ def main():
     line = {"metric": METRIC, "value": ips, "unit": "images/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": workload_config(args, B, world),
-            "fwd_bwd_ms": ms_fwd_bwd, "gpu_launches": launches,
+            "fwd_bwd_ms": ms_fwd_bwd, "host_enqueue_ms_per_step": host_ms, "gpu_launches": launches,
             "e2e": {"value": ips_e2e, "unit": "images/s", "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": int(host1.numel() * 4 * 2), "d2h_bytes_per_step": 4},
             "clocks": sampler.summary(), "roofline": roofline,

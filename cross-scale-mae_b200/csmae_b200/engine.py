@@ -12,10 +12,17 @@ Precision policy (independent of the ambient autocast state, SURVEY.md 0.8 / 8a'
 weights and residual stream, bf16 tensor-core operands with fp32 accumulation, Linear outputs rounded
 to bf16 where the reference's autocast graph rounds them, LayerNorm / softmax / losses in fp32.
 
+Launch overhead: a step is ~640 kernels; after two eager warm-up steps per (shape, mode) the forward chain and the
+backward chain are each captured into a CUDA graph (torch.cuda.CUDAGraph over the same C-ABI launches, PDL edges
+included) and replayed -- inputs are copied into static buffers, the masking noise is still drawn by the caller from
+the global generator.  CSMAE_CUDA_GRAPHS=0 keeps every step eager.
+
 Memory: activations needed by the backward live in a per-model workspace that is reused every step
 (the backward of step i always precedes the forward of step i+1).  A generation counter makes a
 stale backward fail loudly instead of reading overwritten activations.
 """
+import os
+
 import torch
 
 from . import _native as nat
@@ -47,6 +54,10 @@ class HotPathEngine:
         self._coefs = None
         self._coefs_key = None
         self._last_out = None
+        self.use_graphs = os.environ.get("CSMAE_CUDA_GRAPHS", "1") != "0"
+        self._graphs = {}           # key -> dict(fwd graph, outputs, state, static inputs, bwd graph, ...)
+        self._warm = {}             # key -> eager steps seen so far
+        self.graph_warmup_steps = 2
 
     # ------------------------------------------------------------------ parameters
     def param_names(self):
@@ -104,10 +115,61 @@ class HotPathEngine:
 
     # ------------------------------------------------------------------ forward
     def forward(self, imgs_list, noises, mask_ratio, training):
-        m = self.model
         dev = imgs_list[0].device
         if dev.type != "cuda":
             raise nat.NativeError("csmae_b200 runs on sm_100 CUDA devices only (no CPU fallback): got " + str(dev))
+        params = dict(self.model.named_parameters())
+        self._refresh_weights(params)            # outside any graph: runs only when a master weight changed
+        if not self.use_graphs or torch.cuda.is_current_stream_capturing():
+            return self._forward_eager(imgs_list, noises, mask_ratio, training)
+        key = self._graph_key(imgs_list, noises, mask_ratio, training, params)
+        entry = self._graphs.get(key)
+        if entry is None:
+            seen = self._warm.get(key, 0)
+            if seen < self.graph_warmup_steps:
+                self._warm[key] = seen + 1
+                return self._forward_eager(imgs_list, noises, mask_ratio, training)
+            entry = self._capture_forward(key, imgs_list, noises, mask_ratio, training)
+        for dst, src in zip(entry["imgs"], imgs_list):
+            dst.copy_(src, non_blocking=True)
+        for dst, src in zip(entry["noise"], noises):
+            dst.copy_(src, non_blocking=True)
+        entry["fwd"].replay()
+        nat.launch_count += entry["fwd_launches"]
+        self.generation += 1
+        entry["state"]["generation"] = self.generation
+        self._state = entry["state"]
+        self._active_graph = entry
+        return entry["out"]
+
+    def _graph_key(self, imgs_list, noises, mask_ratio, training, params):
+        return (tuple(tuple(im.shape) for im in imgs_list), float(mask_ratio), bool(training),
+                imgs_list[0].device.index, tuple(p.data_ptr() for p in params.values()),
+                tuple(b.data_ptr() for b in self.model.buffers()))
+
+    def _capture_forward(self, key, imgs_list, noises, mask_ratio, training):
+        if len(self._graphs) >= 4:               # shapes keep changing: stop hoarding graphs
+            self._graphs.clear()
+        entry = dict(imgs=[torch.empty_like(im, dtype=torch.float32).contiguous() for im in imgs_list],
+                     noise=[torch.empty_like(nz, dtype=torch.float32).contiguous() for nz in noises], bwd=None)
+        for dst, src in zip(entry["imgs"], imgs_list):
+            dst.copy_(src)
+        for dst, src in zip(entry["noise"], noises):
+            dst.copy_(src)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        c0 = nat.launch_count
+        with torch.cuda.graph(g):
+            out = self._forward_eager(entry["imgs"], entry["noise"], mask_ratio, training)
+        entry["fwd_launches"] = nat.launch_count - c0      # kernels recorded, not run: counted at each replay
+        nat.launch_count = c0
+        entry["fwd"], entry["out"], entry["state"] = g, out, self._state
+        self._graphs[key] = entry
+        return entry
+
+    def _forward_eager(self, imgs_list, noises, mask_ratio, training):
+        m = self.model
+        dev = imgs_list[0].device
         nsm = nat.sm_count(dev)
         ns = len(imgs_list)
         N, C, H, W = imgs_list[0].shape
@@ -121,9 +183,10 @@ class HotPathEngine:
         P = p * p * C
         bf16, f32 = torch.bfloat16, torch.float32
         params = dict(m.named_parameters())
-        w16 = self._refresh_weights(params)
+        w16 = self._w16_views
         buf = lambda name, shape, dt: self._buf(name, shape, dt, dev)
         imgs_list = [im.contiguous().float() for im in imgs_list]
+        self._active_graph = None
 
         self.generation += 1
         st = dict(N=N, ns=ns, NB=NB, L=L, keep=keep, Se=Se, Sd=Sd, D=D, Dd=Dd, C=C, H=H, p=p, P=P, nsm=nsm,
@@ -266,6 +329,47 @@ class HotPathEngine:
             raise RuntimeError(
                 "csmae_b200: backward() of a forward whose activations were overwritten by a later forward of the "
                 "same module (the workspace holds one step); call backward before the next forward")
+        entry = getattr(self, "_active_graph", None)
+        if entry is None:
+            flat, views = self._backward_eager(grad_loss, None)
+            self._state = None
+            return views
+        # graphed step: the gradient chain is captured once over static buffers; what autograd receives is a
+        # copy of the flat gradient buffer (one 4 B/param device copy), so .grad never aliases graph memory
+        if entry["bwd"] is None:
+            entry["g"] = torch.zeros(1, dtype=torch.float32, device=grad_loss.device)
+            entry["g"].copy_(grad_loss.detach().reshape(1))
+            names = self.param_names()
+            params = dict(self.model.named_parameters())
+            sizes = [params[n].numel() for n in names]
+            total = sum((s_ + 3) // 4 * 4 for s_ in sizes)
+            entry["flat"] = torch.zeros(total, dtype=torch.float32, device=grad_loss.device)
+            entry["dense"] = all(s_ % 4 == 0 for s_ in sizes)
+            entry["like"] = [params[n] for n in names]
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            c0 = nat.launch_count
+            with torch.cuda.graph(g):
+                self._backward_eager(entry["g"], entry["flat"])
+            entry["bwd_launches"] = nat.launch_count - c0
+            nat.launch_count = c0
+            entry["bwd"] = g
+            self._state = st                   # capture does not run the kernels; replay below does
+        entry["g"].copy_(grad_loss.detach().reshape(1), non_blocking=True)
+        entry["bwd"].replay()
+        nat.launch_count += entry["bwd_launches"]
+        self._state = None
+        out = entry["flat"].clone()
+        if entry["dense"]:
+            return list(torch._utils._unflatten_dense_tensors(out, entry["like"]))
+        views, off = [], 0
+        for p in entry["like"]:
+            views.append(out[off:off + p.numel()].view(p.shape))
+            off += (p.numel() + 3) // 4 * 4
+        return views
+
+    def _backward_eager(self, grad_loss, flat):
+        st = self._state
         m = self.model
         N, ns, NB, L, keep, Se, Sd = (st[k] for k in ("N", "ns", "NB", "L", "keep", "Se", "Sd"))
         D, Dd, C, H, p, P, nsm = (st[k] for k in ("D", "Dd", "C", "H", "p", "P", "nsm"))
@@ -281,7 +385,10 @@ class HotPathEngine:
         for s_ in sizes:
             offs.append(total)
             total += (s_ + 3) // 4 * 4                         # keep every gradient 16-byte aligned
-        flat = torch.zeros(total, dtype=f32, device=dev)
+        if flat is None:
+            flat = torch.zeros(total, dtype=f32, device=dev)
+        else:
+            flat.zero_()
         G = {n: flat[o:o + s_].view(params[n].shape) for n, o, s_ in zip(names, offs, sizes)}
         g = grad_loss.detach().reshape(1).to(f32).contiguous()
         norm_pix = 1 if m.norm_pix_loss else 0
@@ -352,8 +459,7 @@ class HotPathEngine:
         call("csm_cls_grad", eres, G["cls_token"], NB, Se, D)
         call("csm_linear_wgrad", eres16, B["patches"], G["patch_embed.proj.weight"], rows_e, D, P, nsm)
         call("csm_colsum_bf16", eres16, G["patch_embed.proj.bias"], rows_e, D, Se, nsm)
-        self._state = None
-        return [G[n] for n in names]
+        return flat, [G[n] for n in names]
 
     def _blocks_bwd(self, tag, pname, nlayers, dres, dres16, NB, S, Dm, heads, params, w16, G, dev, nsm,
                     top_bias_done):
@@ -405,7 +511,7 @@ class CrossScaleStep(torch.autograd.Function):
         ctx.generation = engine.generation
         ctx.n_params = len(params)
         engine._last_out = out
-        return out["loss"]
+        return out["loss"].clone()          # a fresh scalar per step: the accumulator it came from is reused
 
     @staticmethod
     def backward(ctx, grad_loss):

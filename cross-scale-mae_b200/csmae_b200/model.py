@@ -196,7 +196,7 @@ class MAE_ViT_Baseline(nn.Module):
             out = eng._last_out
         else:
             out = eng.forward(imgs_list, noises, mask_ratio, self.training)
-            loss = out["loss"]
+            loss = out["loss"].clone()
         return loss, out
 
     def forward(self, imgs, mask_ratio=0.75, mask_seed=None, return_embeds=False, noise=None):

@@ -217,6 +217,8 @@ attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict
   const int tid_h = threadIdx.x - hl * tph;
   const int qt_begin = blockIdx.y * QW * QPW;
   const int qt_end = min(QT, qt_begin + QW * QPW);
+  pdl_wait();
+  pdl_trigger();
   load_rows_async<DH>(sK, base + Dm, 0, S, S16, ld, tid_h, tph);
   load_rows_async<DH>(sV, base + 2 * Dm, 0, S, S16, ld, tid_h, tph);
   for (int qt = qt_begin + wq, i = 0; qt < qt_end; qt += QW, ++i)
@@ -368,6 +370,8 @@ attn_bwd_head_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16*
   const __nv_bfloat16* base = qkv + static_cast<size_t>(b) * S * ld + h * DH;
   const size_t obase = static_cast<size_t>(b) * S * Dm + h * DH;
 
+  pdl_wait();
+  pdl_trigger();
   load_rows_async<DH>(sQ, base, 0, S, S16, ld, tid_h, tph);
   load_rows_async<DH>(sdO, d_out + obase, 0, S, S16, Dm, tid_h, tph);
   load_rows_async<DH>(sKt, base + Dm, kt * 16, S, 16, ld, lane, 32);
@@ -768,10 +772,13 @@ int attn_fwd_launch(const void* qkv, void* out, float* lse, int B, int S, int H,
   if (rc) return rc;
   const float c = 1.4426950408889634f / sqrtf(static_cast<float>(DH));
   dim3 grid(B * H / HPC, (QT + QW * QPW - 1) / (QW * QPW));
-  attn_fwd_kernel<DH><<<grid, HPC * QW * 32, smem, stream>>>(reinterpret_cast<const __nv_bfloat16*>(qkv),
-                                                             reinterpret_cast<__nv_bfloat16*>(out), lse, S, H, Dm, HPC,
-                                                             QW, QPW, c);
-  CSM_CHECK_LAUNCH("attention_fwd");
+  cudaError_t le = csm_launch_pdl(attn_fwd_kernel<DH>, grid, dim3(HPC * QW * 32), smem, stream,
+                                  reinterpret_cast<const __nv_bfloat16*>(qkv), reinterpret_cast<__nv_bfloat16*>(out), lse,
+                                  S, H, Dm, HPC, QW, QPW, c);
+  if (le != cudaSuccess) {
+    csm_set_error("attention_fwd: launch failed: %s", cudaGetErrorString(le));
+    return CSM_ERR_CUDA;
+  }
   return CSM_OK;
 }
 
@@ -794,11 +801,14 @@ int attn_bwd_launch(const void* qkv, const void* o, const void* d_out, const flo
     static size_t cfg_head = 0;
     int rc = set_smem(attn_bwd_head_kernel<DH>, slot * HPC, &cfg_head, "attention_bwd");
     if (rc) return rc;
-    attn_bwd_head_kernel<DH><<<B * H / HPC, HPC * KT * 32, slot * HPC, stream>>>(
-        reinterpret_cast<const __nv_bfloat16*>(qkv), reinterpret_cast<const __nv_bfloat16*>(o),
-        reinterpret_cast<const __nv_bfloat16*>(d_out), lse, reinterpret_cast<__nv_bfloat16*>(dqkv), S, H, Dm, HPC, c,
-        scale);
-    CSM_CHECK_LAUNCH("attention_bwd");
+    cudaError_t le = csm_launch_pdl(attn_bwd_head_kernel<DH>, dim3(B * H / HPC), dim3(HPC * KT * 32), slot * HPC, stream,
+                                    reinterpret_cast<const __nv_bfloat16*>(qkv), reinterpret_cast<const __nv_bfloat16*>(o),
+                                    reinterpret_cast<const __nv_bfloat16*>(d_out), lse,
+                                    reinterpret_cast<__nv_bfloat16*>(dqkv), S, H, Dm, HPC, c, scale);
+    if (le != cudaSuccess) {
+      csm_set_error("attention_bwd: launch failed: %s", cudaGetErrorString(le));
+      return CSM_ERR_CUDA;
+    }
     return CSM_OK;
   }
   CSM_CHECK_ARG(delta != nullptr, "csm_attention_bwd: S=%d needs the delta scratch buffer", S);

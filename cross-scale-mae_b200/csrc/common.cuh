@@ -40,10 +40,36 @@ void csm_set_error(const char* fmt, ...);
 static inline int csm_cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 #ifdef __CUDACC__
+// Launch with programmatic dependent launch (PDL): the grid may be scheduled while the previous kernel of the
+// stream is still draining; every kernel launched this way calls csm::pdl_wait() before it touches global
+// memory, so only its launch latency and prologue overlap the predecessor's tail (~600 dependent launches/step).
+template <typename... KArgs, typename... Args>
+inline cudaError_t csm_launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                  Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+#endif
+
+#ifdef __CUDACC__
 // ---------------------------------------------------------------------------------------------
 // small device utilities
 // ---------------------------------------------------------------------------------------------
 namespace csm {
+
+// PDL: block until the preceding kernel of the stream has completed and its writes are visible / allow the
+// next kernel of the stream to be scheduled (it blocks in its own pdl_wait until this grid has finished).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));

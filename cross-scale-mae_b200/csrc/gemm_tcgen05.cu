@@ -222,6 +222,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // everything above (barrier init, TMEM allocation, descriptor prefetch) overlapped the previous kernel's tail
+  pdl_wait();
+  pdl_trigger();
 
   if (warp == 0) {
     // ------------------------------ TMA producer (both CTAs) ------------------------------
@@ -687,8 +690,11 @@ int launch_gemm(const void* a, uint64_t a_inner, uint64_t a_outer, const void* b
   }
   const int units = p.tiles_m * p.tiles_n * p.splits;
   const int grid = 2 * (units < clusters ? units : clusters);
-  kern<<<grid, GEMM_THREADS, SMEM_TOTAL, stream>>>(ta, tb, to, tx, p);
-  CSM_CHECK_LAUNCH("gemm_tcgen05");
+  cudaError_t le = csm_launch_pdl(kern, dim3(grid), dim3(GEMM_THREADS), SMEM_TOTAL, stream, ta, tb, to, tx, p);
+  if (le != cudaSuccess) {
+    csm_set_error("gemm_tcgen05: launch failed: %s", cudaGetErrorString(le));
+    return CSM_ERR_CUDA;
+  }
   return CSM_OK;
 }
 

@@ -21,6 +21,8 @@ __global__ void layernorm_fwd_kernel(const float* __restrict__ x, const float* _
   const int warps = blockDim.x >> 5;
   const int row = blockIdx.x * warps + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
+  pdl_wait();
+  pdl_trigger();
   if (row >= rows) return;
   const float* xr = x + static_cast<size_t>(row) * D;
   float4 v[LN_MAX_VEC];
@@ -102,6 +104,8 @@ layernorm_bwd_tile_kernel(const __nv_bfloat16* __restrict__ dy_bf16, const float
   const int wir = ct >> 5;                            // warp index inside the row
   const int lane = threadIdx.x & 31;
   const int col = ct * 4;
+  pdl_wait();
+  pdl_trigger();
   const float4 gm = *reinterpret_cast<const float4*>(gamma + col);
   float4 ag = make_float4(0.f, 0.f, 0.f, 0.f), ab = ag, ac = ag;
 
@@ -310,6 +314,8 @@ __global__ void colsum_bf16_kernel(const __nv_bfloat16* __restrict__ dy, float* 
   __shared__ float s[8][256 + 8];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int col = blockIdx.x * 256 + tx * 8;
+  pdl_wait();
+  pdl_trigger();
   float acc[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) acc[j] = 0.f;
@@ -395,9 +401,12 @@ extern "C" int csm_layernorm_fwd(const float* x, const float* gamma, const float
   CSM_CHECK_ARG(rows > 0 && D > 0 && D % 4 == 0 && D <= LN_MAX_VEC * 128,
                 "csm_layernorm_fwd: D must be a multiple of 4 and <= %d (rows=%d D=%d)", LN_MAX_VEC * 128, rows, D);
   const int wpb = 8;
-  layernorm_fwd_kernel<<<csm_cdiv(rows, wpb), wpb * 32, 0, stream>>>(
-      x, gamma, beta, reinterpret_cast<__nv_bfloat16*>(out_bf16), out_f32, mean, rstd, rows, D, eps);
-  CSM_CHECK_LAUNCH("layernorm_fwd");
+  cudaError_t le = csm_launch_pdl(layernorm_fwd_kernel, dim3(csm_cdiv(rows, wpb)), dim3(wpb * 32), 0, stream, x, gamma,
+                                  beta, reinterpret_cast<__nv_bfloat16*>(out_bf16), out_f32, mean, rstd, rows, D, eps);
+  if (le != cudaSuccess) {
+    csm_set_error("layernorm_fwd: launch failed: %s", cudaGetErrorString(le));
+    return CSM_ERR_CUDA;
+  }
   return CSM_OK;
 }
 
@@ -418,9 +427,9 @@ void launch_ln_bwd_tile(const void* dy_bf16, const float* dy2_f32, const float* 
   int grid = csm_cdiv(rows, RPI);
   const int cap = num_sms * ctas_per_sm;               // exactly one resident wave
   if (grid > cap) grid = cap;
-  layernorm_bwd_tile_kernel<TPR><<<grid, THREADS, 0, stream>>>(
-      reinterpret_cast<const __nv_bfloat16*>(dy_bf16), dy2_f32, x, mean, rstd, gamma, dres_in, dres_out,
-      reinterpret_cast<__nv_bfloat16*>(dres_bf16), dgamma, dbeta, dcolsum, rows);
+  csm_launch_pdl(layernorm_bwd_tile_kernel<TPR>, dim3(grid), dim3(THREADS), 0, stream,
+                 reinterpret_cast<const __nv_bfloat16*>(dy_bf16), dy2_f32, x, mean, rstd, gamma, dres_in, dres_out,
+                 reinterpret_cast<__nv_bfloat16*>(dres_bf16), dgamma, dbeta, dcolsum, rows);
 }
 
 extern "C" int csm_layernorm_bwd(const void* dy_bf16, const float* dy2_f32, const float* x, const float* mean,
@@ -471,9 +480,12 @@ extern "C" int csm_colsum_bf16(const void* dy_bf16, float* db, int rows, int N, 
   int gy = csm_cdiv(2 * num_sms, gx);
   const int max_gy = csm_cdiv(rows, 8);
   if (gy > max_gy) gy = max_gy;
-  colsum_bf16_kernel<<<dim3(gx, gy), 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(dy_bf16), db, rows, N,
-                                                       skip_period);
-  CSM_CHECK_LAUNCH("colsum_bf16");
+  cudaError_t le = csm_launch_pdl(colsum_bf16_kernel, dim3(gx, gy), dim3(256), 0, stream,
+                                  reinterpret_cast<const __nv_bfloat16*>(dy_bf16), db, rows, N, skip_period);
+  if (le != cudaSuccess) {
+    csm_set_error("colsum_bf16: launch failed: %s", cudaGetErrorString(le));
+    return CSM_ERR_CUDA;
+  }
   return CSM_OK;
 }
 

@@ -175,3 +175,50 @@ def test_stale_backward_fails_loudly():
     l3, pred, mask = m(x1, mask_ratio=0.75)
     l3.backward()
     assert torch.isfinite(l3) and pred.shape == (4, 16, 768) and mask.shape == (4, 16)
+
+
+def test_cuda_graph_replay_matches_eager():
+    """After two eager warm-up steps the forward and backward chains are replayed from CUDA graphs
+    (engine.py); same inputs and noise must give the same loss / outputs / gradients as the eager steps
+    (identical kernels; only fp32 atomic accumulation order may differ), and new inputs must flow through
+    the static buffers."""
+    import csmae_b200
+    torch.manual_seed(0)
+    cfg = dict(dim_model=128, encoder_num_layers=2, encoder_num_heads=2, decoder_embed_dim=64, decoder_num_layers=2,
+               decoder_num_heads=2, input_size=96, patch_size=16, predictor_hidden_size=128)
+    m = csmae_b200.MAE_ViT_MsLdCeCd(**cfg, device="cuda").cuda().train()
+    assert m._engine.use_graphs
+    g = torch.Generator(device="cuda").manual_seed(3)
+    batches = [(torch.randn(8, 3, 96, 96, device="cuda", generator=g), torch.randn(8, 3, 96, 96, device="cuda", generator=g),
+                torch.rand(8, 36, device="cuda", generator=g), torch.rand(8, 36, device="cuda", generator=g))
+               for _ in range(2)]
+
+    def run(b):
+        x1, x2, n1, n2 = b
+        for p in m.parameters():
+            p.grad = None
+        loss, pred, mask = m(x1, x2, 0.75, noise=[n1, n2])
+        loss.backward()
+        return (loss.detach().clone(), pred.clone(), mask.clone(),
+                {k: p.grad.clone() for k, p in m.named_parameters() if p.grad is not None})
+
+    eager = [run(batches[0]), run(batches[1])]                 # steps 1-2: eager warm-up
+    graphed = [run(batches[0]), run(batches[1]), run(batches[0])]   # step 3 captures, 4-5 replay
+    assert len(m._engine._graphs) == 1 and m._engine._active_graph is not None
+    for i, gi in enumerate(graphed):
+        ref = eager[i % 2]
+        assert torch.equal(gi[2], ref[2]), "mask differs under graph replay"
+        assert abs(gi[0].item() - ref[0].item()) <= 1e-5 * abs(ref[0].item()) + 1e-6
+        assert rel_l2(gi[1], ref[1]) < 1e-5
+        assert gi[3].keys() == ref[3].keys()
+        for k in ref[3]:
+            assert rel_l2(gi[3][k], ref[3][k]) < 1e-4, k
+    # gradients handed to autograd must not alias graph memory: accumulate twice without zeroing
+    x1, x2, n1, n2 = batches[0]
+    for p in m.parameters():
+        p.grad = None
+    for _ in range(2):
+        loss, _, _ = m(x1, x2, 0.75, noise=[n1, n2])
+        loss.backward()
+    k = "decoder.0.attn.qkv.weight"
+    assert rel_l2(dict(m.named_parameters())[k].grad, 2 * eager[0][3][k]) < 1e-4
