@@ -41,7 +41,7 @@ SIGNATURES = {
     "csm_cast_multi": [_P, _I, _I, _P],
     "csm_cast_f32_bf16": [_P, _P, _L, _P],
     "csm_attention_fwd": [_P, _P, _P, _I, _I, _I, _I, _P],
-    "csm_attention_bwd": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
+    "csm_attention_bwd": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
     "csm_recon_loss_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "csm_recon_loss_bwd": [_P, _P, _P, _P, _P, _F, _I, _I, _I, _I, _I, _I, _P],
     "csm_cross_mse_fwd": [_P, _P, _P, _I, _I, _I, _P],
@@ -56,7 +56,7 @@ _lib = None
 _lock = threading.Lock()
 _sm_count = {}
 launch_count = 0   # kernels launched through the C-ABI so far (bench.py reports the delta)
-KERNELS_PER_CALL = {"csm_attention_bwd": 2, "csm_ntxent_fwd": 2}
+KERNELS_PER_CALL = {"csm_ntxent_fwd": 2}
 
 
 class NativeError(RuntimeError):

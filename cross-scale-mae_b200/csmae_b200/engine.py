@@ -491,7 +491,10 @@ class HotPathEngine:
             call("csm_linear_dgrad", dres16, w16[q + "attn.proj.weight"], d_ao, None, rows, Dm, Dm, EPI_BF16)
             dqkv = buf(f"b.{tag}.dqkv", (rows, 3 * Dm), bf16)
             delta = buf(f"b.{tag}.delta", (NB * heads * S,), f32)
-            call("csm_attention_bwd", B[t + "qkv"], B[t + "ao"], d_ao, B[t + "lse"], delta, dqkv, NB, S, heads, d)
+            # (the kernel can also emit the qkv.bias column sums itself -- measured slower than the separate
+            #  pass on B200: the extra tail per CTA is not hidden at one CTA per SM)
+            call("csm_attention_bwd", B[t + "qkv"], B[t + "ao"], d_ao, B[t + "lse"], delta, dqkv, None,
+                 NB, S, heads, d)
             call("csm_linear_wgrad", dqkv, B[t + "ln1"], G[q + "attn.qkv.weight"], rows, 3 * Dm, Dm, nsm)
             call("csm_colsum_bf16", dqkv, G[q + "attn.qkv.bias"], rows, 3 * Dm, 0, nsm)
             call("csm_linear_dgrad", dqkv, w16[q + "attn.qkv.weight"], dln, None, rows, 3 * Dm, Dm, EPI_BF16)

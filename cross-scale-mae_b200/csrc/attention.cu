@@ -30,6 +30,9 @@
 // c = d^-1/2 * log2(e), i.e. the log-sum-exp in the exp2 domain: p = exp2(s * c - L2).
 #include "common.cuh"
 
+extern "C" int csm_colsum_bf16(const void* dy_bf16, float* db, int rows, int N, int skip_period, int num_sms,
+                               cudaStream_t stream);
+
 namespace {
 using namespace csm;
 
@@ -340,7 +343,8 @@ template <int DH>
 __global__ void __launch_bounds__(DH == 64 ? 256 : 512, DH == 64 ? 2 : 1)
 attn_bwd_head_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ o_fwd,
                      const __nv_bfloat16* __restrict__ d_out, const float* __restrict__ lse2,
-                     __nv_bfloat16* __restrict__ dqkv, int S, int H, int Dm, int HPC, float c, float scale) {
+                     __nv_bfloat16* __restrict__ dqkv, float* __restrict__ dbias, int S, int H, int Dm, int HPC,
+                     float c, float scale) {
   extern __shared__ __align__(16) uint8_t smem_attn[];
   constexpr int LDS = DH + 8;
   constexpr int LDQ = DH + 8;                     // f32 dQ rows: 64-bit accesses of a half-warp hit 32 distinct banks
@@ -355,9 +359,9 @@ attn_bwd_head_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16*
   const int bh = blockIdx.x * HPC + hl;
   const int b = bh / H, h = bh % H;
   // per head slot: Q [S16][LDS], dO [S16][LDS], per-warp K and V tiles [16][LDS] each, dQ f32 [S16][LDQ],
-  //                {L2, delta} [S16], per-query-tile step counters [16]
+  //                {L2, delta} [S16], per-query-tile step counters [16], column-sum scratch [2 KT + 16][DH]
   const size_t slot_bytes = static_cast<size_t>(2 * S16 + KT * 32) * LDS * 2 + static_cast<size_t>(S16) * LDQ * 4 +
-                            static_cast<size_t>(S16) * 8 + 64;
+                            static_cast<size_t>(S16) * 8 + 64 + static_cast<size_t>(2 * KT + 16) * DH * 4;
   uint8_t* slot = smem_attn + hl * slot_bytes;
   __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(slot);
   __nv_bfloat16* sdO = sQ + S16 * LDS;
@@ -366,6 +370,7 @@ attn_bwd_head_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16*
   float* sdQ = reinterpret_cast<float*>(sdO + S16 * LDS + KT * 32 * LDS);
   float* sLD = sdQ + S16 * LDQ;                   // interleaved {L2, delta} per query
   int* sFlag = reinterpret_cast<int*>(sLD + 2 * S16);
+  float* sCol = reinterpret_cast<float*>(sFlag + 16);   // [KT][2][DH] dK / dV column sums, then [16][DH] for dQ
   const size_t ld = static_cast<size_t>(3) * Dm;
   const __nv_bfloat16* base = qkv + static_cast<size_t>(b) * S * ld + h * DH;
   const size_t obase = static_cast<size_t>(b) * S * Dm + h * DH;
@@ -537,6 +542,44 @@ attn_bwd_head_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16*
   // both tiles go out through this warp's private K-tile scratch (its fragments are already in registers)
   store_tile_bf16<DH>(dk, sKt, dkg, kt * 16, S, ld, lane);
   store_tile_bf16<DH>(dv, sKt, dvg, kt * 16, S, ld, lane);
+  // qkv.bias gradient = column sums of dqkv over the tokens: taken here from the tiles still on chip instead of
+  // re-reading dqkv from HBM (rows past S are exactly zero)
+  if (dbias != nullptr) {
+#pragma unroll
+    for (int dn = 0; dn < DH / 8; ++dn) {
+      float k0 = dk[dn][0] + dk[dn][2], k1 = dk[dn][1] + dk[dn][3];
+      float v0 = dv[dn][0] + dv[dn][2], v1 = dv[dn][1] + dv[dn][3];
+#pragma unroll
+      for (int off = 4; off < 32; off <<= 1) {
+        k0 += __shfl_xor_sync(0xffffffffu, k0, off);
+        k1 += __shfl_xor_sync(0xffffffffu, k1, off);
+        v0 += __shfl_xor_sync(0xffffffffu, v0, off);
+        v1 += __shfl_xor_sync(0xffffffffu, v1, off);
+      }
+      if (gq == 0) {
+        *reinterpret_cast<float2*>(sCol + (kt * 2 + 0) * DH + dn * 8 + 2 * t) = make_float2(k0, k1);
+        *reinterpret_cast<float2*>(sCol + (kt * 2 + 1) * DH + dn * 8 + 2 * t) = make_float2(v0, v1);
+      }
+    }
+    const int ngrp = max(1, min(16, tph / DH));
+    for (int idx = tid_h; idx < ngrp * DH; idx += tph) {
+      const int colq = idx % DH, grp = idx / DH;
+      float a = 0.f;
+      for (int r = grp; r < S; r += ngrp) a += sdQ[r * LDQ + colq];
+      sCol[(2 * KT + grp) * DH + colq] = a * scale;
+    }
+    __syncthreads();
+    for (int idx = tid_h; idx < 3 * DH; idx += tph) {
+      const int which = idx / DH, col = idx % DH;
+      float a = 0.f;
+      if (which == 0) {
+        for (int gI = 0; gI < ngrp; ++gI) a += sCol[(2 * KT + gI) * DH + col];
+      } else {
+        for (int k2 = 0; k2 < KT; ++k2) a += sCol[(k2 * 2 + which - 1) * DH + col];
+      }
+      atomicAdd(dbias + which * Dm + h * DH + col, a);
+    }
+  }
   // dQ = scale * sum over key tiles, written once (the last step's barrier already ordered the accumulation)
   {
     __nv_bfloat16* dqg = dqkv + static_cast<size_t>(b) * S * ld + h * DH;
@@ -784,7 +827,7 @@ int attn_fwd_launch(const void* qkv, void* out, float* lse, int B, int S, int H,
 
 template <int DH>
 int attn_bwd_launch(const void* qkv, const void* o, const void* d_out, const float* lse, float* delta, void* dqkv,
-                    int B, int S, int H, cudaStream_t stream) {
+                    float* dbias, int B, int S, int H, cudaStream_t stream) {
   const int Dm = H * DH;
   const float scale = 1.0f / sqrtf(static_cast<float>(DH));
   const float c = 1.4426950408889634f * scale;
@@ -797,14 +840,14 @@ int attn_bwd_launch(const void* qkv, const void* o, const void* d_out, const flo
     if (HPC > 4) HPC = 4;
     while (HPC > 1 && ((B * H) % HPC != 0 || HPC * KT > max_warps)) --HPC;
     const size_t slot = static_cast<size_t>(2 * S16 + KT * 32) * (DH + 8) * 2 + static_cast<size_t>(S16) * (DH + 8) * 4 +
-                        static_cast<size_t>(S16) * 8 + 64;
+                        static_cast<size_t>(S16) * 8 + 64 + static_cast<size_t>(2 * KT + 16) * DH * 4;
     static size_t cfg_head = 0;
     int rc = set_smem(attn_bwd_head_kernel<DH>, slot * HPC, &cfg_head, "attention_bwd");
     if (rc) return rc;
     cudaError_t le = csm_launch_pdl(attn_bwd_head_kernel<DH>, dim3(B * H / HPC), dim3(HPC * KT * 32), slot * HPC, stream,
                                     reinterpret_cast<const __nv_bfloat16*>(qkv), reinterpret_cast<const __nv_bfloat16*>(o),
                                     reinterpret_cast<const __nv_bfloat16*>(d_out), lse,
-                                    reinterpret_cast<__nv_bfloat16*>(dqkv), S, H, Dm, HPC, c, scale);
+                                    reinterpret_cast<__nv_bfloat16*>(dqkv), dbias, S, H, Dm, HPC, c, scale);
     if (le != cudaSuccess) {
       csm_set_error("attention_bwd: launch failed: %s", cudaGetErrorString(le));
       return CSM_ERR_CUDA;
@@ -830,6 +873,8 @@ int attn_bwd_launch(const void* qkv, const void* o, const void* d_out, const flo
       reinterpret_cast<const __nv_bfloat16*>(qkv), reinterpret_cast<const __nv_bfloat16*>(d_out), lse, delta,
       reinterpret_cast<__nv_bfloat16*>(dqkv), S, H, Dm, c, scale);
   CSM_CHECK_LAUNCH("attention_bwd_dkv");
+  // the long-sequence path has no fused bias sums: one column-sum pass over dqkv
+  if (dbias != nullptr) return csm_colsum_bf16(dqkv, dbias, B * S, 3 * Dm, 0, 0, stream);
   return CSM_OK;
 }
 
@@ -845,13 +890,13 @@ extern "C" int csm_attention_fwd(const void* qkv_bf16, void* out_bf16, float* ls
 }
 
 extern "C" int csm_attention_bwd(const void* qkv_bf16, const void* out_bf16, const void* d_out_bf16, const float* lse,
-                                 float* delta_scratch, void* dqkv_bf16, int B, int S, int H, int head_dim,
-                                 cudaStream_t stream) {
+                                 float* delta_scratch, void* dqkv_bf16, float* dbias, int B, int S, int H,
+                                 int head_dim, cudaStream_t stream) {
   CSM_CHECK_ARG(B > 0 && S > 0 && H > 0, "csm_attention_bwd: bad sizes B=%d S=%d H=%d", B, S, H);
   if (head_dim == 32)
-    return attn_bwd_launch<32>(qkv_bf16, out_bf16, d_out_bf16, lse, delta_scratch, dqkv_bf16, B, S, H, stream);
+    return attn_bwd_launch<32>(qkv_bf16, out_bf16, d_out_bf16, lse, delta_scratch, dqkv_bf16, dbias, B, S, H, stream);
   if (head_dim == 64)
-    return attn_bwd_launch<64>(qkv_bf16, out_bf16, d_out_bf16, lse, delta_scratch, dqkv_bf16, B, S, H, stream);
+    return attn_bwd_launch<64>(qkv_bf16, out_bf16, d_out_bf16, lse, delta_scratch, dqkv_bf16, dbias, B, S, H, stream);
   csm_set_error("csm_attention_bwd: head_dim must be 32 or 64 (got %d)", head_dim);
   return CSM_ERR_ARG;
 }

@@ -477,7 +477,7 @@ extern "C" int csm_colsum_bf16(const void* dy_bf16, float* db, int rows, int N, 
   CSM_CHECK_ARG(rows > 0 && N > 0 && N % 8 == 0, "csm_colsum_bf16: N must be a multiple of 8 (rows=%d N=%d)", rows, N);
   if (num_sms <= 0) num_sms = 148;
   const int gx = csm_cdiv(N, 256);
-  int gy = csm_cdiv(2 * num_sms, gx);
+  int gy = csm_cdiv(6 * num_sms, gx);       // ~6 CTAs of 256 threads per SM: enough 16-byte loads in flight for HBM
   const int max_gy = csm_cdiv(rows, 8);
   if (gy > max_gy) gy = max_gy;
   cudaError_t le = csm_launch_pdl(colsum_bf16_kernel, dim3(gx, gy), dim3(256), 0, stream,

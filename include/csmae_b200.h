@@ -92,8 +92,10 @@ int csm_cast_f32_bf16(const float* src, void* dst_bf16, long long n, csm_stream_
 /* ---- attention (timm 0.4.12 Attention; MAE_ViT_Baseline.py:160-188) -------------------------- */
 int csm_attention_fwd(const void* qkv_bf16, void* out_bf16, float* lse, int B, int S, int H, int head_dim,
                       csm_stream_t stream);
+/* dbias (nullable, f32 [3*H*head_dim]) accumulates the column sums of dqkv over the tokens = attn.qkv.bias gradient */
 int csm_attention_bwd(const void* qkv_bf16, const void* out_bf16, const void* d_out_bf16, const float* lse,
-                      float* delta_scratch, void* dqkv_bf16, int B, int S, int H, int head_dim, csm_stream_t stream);
+                      float* delta_scratch, void* dqkv_bf16, float* dbias, int B, int S, int H, int head_dim,
+                      csm_stream_t stream);
 
 /* ---- losses ---------------------------------------------------------------------------------
  * masked per-patch MSE against the image read in patch order (MAE_ViT_Shared.py:24-39,97-120) */

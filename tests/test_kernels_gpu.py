@@ -296,12 +296,17 @@ def test_attention_fwd_bwd(nat, B, S, H, d):
     ref.backward(d_out.float())
     dqkv = torch.full((B * S, 3 * Dm), float("nan"), device="cuda", dtype=bf16)
     delta = torch.empty(B * H * S, device="cuda")
-    nat.call("csm_attention_bwd", qkv, out, d_out, lse, delta, dqkv, B, S, H, d)
+    dbias = torch.zeros(3 * Dm, device="cuda")
+    nat.call("csm_attention_bwd", qkv, out, d_out, lse, delta, dqkv, dbias, B, S, H, d)
     g = ql.grad
     err = (dqkv.float() - g).abs().max().item()
     assert err <= 3e-2 * g.abs().max().item() + 1e-3, f"attention bwd max err {err:.3e} vs max {g.abs().max():.3e}"
     rel = ((dqkv.float() - g).norm() / g.norm()).item()
     assert rel < 2e-2, f"attention bwd relative L2 error {rel:.3e}"
+    # fused qkv.bias gradient: column sums of dqkv over the tokens
+    bref = g.sum(0)
+    berr = (dbias - bref).abs().max().item()
+    assert berr <= 2e-2 * bref.abs().max().item() + 2e-3 * math.sqrt(B * S), f"fused qkv bias grad err {berr:.3e}"
 
 
 # ------------------------------------------------------------------------------------------------ losses
