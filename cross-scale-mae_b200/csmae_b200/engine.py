@@ -159,7 +159,7 @@ class HotPathEngine:
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
         c0 = nat.launch_count
-        with torch.cuda.graph(g):
+        with torch.cuda.graph(g, capture_error_mode="thread_local"):
             out = self._forward_eager(entry["imgs"], entry["noise"], mask_ratio, training)
         entry["fwd_launches"] = nat.launch_count - c0      # kernels recorded, not run: counted at each replay
         nat.launch_count = c0
@@ -349,7 +349,7 @@ class HotPathEngine:
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
             c0 = nat.launch_count
-            with torch.cuda.graph(g):
+            with torch.cuda.graph(g, capture_error_mode="thread_local"):
                 self._backward_eager(entry["g"], entry["flat"])
             entry["bwd_launches"] = nat.launch_count - c0
             nat.launch_count = c0
