@@ -156,7 +156,8 @@ def workload_config(args, batch, world):
     return {"workload": f"MAE_ViT_MsLdCeCd vit_{args.arch}_patch16 two-scale ({args.input_size}+{args.input_size}) "
                         f"bs={batch}/GPU mask_ratio=0.75, fwd+bwd+AdamW",
             "global_batch": batch * world, "input_size": args.input_size,
-            "parallelism": f"dp{world}" if world > 1 else "single",
+            "parallelism": (f"dp{world} ({'torch DDP' if getattr(args, 'torch_ddp', False) else 'engine-overlapped NCCL all-reduce'})"
+                            if world > 1 else "single"),
             "l2_policy": "per-step working set (GBs of activations + 1.4 GB weights/grads/moments) exceeds the 126 MB L2"}
 
 
@@ -172,6 +173,7 @@ def main():
     ap.add_argument("--input-size", type=int, default=224)
     ap.add_argument("--cpu-batch", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--torch-ddp", action="store_true", help="N>1: wrap with torch's DistributedDataParallel")
     ap.add_argument("--profile-kernels", action="store_true", help="print the per-kernel CUDA-event breakdown")
     args = ap.parse_args()
     if args.batch is None:
@@ -198,9 +200,10 @@ def main():
     model = ctor(input_size=args.input_size, device=str(dev)).to(dev).train()
     step_model = model
     if world > 1:
-        # as main_pretrain.py:417-421 (encoder_norm never receives a gradient upstream either)
-        step_model = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local_rank],
-                                                               find_unused_parameters=True)
+        # same constructor call as main_pretrain.py:417-421; csmae_b200's wrapper lets the engine all-reduce the
+        # flat gradient buffer in segments overlapped with the backward (--torch-ddp: torch's own wrapper)
+        wrapper = torch.nn.parallel.DistributedDataParallel if args.torch_ddp else csmae_b200.DistributedDataParallel
+        step_model = wrapper(model, device_ids=[local_rank], find_unused_parameters=True)
     decay = [p for n, p in model.named_parameters() if p.requires_grad and not (p.ndim == 1 or n.endswith(".bias"))]
     no_decay = [p for n, p in model.named_parameters() if p.requires_grad and (p.ndim == 1 or n.endswith(".bias"))]
     opt = torch.optim.AdamW([{"params": no_decay, "weight_decay": 0.0}, {"params": decay, "weight_decay": 0.05}],
@@ -294,7 +297,7 @@ def main():
 
     # per-kernel breakdown of one step with CUDA events on the launching stream (outside the timed region)
     model._engine.use_graphs = False          # the breakdown times each C-ABI call eagerly
-    breakdown = kernel_breakdown(_native, lambda: step(imgs1, imgs2)) if rank == 0 else None
+    breakdown = kernel_breakdown(_native, lambda: step(imgs1, imgs2))     # every rank: the step all-reduces
 
     if rank != 0:
         if world > 1:

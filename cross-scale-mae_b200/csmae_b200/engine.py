@@ -37,6 +37,61 @@ NTXENT_EPS = 1e-8      # util/contrast_loss.py:51
 _GEMM_WEIGHT_SUFFIXES = ("qkv.weight", "proj.weight", "fc1.weight", "fc2.weight")
 
 
+def grad_segments(names, offsets, total, enc_layers, enc_groups):
+    """Slices [start, end) of the flat gradient buffer in the order the backward chain completes them, for the
+    overlapped gradient all-reduce.  The buffer follows named_parameters() order (cls_token, mask_token,
+    patch_embed, decoder_embed, encoder.0.., decoder.0.., decoder_pred, decoder_norm, predictor); the backward
+    runs decoder_pred/predictor/decoder_norm, decoder blocks, decoder_embed, encoder blocks (descending), patch_embed.
+      segment 0      : [first decoder.* parameter, total)        complete after the decoder blocks
+      segments 1..G-1: encoder layer groups, highest layers first
+      last segment   : [0, start of the second-lowest group)     complete at the very end
+    Returns (segments, boundaries): boundaries[k] = the encoder layer after whose backward segment k (k >= 1) is
+    complete; segment 0's boundary is the end of the decoder backward and the last one the end of the chain."""
+    first = {}
+    for n, o in zip(names, offsets):
+        key = ".".join(n.split(".")[:2]) if n.startswith(("encoder.", "decoder.")) and n.split(".")[1].isdigit() else n
+        first.setdefault(key, o)
+    dec0 = first.get("decoder.0")
+    if dec0 is None or enc_layers == 0 or "encoder.0" not in first:
+        return [(0, total)], []
+    groups = max(1, min(enc_groups, enc_layers))
+    bounds = [round(j * enc_layers / groups) for j in range(groups + 1)]          # 0 = b_0 < ... < b_G = Le
+    segs, layers = [(dec0, total)], []
+    for j in range(groups - 1, 0, -1):
+        start = first[f"encoder.{bounds[j]}"]
+        end = first[f"encoder.{bounds[j + 1]}"] if bounds[j + 1] < enc_layers else dec0
+        segs.append((start, end))
+        layers.append(bounds[j])
+    segs.append((0, first[f"encoder.{bounds[1]}"] if groups > 1 else dec0))
+    return segs, layers
+
+
+class _GraphSequence:
+    """Captures one call chain into several CUDA graphs: cut() ends the current capture and starts the next."""
+
+    def __init__(self):
+        self.graphs = []
+        self._ctx = None
+        self._pool = None
+
+    def begin(self):
+        g = torch.cuda.CUDAGraph()
+        kw = {} if self._pool is None else {"pool": self._pool}
+        self._ctx = torch.cuda.graph(g, capture_error_mode="thread_local", **kw)
+        self._ctx.__enter__()
+        self.graphs.append(g)
+
+    def cut(self):
+        self.end()
+        self.begin()
+
+    def end(self):
+        self._ctx.__exit__(None, None, None)
+        if self._pool is None:
+            self._pool = self.graphs[0].pool()
+        self._ctx = None
+
+
 class HotPathEngine:
     def __init__(self, model, use_cd=False, use_ce=False):
         self.model = model
@@ -58,6 +113,23 @@ class HotPathEngine:
         self._graphs = {}           # key -> dict(fwd graph, outputs, state, static inputs, bwd graph, ...)
         self._warm = {}             # key -> eager steps seen so far
         self.graph_warmup_steps = 2
+        self._sync_enabled = False  # overlapped gradient all-reduce (parallel.py)
+        self._sync_group = None     # its process group (None = the default group)
+        self._sync_world = 1
+        self._sync_groups = 3       # encoder layer groups -> 2 + groups all-reduce segments
+
+    def enable_grad_sync(self, group, world, enc_groups=3):
+        """Data-parallel gradient averaging inside the backward: the flat gradient buffer is all-reduced in
+        segments as the chain completes them (NCCL on its own stream), overlapping the rest of the backward."""
+        self._sync_enabled = world > 1
+        self._sync_group, self._sync_world, self._sync_groups = group, world, enc_groups
+        self._graphs.clear()
+
+    def _issue_allreduce(self, flat, seg, pending):
+        import torch.distributed as dist
+        start, end = seg
+        if end > start:
+            pending.append(dist.all_reduce(flat[start:end], op=dist.ReduceOp.AVG, group=self._sync_group, async_op=True))
 
     # ------------------------------------------------------------------ parameters
     def param_names(self):
@@ -330,12 +402,22 @@ class HotPathEngine:
                 "csmae_b200: backward() of a forward whose activations were overwritten by a later forward of the "
                 "same module (the workspace holds one step); call backward before the next forward")
         entry = getattr(self, "_active_graph", None)
+        sync = self._sync_enabled
         if entry is None:
-            flat, views = self._backward_eager(grad_loss, None)
+            pending = []
+            segs_box = {}
+
+            def boundary(k):
+                if sync:
+                    self._issue_allreduce(segs_box["flat"], segs_box["segs"][k], pending)
+            flat, views = self._backward_eager(grad_loss, None, boundary if sync else None, segs_box)
+            for w in pending:
+                w.wait()
             self._state = None
             return views
-        # graphed step: the gradient chain is captured once over static buffers; what autograd receives is a
-        # copy of the flat gradient buffer (one 4 B/param device copy), so .grad never aliases graph memory
+        # graphed step: the gradient chain is captured once over static buffers (in several graphs when the
+        # gradient all-reduce is overlapped: one per segment); what autograd receives is a copy of the flat
+        # gradient buffer (one 4 B/param device copy), so .grad never aliases graph memory
         if entry["bwd"] is None:
             entry["g"] = torch.zeros(1, dtype=torch.float32, device=grad_loss.device)
             entry["g"].copy_(grad_loss.detach().reshape(1))
@@ -347,16 +429,28 @@ class HotPathEngine:
             entry["dense"] = all(s_ % 4 == 0 for s_ in sizes)
             entry["like"] = [params[n] for n in names]
             torch.cuda.synchronize()
-            g = torch.cuda.CUDAGraph()
+            seq = _GraphSequence()
+            segs_box = {}
             c0 = nat.launch_count
-            with torch.cuda.graph(g, capture_error_mode="thread_local"):
-                self._backward_eager(entry["g"], entry["flat"])
+            seq.begin()
+            try:
+                cut = (lambda k: seq.cut() if k < len(segs_box["segs"]) - 1 else None) if sync else None
+                self._backward_eager(entry["g"], entry["flat"], cut, segs_box)
+            finally:
+                seq.end()
             entry["bwd_launches"] = nat.launch_count - c0
             nat.launch_count = c0
-            entry["bwd"] = g
+            entry["bwd"] = seq.graphs
+            entry["segs"] = segs_box.get("segs", [(0, total)])
             self._state = st                   # capture does not run the kernels; replay below does
         entry["g"].copy_(grad_loss.detach().reshape(1), non_blocking=True)
-        entry["bwd"].replay()
+        pending = []
+        for k, g in enumerate(entry["bwd"]):
+            g.replay()
+            if sync and k < len(entry["segs"]):
+                self._issue_allreduce(entry["flat"], entry["segs"][k], pending)
+        for w in pending:
+            w.wait()
         nat.launch_count += entry["bwd_launches"]
         self._state = None
         out = entry["flat"].clone()
@@ -368,7 +462,10 @@ class HotPathEngine:
             off += (p.numel() + 3) // 4 * 4
         return views
 
-    def _backward_eager(self, grad_loss, flat):
+    def _backward_eager(self, grad_loss, flat, boundary=None, segs_box=None):
+        """The hand-written backward chain.  boundary(k), when given, is called right after the kernels that
+        complete gradient segment k (see grad_segments) have been issued -- the caller all-reduces that slice
+        (eager) or cuts the CUDA-graph capture there."""
         st = self._state
         m = self.model
         N, ns, NB, L, keep, Se, Sd = (st[k] for k in ("N", "ns", "NB", "L", "keep", "Se", "Sd"))
@@ -390,6 +487,13 @@ class HotPathEngine:
         else:
             flat.zero_()
         G = {n: flat[o:o + s_].view(params[n].shape) for n, o, s_ in zip(names, offs, sizes)}
+        segs, seg_layers = grad_segments(names, offs, total, len(m.encoder), self._sync_groups)
+        if segs_box is not None:
+            segs_box["flat"], segs_box["segs"] = flat, segs
+        if boundary is None or len(segs) == 1:
+            seg_layers, fire = [], (lambda k: None)
+        else:
+            fire = boundary
         g = grad_loss.detach().reshape(1).to(f32).contiguous()
         norm_pix = 1 if m.norm_pix_loss else 0
         rows_d, rows_e = NB * Sd, NB * Se
@@ -435,6 +539,8 @@ class HotPathEngine:
              dres, dres16, G["decoder_norm.weight"], G["decoder_norm.bias"], top_fc2_bias, rows_d, Dd, nsm)
         self._blocks_bwd("dec", "decoder", len(m.decoder), dres, dres16, NB, Sd, Dd, m.decoder_num_heads, params, w16,
                          G, dev, nsm, top_bias_done=True)
+        if len(segs) > 1:
+            fire(0)                                  # decoder.*, decoder_pred, decoder_norm, predictor are final
 
         # ---- un-shuffle backward, decoder_embed ---------------------------------------------------
         d_demb = buf("b.d_demb", (rows_e, Dd), bf16)
@@ -453,16 +559,21 @@ class HotPathEngine:
         eres16 = buf("b.enc.dres16", (rows_e, D), bf16)
         call("csm_encoder_out_grad", d_enc, d_feat, eres, eres16, NB, Se, D)
         self._blocks_bwd("enc", "encoder", len(m.encoder), eres, eres16, NB, Se, D, m.encoder_num_heads, params, w16,
-                         G, dev, nsm, top_bias_done=False)
+                         G, dev, nsm, top_bias_done=False,
+                         after_layer=lambda i: fire(1 + seg_layers.index(i)) if i in seg_layers else None)
 
         # ---- cls token, patch embed (only the kept patches carry gradient; cls-slot rows are zero) -
         call("csm_cls_grad", eres, G["cls_token"], NB, Se, D)
         call("csm_linear_wgrad", eres16, B["patches"], G["patch_embed.proj.weight"], rows_e, D, P, nsm)
         call("csm_colsum_bf16", eres16, G["patch_embed.proj.bias"], rows_e, D, Se, nsm)
+        if len(segs) > 1:
+            fire(len(segs) - 1)
+        elif boundary is not None:
+            boundary(0)
         return flat, [G[n] for n in names]
 
     def _blocks_bwd(self, tag, pname, nlayers, dres, dres16, NB, S, Dm, heads, params, w16, G, dev, nsm,
-                    top_bias_done):
+                    top_bias_done, after_layer=None):
         bf16, f32 = torch.bfloat16, torch.float32
         rows = NB * S
         d = Dm // heads
@@ -501,6 +612,8 @@ class HotPathEngine:
             below_fc2_bias = G[f"{pname}.{i - 1}.mlp.fc2.bias"] if i > 0 else None
             call("csm_layernorm_bwd", dln, None, x_in, B[t + "mean1"], B[t + "rstd1"], params[q + "norm1.weight"],
                  dres, dres, dres16, G[q + "norm1.weight"], G[q + "norm1.bias"], below_fc2_bias, rows, Dm, nsm)
+            if after_layer is not None:
+                after_layer(i)
 
 
 class CrossScaleStep(torch.autograd.Function):

@@ -191,3 +191,33 @@ def test_ddp_gloo_world2():
     for p in procs:
         p.join(timeout=60)
     assert sorted(results) == [(0, True), (1, True)], results
+
+
+def test_grad_segments_cover_flat_buffer_in_completion_order():
+    """Host logic of the overlapped gradient all-reduce (engine.grad_segments): segments are disjoint, cover
+    the whole flat buffer, the decoder tail comes first and the head (cls/mask/patch_embed/decoder_embed +
+    lowest encoder group) last; boundaries name descending encoder layers."""
+    from csmae_b200.engine import grad_segments
+    import csmae_b200
+    m = csmae_b200.MAE_ViT_MsLdCeCd(dim_model=64, encoder_num_layers=6, encoder_num_heads=2, decoder_embed_dim=32,
+                                    decoder_num_layers=2, decoder_num_heads=2, input_size=32, patch_size=16,
+                                    predictor_hidden_size=32)
+    names = m._engine.param_names()
+    params = dict(m.named_parameters())
+    offs, total = [], 0
+    for n in names:
+        offs.append(total)
+        total += (params[n].numel() + 3) // 4 * 4
+    for groups in (1, 2, 3, 6, 9):
+        segs, layers = grad_segments(names, offs, total, 6, groups)
+        assert len(segs) == len(layers) + 2
+        covered = sorted(segs)
+        assert covered[0][0] == 0 and covered[-1][1] == total
+        assert all(a[1] == b[0] for a, b in zip(covered, covered[1:])), "segments must tile the buffer"
+        assert segs[0][1] == total and segs[-1][0] == 0
+        assert layers == sorted(layers, reverse=True) and all(0 < l < 6 for l in layers)
+        dec0 = offs[names.index("decoder.0.norm1.weight")]
+        assert segs[0][0] == dec0
+        for k, l in enumerate(layers):
+            assert segs[1 + k][0] == offs[names.index(f"encoder.{l}.norm1.weight")]
+    assert grad_segments(["a", "b"], [0, 4], 8, 0, 3) == ([(0, 8)], [])

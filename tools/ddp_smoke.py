@@ -31,7 +31,8 @@ def main():
                    decoder_num_heads=2, input_size=96, patch_size=16, predictor_hidden_size=128)
         model = csmae_b200.MAE_ViT_MsLdCeCd(**cfg, device=str(dev)).to(dev).train()
         B, S = 8, 96
-    ddp = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], find_unused_parameters=True)
+    wrapper = csmae_b200.DistributedDataParallel if "--native" in sys.argv else torch.nn.parallel.DistributedDataParallel
+    ddp = wrapper(model, device_ids=[local], find_unused_parameters=True)
     opt = torch.optim.AdamW([p for p in model.parameters() if p.requires_grad], lr=1e-4, betas=(0.9, 0.95))
     g = torch.Generator(device=dev).manual_seed(100 + rank)
     torch.manual_seed(1 + rank)
@@ -41,6 +42,18 @@ def main():
         opt.zero_grad(set_to_none=True)
         loss, _, _ = ddp(x1, x2, 0.75)
         loss.backward()
+        if "--check-grads" in sys.argv and step in (0, 3):
+            bad = []
+            for n, p_ in model.named_parameters():
+                if p_.grad is None:
+                    continue
+                gs = [torch.empty_like(p_.grad) for _ in range(world)]
+                dist.all_gather(gs, p_.grad.contiguous())
+                d = (gs[0] - gs[-1]).abs().max().item()
+                if d != 0.0:
+                    bad.append((n, d, gs[0].abs().max().item()))
+            if rank == 0:
+                print(f"step {step}: {len(bad)} gradients differ across ranks", bad[:12], flush=True)
         opt.step()
         print(f"[rank {rank}] step {step} loss {loss.item():.5f} graphs={len(model._engine._graphs)}", flush=True)
     # replicas must hold identical weights after identical all-reduced updates
