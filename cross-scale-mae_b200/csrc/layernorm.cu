@@ -13,61 +13,76 @@ __device__ __forceinline__ void red_add_v4(float* addr, const float4 v) {   // 1
                : "memory");
 }
 
-// One warp per row.  Statistics in fp32 (two-pass: mean, then centred variance), output rounded once.
-__global__ void layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
-                                     const float* __restrict__ beta, __nv_bfloat16* __restrict__ out_bf16,
-                                     float* __restrict__ out_f32, float* __restrict__ mean_out,
-                                     float* __restrict__ rstd_out, int rows, int D, float eps) {
+// One warp per row, VEC float4 per lane (D <= VEC * 128).  Statistics in fp32 (two-pass: mean, then centred
+// variance), output rounded once.  Each warp walks rows with a stride and keeps the NEXT row's loads in flight
+// while it reduces and writes the current one (the kernel is a chain of ~1 us memory latencies otherwise).
+template <int VEC>
+__global__ void __launch_bounds__(256)
+layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                     __nv_bfloat16* __restrict__ out_bf16, float* __restrict__ out_f32, float* __restrict__ mean_out,
+                     float* __restrict__ rstd_out, int rows, int D, float eps) {
   const int warps = blockDim.x >> 5;
-  const int row = blockIdx.x * warps + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
+  const int stride = gridDim.x * warps;
+  int row = blockIdx.x * warps + (threadIdx.x >> 5);
   pdl_wait();
   pdl_trigger();
   if (row >= rows) return;
-  const float* xr = x + static_cast<size_t>(row) * D;
-  float4 v[LN_MAX_VEC];
-  float s = 0.f;
+  const float inv_d = 1.0f / static_cast<float>(D);
+  float4 cur[VEC], nxt[VEC];
+  auto load = [&](float4 (&v)[VEC], int r) {
+    const float* xr = x + static_cast<size_t>(r) * D;
 #pragma unroll
-  for (int k = 0; k < LN_MAX_VEC; ++k) {
-    const int i = (k * 32 + lane) * 4;
-    if (i < D) {
-      v[k] = *reinterpret_cast<const float4*>(xr + i);
-      s += v[k].x + v[k].y + v[k].z + v[k].w;
+    for (int k = 0; k < VEC; ++k) {
+      const int i = (k * 32 + lane) * 4;
+      v[k] = i < D ? *reinterpret_cast<const float4*>(xr + i) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
-  }
-  const float mean = warp_sum(s) / D;
-  float ss = 0.f;
+  };
+  load(cur, row);
+  for (; row < rows; row += stride) {
+    const bool more = row + stride < rows;
+    if (more) load(nxt, row + stride);
+    float s = 0.f;
 #pragma unroll
-  for (int k = 0; k < LN_MAX_VEC; ++k) {
-    const int i = (k * 32 + lane) * 4;
-    if (i < D) {
-      const float a = v[k].x - mean, b = v[k].y - mean, c = v[k].z - mean, d = v[k].w - mean;
-      ss += a * a + b * b + c * c + d * d;
-    }
-  }
-  const float rstd = rsqrtf(warp_sum(ss) / D + eps);
-  if (lane == 0) {
-    mean_out[row] = mean;
-    rstd_out[row] = rstd;
-  }
+    for (int k = 0; k < VEC; ++k) s += cur[k].x + cur[k].y + cur[k].z + cur[k].w;
+    const float mean = warp_sum(s) * inv_d;
+    float ss = 0.f;
 #pragma unroll
-  for (int k = 0; k < LN_MAX_VEC; ++k) {
-    const int i = (k * 32 + lane) * 4;
-    if (i < D) {
-      const float4 g = *reinterpret_cast<const float4*>(gamma + i);
-      const float4 b = *reinterpret_cast<const float4*>(beta + i);
-      float4 o;
-      o.x = (v[k].x - mean) * rstd * g.x + b.x;
-      o.y = (v[k].y - mean) * rstd * g.y + b.y;
-      o.z = (v[k].z - mean) * rstd * g.z + b.z;
-      o.w = (v[k].w - mean) * rstd * g.w + b.w;
-      if (out_f32 != nullptr) *reinterpret_cast<float4*>(out_f32 + static_cast<size_t>(row) * D + i) = o;
-      if (out_bf16 != nullptr) {
-        uint2 pk;
-        pk.x = pack_bf16x2(o.x, o.y);
-        pk.y = pack_bf16x2(o.z, o.w);
-        *reinterpret_cast<uint2*>(out_bf16 + static_cast<size_t>(row) * D + i) = pk;
+    for (int k = 0; k < VEC; ++k) {
+      const int i = (k * 32 + lane) * 4;
+      if (i < D) {
+        const float a = cur[k].x - mean, b = cur[k].y - mean, c = cur[k].z - mean, d = cur[k].w - mean;
+        ss += a * a + b * b + c * c + d * d;
       }
+    }
+    const float rstd = rsqrtf(warp_sum(ss) * inv_d + eps);
+    if (lane == 0) {
+      mean_out[row] = mean;
+      rstd_out[row] = rstd;
+    }
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) {
+      const int i = (k * 32 + lane) * 4;
+      if (i < D) {
+        const float4 g = *reinterpret_cast<const float4*>(gamma + i);
+        const float4 b = *reinterpret_cast<const float4*>(beta + i);
+        float4 o;
+        o.x = (cur[k].x - mean) * rstd * g.x + b.x;
+        o.y = (cur[k].y - mean) * rstd * g.y + b.y;
+        o.z = (cur[k].z - mean) * rstd * g.z + b.z;
+        o.w = (cur[k].w - mean) * rstd * g.w + b.w;
+        if (out_f32 != nullptr) *reinterpret_cast<float4*>(out_f32 + static_cast<size_t>(row) * D + i) = o;
+        if (out_bf16 != nullptr) {
+          uint2 pk;
+          pk.x = pack_bf16x2(o.x, o.y);
+          pk.y = pack_bf16x2(o.z, o.w);
+          *reinterpret_cast<uint2*>(out_bf16 + static_cast<size_t>(row) * D + i) = pk;
+        }
+      }
+    }
+    if (more) {
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) cur[k] = nxt[k];
     }
   }
 }
@@ -395,14 +410,35 @@ __global__ void cast_f32_bf16_kernel(const float* __restrict__ src, __nv_bfloat1
 
 }  // namespace
 
+template <int VEC>
+cudaError_t launch_ln_fwd(const float* x, const float* gamma, const float* beta, void* out_bf16, float* out_f32,
+                          float* mean, float* rstd, int rows, int D, float eps, cudaStream_t stream) {
+  static int ctas_per_sm = 0, num_sms = 0;
+  if (ctas_per_sm == 0) {
+    int occ = 0, dev = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, layernorm_fwd_kernel<VEC>, 256, 0) != cudaSuccess || occ < 1)
+      occ = 1;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || num_sms < 1) num_sms = 148;
+    ctas_per_sm = occ;
+  }
+  int grid = csm_cdiv(rows, 8);
+  const int cap = num_sms * ctas_per_sm;            // one resident wave; warps stride over the remaining rows
+  if (grid > cap) grid = cap;
+  return csm_launch_pdl(layernorm_fwd_kernel<VEC>, dim3(grid), dim3(256), 0, stream, x, gamma, beta,
+                        reinterpret_cast<__nv_bfloat16*>(out_bf16), out_f32, mean, rstd, rows, D, eps);
+}
+
 extern "C" int csm_layernorm_fwd(const float* x, const float* gamma, const float* beta, void* out_bf16,
                                  float* out_f32, float* mean, float* rstd, int rows, int D, float eps,
                                  cudaStream_t stream) {
   CSM_CHECK_ARG(rows > 0 && D > 0 && D % 4 == 0 && D <= LN_MAX_VEC * 128,
                 "csm_layernorm_fwd: D must be a multiple of 4 and <= %d (rows=%d D=%d)", LN_MAX_VEC * 128, rows, D);
-  const int wpb = 8;
-  cudaError_t le = csm_launch_pdl(layernorm_fwd_kernel, dim3(csm_cdiv(rows, wpb)), dim3(wpb * 32), 0, stream, x, gamma,
-                                  beta, reinterpret_cast<__nv_bfloat16*>(out_bf16), out_f32, mean, rstd, rows, D, eps);
+  cudaError_t le;
+  if (D <= 256) le = launch_ln_fwd<2>(x, gamma, beta, out_bf16, out_f32, mean, rstd, rows, D, eps, stream);
+  else if (D <= 512) le = launch_ln_fwd<4>(x, gamma, beta, out_bf16, out_f32, mean, rstd, rows, D, eps, stream);
+  else if (D <= 768) le = launch_ln_fwd<6>(x, gamma, beta, out_bf16, out_f32, mean, rstd, rows, D, eps, stream);
+  else le = launch_ln_fwd<8>(x, gamma, beta, out_bf16, out_f32, mean, rstd, rows, D, eps, stream);
   if (le != cudaSuccess) {
     csm_set_error("layernorm_fwd: launch failed: %s", cudaGetErrorString(le));
     return CSM_ERR_CUDA;

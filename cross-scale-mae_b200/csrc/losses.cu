@@ -147,6 +147,7 @@ __global__ void bn_patch_fwd_kernel(const __nv_bfloat16* __restrict__ h, const f
   float mean, rstd;
   if (training) {
   float s = 0.f;
+#pragma unroll 4
   for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
     const int n = idx / per_row, c = (idx % per_row) * 8;
     const uint4 v = *reinterpret_cast<const uint4*>(h + (static_cast<size_t>(n) * Sd + 1 + l) * Hp + c);
@@ -160,6 +161,7 @@ __global__ void bn_patch_fwd_kernel(const __nv_bfloat16* __restrict__ h, const f
   const float cnt = static_cast<float>(N) * Hp;
   mean = block_sum(s, s_buf) / cnt;
   float ss = 0.f;
+#pragma unroll 4
   for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
     const int n = idx / per_row, c = (idx % per_row) * 8;
     const uint4 v = *reinterpret_cast<const uint4*>(h + (static_cast<size_t>(n) * Sd + 1 + l) * Hp + c);
@@ -185,6 +187,7 @@ __global__ void bn_patch_fwd_kernel(const __nv_bfloat16* __restrict__ h, const f
     rstd = rsqrtf(running_var[l] + eps);
   }
   const float a = rstd * gamma[l], b = beta[l] - mean * rstd * gamma[l];
+#pragma unroll 4
   for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
     const int n = idx / per_row, c = (idx % per_row) * 8;
     const size_t off = (static_cast<size_t>(n) * Sd + 1 + l) * Hp + c;
@@ -219,6 +222,7 @@ __global__ void bn_patch_bwd_kernel(const __nv_bfloat16* __restrict__ h, const _
   const int total = N * per_row;
   const float mean = mean_in[l], rstd = rstd_in[l];
   float s1 = 0.f, s2 = 0.f;
+#pragma unroll 2
   for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
     const int n = idx / per_row, c = (idx % per_row) * 8;
     const size_t off = (static_cast<size_t>(n) * Sd + 1 + l) * Hp + c;
@@ -242,6 +246,7 @@ __global__ void bn_patch_bwd_kernel(const __nv_bfloat16* __restrict__ h, const _
   }
   const float cnt = static_cast<float>(N) * Hp;
   const float m1 = s1 / cnt, m2 = s2 / cnt, gr = gamma[l] * rstd;
+#pragma unroll 2
   for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
     const int n = idx / per_row, c = (idx % per_row) * 8;
     const size_t off = (static_cast<size_t>(n) * Sd + 1 + l) * Hp + c;
@@ -283,6 +288,7 @@ __global__ void token_mean_normalize_kernel(const float* __restrict__ x, float* 
     const int i = threadIdx.x + k * blockDim.x;
     float a = 0.f;
     if (i < D) {
+#pragma unroll 8
       for (int t = 1; t < Se; ++t) a += xr[static_cast<size_t>(t) * D + i];
       a /= static_cast<float>(Se - 1);
     }
@@ -313,12 +319,23 @@ __global__ void ntxent_fwd_kernel(const float* __restrict__ zhat, float* __restr
   const int i = blockIdx.x, n2 = 2 * B;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
   const float* zi = zhat + static_cast<size_t>(i) * D;
-  for (int j = w; j < n2; j += nw) {
-    const float* zj = zhat + static_cast<size_t>(j) * D;
-    float d = 0.f;
-    for (int k = lane; k < D; k += 32) d += zi[k] * zj[k];
-    d = warp_sum(d);
-    if (lane == 0) s_e[j] = __expf(d * inv_tau);
+  for (int j0 = w * 4; j0 < n2; j0 += nw * 4) {        // four independent dot products in flight per warp
+    float d[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int k = lane * 4; k < D; k += 128) {
+      const float4 a = *reinterpret_cast<const float4*>(zi + k);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (j0 + u < n2) {
+          const float4 b = *reinterpret_cast<const float4*>(zhat + static_cast<size_t>(j0 + u) * D + k);
+          d[u] += a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w;
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const float du = warp_sum(d[u]);
+      if (lane == 0 && j0 + u < n2) s_e[j0 + u] = __expf(du * inv_tau);
+    }
   }
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -342,12 +359,23 @@ __global__ void ntxent_bwd_kernel(const float* __restrict__ zhat, const float* _
   const float* zi = zhat + static_cast<size_t>(i) * D;
   const int pos_i = (i + B) % n2;
   const float inv_n = 1.f / static_cast<float>(n2);
-  for (int j = w; j < n2; j += nw) {
-    const float* zj = zhat + static_cast<size_t>(j) * D;
-    float d = 0.f;
-    for (int k = lane; k < D; k += 32) d += zi[k] * zj[k];
-    d = warp_sum(d);
-    if (lane == 0) {
+  for (int j0 = w * 4; j0 < n2; j0 += nw * 4) {
+    float dd[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int k = lane * 4; k < D; k += 128) {
+      const float4 a = *reinterpret_cast<const float4*>(zi + k);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (j0 + u < n2) {
+          const float4 b = *reinterpret_cast<const float4*>(zhat + static_cast<size_t>(j0 + u) * D + k);
+          dd[u] += a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w;
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+    const int j = j0 + u;
+    const float d = warp_sum(dd[u]);
+    if (lane == 0 && j < n2) {
       const float e = __expf(d * inv_tau);
       float gij = 0.f, gji = 0.f;
       if (j == pos_i) {
@@ -359,6 +387,7 @@ __global__ void ntxent_bwd_kernel(const float* __restrict__ zhat, const float* _
       }
       s_w[j] = (gij + gji) * inv_n * inv_tau;
     }
+    }
   }
   __syncthreads();
   float v[4], dot = 0.f;
@@ -367,6 +396,7 @@ __global__ void ntxent_bwd_kernel(const float* __restrict__ zhat, const float* _
     const int c = threadIdx.x + k * blockDim.x;
     float a = 0.f;
     if (c < D) {
+#pragma unroll 8
       for (int j = 0; j < n2; ++j) a += s_w[j] * zhat[static_cast<size_t>(j) * D + c];
       dot += a * zi[c];
     }
@@ -438,7 +468,7 @@ extern "C" int csm_bn_patch_fwd(const void* h_bf16, const float* gamma, const fl
   CSM_CHECK_ARG(N > 0 && L > 0 && Hp % 8 == 0, "csm_bn_patch_fwd: bad sizes N=%d L=%d Hp=%d", N, L, Hp);
   CSM_CHECK_ARG(training || (running_mean != nullptr && running_var != nullptr),
                 "csm_bn_patch_fwd: eval mode needs running statistics");
-  bn_patch_fwd_kernel<<<L, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(h_bf16), gamma, beta,
+  bn_patch_fwd_kernel<<<L, 1024, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(h_bf16), gamma, beta,
                                              reinterpret_cast<__nv_bfloat16*>(out_bf16), mean, rstd, running_mean,
                                              running_var, N, L + 1, Hp, eps, momentum, training);
   CSM_CHECK_LAUNCH("bn_patch_fwd");
@@ -449,7 +479,7 @@ extern "C" int csm_bn_patch_bwd(const void* h_bf16, const void* out_bf16, const 
                                 const float* mean, const float* rstd, void* dh_bf16, float* dgamma, float* dbeta,
                                 int N, int L, int Hp, cudaStream_t stream) {
   CSM_CHECK_ARG(N > 0 && L > 0 && Hp % 8 == 0, "csm_bn_patch_bwd: bad sizes N=%d L=%d Hp=%d", N, L, Hp);
-  bn_patch_bwd_kernel<<<L, 256, 0, stream>>>(
+  bn_patch_bwd_kernel<<<L, 1024, 0, stream>>>(
       reinterpret_cast<const __nv_bfloat16*>(h_bf16), reinterpret_cast<const __nv_bfloat16*>(out_bf16),
       reinterpret_cast<const __nv_bfloat16*>(d_out_bf16), gamma, mean, rstd, reinterpret_cast<__nv_bfloat16*>(dh_bf16),
       dgamma, dbeta, N, L + 1, Hp);
@@ -459,7 +489,8 @@ extern "C" int csm_bn_patch_bwd(const void* h_bf16, const void* out_bf16, const 
 
 extern "C" int csm_ntxent_fwd(const float* enc_out, float* zhat, float* fnorm, float* neg, float* loss_sum, int B,
                               int Se, int D, float tau, float eps, cudaStream_t stream) {
-  CSM_CHECK_ARG(B > 0 && Se >= 2 && D > 0 && D <= 1024, "csm_ntxent_fwd: bad sizes B=%d Se=%d D=%d", B, Se, D);
+  CSM_CHECK_ARG(B > 0 && Se >= 2 && D > 0 && D <= 1024 && D % 4 == 0, "csm_ntxent_fwd: bad sizes B=%d Se=%d D=%d", B, Se,
+                D);
   token_mean_normalize_kernel<<<2 * B, 256, 0, stream>>>(enc_out, zhat, fnorm, Se, D);
   CSM_CHECK_LAUNCH("token_mean_normalize");
   ntxent_fwd_kernel<<<2 * B, 128, 2 * B * sizeof(float), stream>>>(zhat, neg, loss_sum, B, D, 1.f / tau, eps);
