@@ -340,7 +340,7 @@ attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict
 // backward, single pass (S16 <= 256): grid (B*H / HPC); CTA = HPC heads x KT warps, warp = one 16-key tile
 // ---------------------------------------------------------------------------------------------
 template <int DH>
-__global__ void __launch_bounds__(DH == 64 ? 256 : 512, DH == 64 ? 2 : 1)
+__global__ void __launch_bounds__(DH == 64 ? 128 : 512, DH == 64 ? 3 : 1)
 attn_bwd_head_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ o_fwd,
                      const __nv_bfloat16* __restrict__ d_out, const float* __restrict__ lse2,
                      __nv_bfloat16* __restrict__ dqkv, float* __restrict__ dbias, int S, int H, int Dm, int HPC,
@@ -832,9 +832,9 @@ int attn_bwd_launch(const void* qkv, const void* o, const void* d_out, const flo
   const float scale = 1.0f / sqrtf(static_cast<float>(DH));
   const float c = 1.4426950408889634f * scale;
   const int S16 = (S + 15) & ~15;
-  if (S16 <= (DH == 64 ? 128 : 256)) {
+  if (S16 <= (DH == 64 ? 64 : 256)) {   // d = 64 needs ~170 registers per thread: CTAs of 4 warps, 3 per SM
     const int KT = S16 >> 4;
-    const int max_warps = DH == 64 ? 8 : 16;       // the kernel's launch bound
+    const int max_warps = DH == 64 ? 4 : 16;       // the kernel's launch bound
     int HPC = 8 / KT;                               // heads per CTA for short sequences (<= 8 warps)
     if (HPC < 1) HPC = 1;
     if (HPC > 4) HPC = 4;
