@@ -308,12 +308,21 @@ def main():
     peaks = measured_peaks()
     ips = B * world / (ms_step * 1e-3)
     ips_e2e = B * world / (ms_e2e * 1e-3)
+    # DRAM bytes per GEMM launch from the committed ncu --set full capture of the same shapes (ViT-B only)
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r1c_gemm_dram_traffic.json")
+    if args.arch == "base" and args.input_size == 224 and B == 64 and os.path.exists(tpath):
+        with open(tpath) as f:
+            traffic = json.load(f)["avg_bytes_per_launch"]
     gemm_ms = sum(v["ms"] for k, v in breakdown.items() if k.startswith("csm_linear"))
+    gemm_n = sum(v["n"] for k, v in breakdown.items() if k.startswith("csm_linear"))
     step_ms_prof = sum(v["ms"] for v in breakdown.values())
     gemm_tflops = 3 * fl["gemm_fwd"] * B / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
     roofline = {"bound": "tensor", "kernel": "gemm_kernel (tcgen05; csm_linear_fwd/dgrad/wgrad, all launches of one step)",
                 "achieved": gemm_tflops, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
-                "frac": gemm_tflops / peaks["tflops_sustained"], "traffic": None,
+                "frac": gemm_tflops / peaks["tflops_sustained"], "traffic": traffic,
+                "launches_per_step": gemm_n, "avg_launch_us": gemm_ms * 1e3 / gemm_n if gemm_n else None,
+                "flops_per_launch_avg": 3 * fl["gemm_fwd"] * B / gemm_n if gemm_n else None,
                 "peak_source": peaks["source"] + " (sustained: kernel timed inside a long step)",
                 "share_of_step": gemm_ms / step_ms_prof if step_ms_prof else None,
                 "step_frac_of_flop_roofline": ips / world * fl["fwd_bwd"] / (peaks["tflops_sustained"] * 1e12)}

@@ -188,9 +188,7 @@ class MAE_ViT_Baseline(nn.Module):
         eng = self._engine
         if noises is None:
             noises = [self._draw_noise(im.shape[0], im.device, mask_seed) for im in imgs_list]
-        names = eng.param_names()
-        pd = dict(self.named_parameters())
-        plist = [pd[n] for n in names]
+        plist = eng.snapshot()["plist"]
         if torch.is_grad_enabled() and any(p.requires_grad for p in plist):
             loss = CrossScaleStep.apply(eng, imgs_list, noises, mask_ratio, self.training, *plist)
             out = eng._last_out
