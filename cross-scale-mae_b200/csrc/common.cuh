@@ -75,8 +75,13 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
+// Round-to-nearest-even to bf16 precision, result kept as fp32.  Integer arithmetic on purpose: the scalar
+// cvt (F2F.BF16) runs on the XU pipe at a quarter of the MUFU rate on sm_100 and was the binding pipe of the GEMM
+// epilogues that round every accumulator (ncu: XU 85 % busy).  Inf stays Inf; NaN payloads are not preserved.
 __device__ __forceinline__ float bf16_round(float x) {
-  return __bfloat162float(__float2bfloat16_rn(x));
+  uint32_t u = __float_as_uint(x);
+  u += 0x7FFFu + ((u >> 16) & 1u);
+  return __uint_as_float(u & 0xFFFF0000u);
 }
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
@@ -85,8 +90,14 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 }
 
 __device__ __forceinline__ float2 unpack_bf16x2(uint32_t v) {
-  __nv_bfloat162 b = *reinterpret_cast<__nv_bfloat162*>(&v);
-  return __bfloat1622float2(b);
+  return make_float2(__uint_as_float(v << 16), __uint_as_float(v & 0xFFFF0000u));
+}
+
+// Two values rounded to bf16 at once: one packed cvt (F2FP, not an XU op) + two logic ops.
+__device__ __forceinline__ void bf16_round_pair(float& a, float& b) {
+  const float2 r = unpack_bf16x2(pack_bf16x2(a, b));
+  a = r.x;
+  b = r.y;
 }
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -109,8 +120,10 @@ __device__ __forceinline__ float warp_max(float v) {
 // K/32 instructions per output element before it, not the tensor pipe, bounds the kernel.
 __device__ __forceinline__ void gelu_and_grad(float x, float& g, float& gp) {
   const float ax = fabsf(x);
-  float t, e;
+  // (the epilogue is instruction-issue bound: one MUFU.RCP beats a Newton iteration on the FMA pipe)
+  float t;
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(ax, 0.2316419f, 1.0f)));
+  float e;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * x * -0.72134752044f));      // exp(-x^2/2)
   // coefficients pre-multiplied by 1/sqrt(2 pi)
   float poly = fmaf(t, 0.53070271f, -0.72657601f);

@@ -14,9 +14,10 @@
 // tcgen05.mma.cta_group::2 (M = 256) into TMEM accumulators that live in both SMs.
 //   warp 0      TMA producer (both CTAs; completion signalled on the LEADER's full barrier)
 //   warp 1      TMEM allocator; in the leader CTA the single-thread MMA issuer
-//   warps 2..9  epilogue: tcgen05.ld -> registers -> fused bias / GELU / residual / dGELU ->
-//               128B-swizzled staging tile in shared memory -> TMA store (or TMA reduce-add);
-//               residual / pre-activation inputs arrive by TMA load into the same staging tile
+//   warps 2..17 epilogue (16 warps: the GELU / gelu' epilogues are FP32-issue bound, K/32 instructions per
+//               output element is all the main loop hides): tcgen05.ld -> registers -> fused bias / GELU /
+//               residual / dGELU -> 64B-swizzled 32 x 64 B staging tile in shared memory -> TMA store (or TMA
+//               reduce-add); residual / gelu' inputs arrive by TMA load into the same staging tile
 // The accumulator is double-buffered in TMEM (2 x 256 columns), so the epilogue of tile i overlaps
 // the main loop of tile i+1; the smem ring is 5 stages of 32 KB.
 //
@@ -39,12 +40,12 @@ constexpr int BK = 64;             // 64 bf16 = 128 bytes = one swizzle row
 constexpr int UMMA_K = 16;
 constexpr int MAX_BN = 256;
 constexpr int STAGES = 5;
-constexpr int EPI_WARPS = 8;
+constexpr int EPI_WARPS = 16;                       // 4 per TMEM lane quarter = 4 per SM sub-partition
 constexpr int GEMM_THREADS = 32 * (2 + EPI_WARPS);
 constexpr int A_BYTES = BM * BK * 2;                 // 16 KB
 constexpr int B_BYTES_MAX = (MAX_BN / 2) * BK * 2;   // 16 KB (each CTA holds half of the B tile)
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES_MAX;
-constexpr int STG_BYTES = 4096;                      // one staging tile: 32 rows x 128 B
+constexpr int STG_BYTES = 2048;                      // one staging tile: 32 rows x 64 B (32 bf16 or 16 f32 columns)
 constexpr int STG_BUFS = 2;
 constexpr int SMEM_RING = STAGES * STAGE_BYTES;
 constexpr int SMEM_STG = EPI_WARPS * STG_BUFS * STG_BYTES;
@@ -159,6 +160,17 @@ __device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
   uint4 v;
   asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
   return v;
+}
+
+// 32 lanes x 16 consecutive 32-bit columns
+__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
 }
 
 struct WorkUnit {
@@ -297,24 +309,23 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       }
     }
   } else {
-    // ------------------------------ epilogue (both CTAs, 8 warps) --------------------------
+    // ------------------------------ epilogue (both CTAs, 16 warps) -------------------------
     const int ew = warp - 2;
     const int q = warp & 3;                        // TMEM lane quarter this warp may access
-    const int half = ew >> 2;                      // which chunks of the tile this warp takes
+    const int quad = ew >> 2;                      // which chunks of the tile this warp takes (c % 4 == quad)
     constexpr bool OUT_F32 = (EPI == EPI_RESID || EPI == EPI_F32 || EPI == EPI_F32_ATOMIC);
     constexpr bool HAS_AUX = (EPI == EPI_RESID || EPI == EPI_DGELU);
-    constexpr int CW = OUT_F32 ? 32 : 64;          // columns per staging tile (128 bytes per row)
+    constexpr int CW = OUT_F32 ? 16 : 32;          // columns per staging tile (64 bytes per row)
     uint8_t* stg = smem + SMEM_RING + ew * (STG_BUFS * STG_BYTES);
     uint64_t* my_aux_bar = aux_bar + ew * STG_BUFS;
     const uint32_t tmem_empty_leader0 = mapa_u32(smem_u32(&tmem_empty[0]), 0);
     const uint32_t tmem_empty_leader1 = mapa_u32(smem_u32(&tmem_empty[1]), 0);
     const int nchunks = p.bn / CW;
-    const uint32_t sw = static_cast<uint32_t>(lane & 7);
+    const uint32_t sw = static_cast<uint32_t>((lane >> 1) & 3);   // 64B swizzle: 16-byte chunk ^= (row / 2) % 4
     uint32_t seq = 0;        // staging-buffer sequence number (continues across tiles)
     uint32_t aux_seq = 0;    // aux loads issued so far
     uint32_t tile_it = 0;
 
-    // first aux prefetch of the first tile
     auto issue_aux = [&](const WorkUnit& w, int c) {
       const uint32_t b = aux_seq & 1;
       mbar_expect_tx(&my_aux_bar[b], STG_BYTES);
@@ -329,27 +340,27 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       const uint32_t acc_ph = (tile_it >> 1) & 1;
       const int row0 = w.m_tile * (2 * BM) + static_cast<int>(rank) * BM + q * 32;
       const int col_tile = w.n_tile * p.bn;
-      if (HAS_AUX && lane == 0 && half < nchunks) {
+      if (HAS_AUX && lane == 0 && quad < nchunks) {
         // the staging buffer the load lands in must have been read out by its previous TMA store
         bulk_wait_read<0>();
-        issue_aux(w, half);
+        issue_aux(w, quad);
       }
       mbar_wait(&tmem_full[acc], acc_ph);
       tc_fence_after();
-      if (half >= nchunks) {     // narrow tile: this warp has no chunk, it only releases the accumulator
+      if (quad >= nchunks) {     // narrow tile: this warp has no chunk, it only releases the accumulator
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster(acc ? tmem_empty_leader1 : tmem_empty_leader0);
       }
       const uint32_t tmem_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * ACC_COLS;
 
 #pragma unroll 1
-      for (int c = half; c < nchunks; c += 2) {
+      for (int c = quad; c < nchunks; c += 4) {
         const int col0 = col_tile + c * CW;
-        const bool last = (c + 2 >= nchunks);
+        const bool last = (c + 4 >= nchunks);
         // ---- accumulator chunk -> registers ----
         uint32_t r[CW];
-        tmem_ld_32x32(tmem_row + c * CW, *reinterpret_cast<uint32_t(*)[32]>(&r[0]));
-        if (CW == 64) tmem_ld_32x32(tmem_row + c * CW + 32, *reinterpret_cast<uint32_t(*)[32]>(&r[CW - 32]));
+        if (CW == 32) tmem_ld_32x32(tmem_row + c * CW, *reinterpret_cast<uint32_t(*)[32]>(&r[0]));
+        else tmem_ld_32x16(tmem_row + c * CW, *reinterpret_cast<uint32_t(*)[16]>(&r[0]));
         tmem_ld_wait();
         if (last) {
           // all TMEM reads of this tile by this warp are done: hand the buffer back to the MMA issuer
@@ -375,34 +386,41 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           const uint32_t b = seq & 1;
           if (lane == 0) bulk_wait_read<1>();     // the store that last used this buffer has read it out
           __syncwarp();
-          const uint32_t sbase = smem_u32(stg + b * STG_BYTES) + lane * 128;
+          const uint32_t sbase = smem_u32(stg + b * STG_BYTES) + lane * 64;
           if (OUT_F32) {
 #pragma unroll
-            for (int g = 0; g < 8; ++g) {
+            for (int g = 0; g < 4; ++g) {
               uint4 o;
               o.x = __float_as_uint(v[g * 4 + 0]); o.y = __float_as_uint(v[g * 4 + 1]);
               o.z = __float_as_uint(v[g * 4 + 2]); o.w = __float_as_uint(v[g * 4 + 3]);
               st_shared_v4(sbase + ((static_cast<uint32_t>(g) ^ sw) << 4), o);
             }
           } else if (EPI == EPI_GELU) {
-            // one pass: h rounded to bf16 (the reference's fc1 output), gelu(h) -> v, gelu'(h) -> first staging tile
+            // one pass: h rounded to bf16 (the reference's fc1 output); gelu'(h) and gelu(h) go to the two staging
+            // tiles of this warp, one proxy fence, two TMA stores
+            if (lane == 0) bulk_wait_read<0>();   // both buffers are rewritten
+            __syncwarp();
+            const uint32_t sbase2 = smem_u32(stg + (b ^ 1) * STG_BYTES) + lane * 64;
 #pragma unroll
-            for (int g = 0; g < 8; ++g) {
-              uint4 o;
+            for (int g = 0; g < 4; ++g) {
+              uint4 o, o2;
               uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
+              uint32_t* ow2 = reinterpret_cast<uint32_t*>(&o2);
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
                 float ga, gpa, gb, gpb;
-                gelu_and_grad(bf16_round(v[g * 8 + 2 * j]), ga, gpa);
-                gelu_and_grad(bf16_round(v[g * 8 + 2 * j + 1]), gb, gpb);
+                bf16_round_pair(v[g * 8 + 2 * j], v[g * 8 + 2 * j + 1]);
+                gelu_and_grad(v[g * 8 + 2 * j], ga, gpa);
+                gelu_and_grad(v[g * 8 + 2 * j + 1], gb, gpb);
                 ow[j] = pack_bf16x2(gpa, gpb);
-                r[g * 4 + j] = pack_bf16x2(ga, gb);
+                ow2[j] = pack_bf16x2(ga, gb);
               }
               st_shared_v4(sbase + ((static_cast<uint32_t>(g) ^ sw) << 4), o);
+              st_shared_v4(sbase2 + ((static_cast<uint32_t>(g) ^ sw) << 4), o2);
             }
           } else {
 #pragma unroll
-            for (int g = 0; g < 8; ++g) {
+            for (int g = 0; g < 4; ++g) {
               uint4 o;
               o.x = pack_bf16x2(v[g * 8 + 0], v[g * 8 + 1]); o.y = pack_bf16x2(v[g * 8 + 2], v[g * 8 + 3]);
               o.z = pack_bf16x2(v[g * 8 + 4], v[g * 8 + 5]); o.w = pack_bf16x2(v[g * 8 + 6], v[g * 8 + 7]);
@@ -418,18 +436,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           }
           ++seq;
           if (EPI == EPI_GELU) {
-            const uint32_t b2 = seq & 1;
-            if (lane == 0) bulk_wait_read<1>();
-            __syncwarp();
-            const uint32_t sbase2 = smem_u32(stg + b2 * STG_BYTES) + lane * 128;
-#pragma unroll
-            for (int g = 0; g < 8; ++g)
-              st_shared_v4(sbase2 + ((static_cast<uint32_t>(g) ^ sw) << 4),
-                           make_uint4(r[g * 4 + 0], r[g * 4 + 1], r[g * 4 + 2], r[g * 4 + 3]));
-            fence_proxy_async();
-            __syncwarp();
             if (lane == 0) {
-              tma_store_2d(&tmap_aux, stg + b2 * STG_BYTES, col0, row0);
+              tma_store_2d(&tmap_aux, stg + (b ^ 1) * STG_BYTES, col0, row0);
               bulk_commit();
             }
             ++seq;
@@ -437,29 +445,31 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         } else {
           // ---- residual / dGELU: the aux tile was TMA-loaded into the staging buffer; combine in place ----
           const uint32_t b = seq & 1;
-          // prefetch the aux tile of the next chunk (or of the next tile's first chunk) into the other buffer
+          // prefetch the aux tile of this warp's next chunk into the other buffer
           if (lane == 0) {
             bulk_wait_read<0>();                    // the other buffer's last store has read it out
             if (!last) {
-              issue_aux(w, c + 2);
+              issue_aux(w, c + 4);
             }
           }
           mbar_wait(&my_aux_bar[b], (seq >> 1) & 1);
-          const uint32_t sbase = smem_u32(stg + b * STG_BYTES) + lane * 128;
+          const uint32_t sbase = smem_u32(stg + b * STG_BYTES) + lane * 64;
           if (EPI == EPI_RESID) {
 #pragma unroll
-            for (int g = 0; g < 8; ++g) {
+            for (int g = 0; g < 4; ++g) {
               const uint32_t a = sbase + ((static_cast<uint32_t>(g) ^ sw) << 4);
               uint4 x = ld_shared_v4(a);
-              x.x = __float_as_uint(__uint_as_float(x.x) + bf16_round(v[g * 4 + 0]));
-              x.y = __float_as_uint(__uint_as_float(x.y) + bf16_round(v[g * 4 + 1]));
-              x.z = __float_as_uint(__uint_as_float(x.z) + bf16_round(v[g * 4 + 2]));
-              x.w = __float_as_uint(__uint_as_float(x.w) + bf16_round(v[g * 4 + 3]));
+              bf16_round_pair(v[g * 4 + 0], v[g * 4 + 1]);
+              bf16_round_pair(v[g * 4 + 2], v[g * 4 + 3]);
+              x.x = __float_as_uint(__uint_as_float(x.x) + v[g * 4 + 0]);
+              x.y = __float_as_uint(__uint_as_float(x.y) + v[g * 4 + 1]);
+              x.z = __float_as_uint(__uint_as_float(x.z) + v[g * 4 + 2]);
+              x.w = __float_as_uint(__uint_as_float(x.w) + v[g * 4 + 3]);
               st_shared_v4(a, x);
             }
           } else {   // EPI_DGELU
 #pragma unroll
-            for (int g = 0; g < 8; ++g) {
+            for (int g = 0; g < 4; ++g) {
               const uint32_t a = sbase + ((static_cast<uint32_t>(g) ^ sw) << 4);
               const uint4 hv = ld_shared_v4(a);
               const uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w};
@@ -468,7 +478,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
                 const float2 h2 = unpack_bf16x2(hw[j]);
-                ow[j] = pack_bf16x2(bf16_round(v[g * 8 + 2 * j]) * h2.x, bf16_round(v[g * 8 + 2 * j + 1]) * h2.y);
+                bf16_round_pair(v[g * 8 + 2 * j], v[g * 8 + 2 * j + 1]);
+                ow[j] = pack_bf16x2(v[g * 8 + 2 * j] * h2.x, v[g * 8 + 2 * j + 1] * h2.y);
               }
               st_shared_v4(a, o);
             }
@@ -518,10 +529,10 @@ PFN_encodeTiled get_encode_fn() {
 struct MapKey {
   const void* ptr;
   uint64_t inner, outer, ld;
-  uint32_t box_inner, box_outer, elem_bytes;
+  uint32_t box_inner, box_outer, elem_bytes, swizzle_bytes;
   bool operator==(const MapKey& o) const {
     return ptr == o.ptr && inner == o.inner && outer == o.outer && ld == o.ld && box_inner == o.box_inner &&
-           box_outer == o.box_outer && elem_bytes == o.elem_bytes;
+           box_outer == o.box_outer && elem_bytes == o.elem_bytes && swizzle_bytes == o.swizzle_bytes;
   }
 };
 struct MapKeyHash {
@@ -529,18 +540,18 @@ struct MapKeyHash {
     size_t h = reinterpret_cast<size_t>(k.ptr);
     h ^= k.inner * 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2);
     h ^= k.outer * 0xC2B2AE3D27D4EB4Full + (h << 6) + (h >> 2);
-    h ^= (k.ld * 31 + k.box_inner * 131 + k.box_outer * 7 + k.elem_bytes) + (h << 6) + (h >> 2);
+    h ^= (k.ld * 31 + k.box_inner * 131 + k.box_outer * 7 + k.elem_bytes + k.swizzle_bytes * 3) + (h << 6) + (h >> 2);
     return h;
   }
 };
 
 // Row-major matrix [outer, inner] of bf16 (elem_bytes 2) or f32 (4) with leading dimension ld (elements);
-// 128B-swizzled boxes {box_inner, box_outer}.
+// boxes {box_inner, box_outer}, 128B-swizzled (GEMM operands) or 64B-swizzled (epilogue staging tiles).
 int get_tensor_map(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld,
-                   uint32_t box_inner, uint32_t box_outer, uint32_t elem_bytes = 2) {
+                   uint32_t box_inner, uint32_t box_outer, uint32_t elem_bytes = 2, uint32_t swizzle_bytes = 128) {
   static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
   static std::mutex mu;
-  MapKey key{ptr, inner, outer, ld, box_inner, box_outer, elem_bytes};
+  MapKey key{ptr, inner, outer, ld, box_inner, box_outer, elem_bytes, swizzle_bytes};
   {
     std::lock_guard<std::mutex> lock(mu);
     auto it = cache.find(key);
@@ -566,7 +577,8 @@ int get_tensor_map(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t o
   CUtensorMap m;
   CUresult r = enc(&m, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
                    const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     csm_set_error("cuTensorMapEncodeTiled failed with CUresult %d (inner=%llu outer=%llu ld=%llu box=%ux%u)", (int)r,
                   (unsigned long long)inner, (unsigned long long)outer, (unsigned long long)ld, box_inner, box_outer);
@@ -678,14 +690,14 @@ int launch_gemm(const void* a, uint64_t a_inner, uint64_t a_outer, const void* b
   rc = B_MN ? get_tensor_map(&tb, b, b_inner, b_outer, b_inner, 64, BK)
             : get_tensor_map(&tb, b, b_inner, b_outer, b_inner, BK, p.bn / 2);
   if (rc) return rc;
-  rc = get_tensor_map(&to, out, N, M, N, OUT_F32 ? 32 : 64, 32, OUT_F32 ? 4 : 2);
+  rc = get_tensor_map(&to, out, N, M, N, OUT_F32 ? 16 : 32, 32, OUT_F32 ? 4 : 2, 64);
   if (rc) return rc;
   tx = to;
   if (EPI == EPI_GELU || EPI == EPI_DGELU) {
-    rc = get_tensor_map(&tx, aux, N, M, N, 64, 32, 2);
+    rc = get_tensor_map(&tx, aux, N, M, N, 32, 32, 2, 64);
     if (rc) return rc;
   } else if (EPI == EPI_RESID) {
-    rc = get_tensor_map(&tx, aux, N, M, N, 32, 32, 4);
+    rc = get_tensor_map(&tx, aux, N, M, N, 16, 32, 4, 64);
     if (rc) return rc;
   }
   const int units = p.tiles_m * p.tiles_n * p.splits;
