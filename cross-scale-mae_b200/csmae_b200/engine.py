@@ -114,6 +114,9 @@ class HotPathEngine:
         self._graphs = {}           # key -> dict(fwd graph, outputs, state, static inputs, bwd graph, ...)
         self._warm = {}             # key -> eager steps seen so far
         self.graph_warmup_steps = 2
+        self.use_side_stream = os.environ.get("CSMAE_SIDE_STREAM", "1") != "0"
+        self._side = {}
+        self._side_dirty = False
         self._sync_enabled = False  # overlapped gradient all-reduce (parallel.py)
         self._sync_group = None     # its process group (None = the default group)
         self._sync_world = 1
@@ -125,6 +128,38 @@ class HotPathEngine:
         self._sync_enabled = world > 1
         self._sync_group, self._sync_world, self._sync_groups = group, world, enc_groups
         self._graphs.clear()
+
+    # ------------------------------------------------------------------ second stream for the weight gradients
+    # wgrad GEMMs and bias column sums only feed the flat gradient buffer: they run on a side stream so that their
+    # CTAs fill the SMs the critical chain (dgrad / LayerNorm / attention backward) leaves idle in its tails.  All
+    # buffers they read are per-layer, so the side stream may lag without write-after-read hazards; it is joined
+    # before every gradient-segment boundary.
+    def _side_stream(self, dev):
+        s = self._side.get(dev)
+        if s is None:
+            s = torch.cuda.Stream(device=dev)
+            self._side[dev] = s
+        return s
+
+    def _on_side(self, dev, fn):
+        if not self.use_side_stream:
+            fn()
+            return
+        main = torch.cuda.current_stream(dev)
+        side = self._side_stream(dev)
+        ev = torch.cuda.Event()
+        ev.record(main)
+        side.wait_event(ev)
+        with torch.cuda.stream(side):
+            fn()
+        self._side_dirty = True
+
+    def _join_side(self, dev):
+        if self.use_side_stream and self._side_dirty:
+            ev = torch.cuda.Event()
+            ev.record(self._side_stream(dev))
+            torch.cuda.current_stream(dev).wait_event(ev)
+            self._side_dirty = False
 
     def _issue_allreduce(self, flat, seg, pending):
         import torch.distributed as dist
@@ -519,7 +554,9 @@ class HotPathEngine:
         if boundary is None or len(segs) == 1:
             seg_layers, fire = [], (lambda k: None)
         else:
-            fire = boundary
+            def fire(k):
+                self._join_side(dev)             # the segment's weight gradients must have landed
+                boundary(k)
         g = grad_loss.detach().reshape(1).to(f32).contiguous()
         norm_pix = 1 if m.norm_pix_loss else 0
         rows_d, rows_e = NB * Sd, NB * Se
@@ -584,7 +621,7 @@ class HotPathEngine:
         eres = buf("b.enc.dres", (rows_e, D), f32)
         eres16 = buf("b.enc.dres16", (rows_e, D), bf16)
         call("csm_encoder_out_grad", d_enc, d_feat, eres, eres16, NB, Se, D)
-        self._blocks_bwd("enc", "encoder", len(m.encoder), eres, eres16, NB, Se, D, m.encoder_num_heads, params, w16,
+        eres16 = self._blocks_bwd("enc", "encoder", len(m.encoder), eres, eres16, NB, Se, D, m.encoder_num_heads, params, w16,
                          G, dev, nsm, top_bias_done=False,
                          after_layer=lambda i: fire(1 + seg_layers.index(i)) if i in seg_layers else None)
 
@@ -592,6 +629,7 @@ class HotPathEngine:
         call("csm_cls_grad", eres, G["cls_token"], NB, Se, D)
         call("csm_linear_wgrad", eres16, B["patches"], G["patch_embed.proj.weight"], rows_e, D, P, nsm)
         call("csm_colsum_bf16", eres16, G["patch_embed.proj.bias"], rows_e, D, Se, nsm)
+        self._join_side(dev)
         if len(segs) > 1:
             fire(len(segs) - 1)
         elif boundary is not None:
@@ -609,37 +647,56 @@ class HotPathEngine:
             t, q = f"{tag}.{i}.", f"{pname}.{i}."
             hid = params[q + "mlp.fc1.weight"].shape[0]
             x_in = B[f"{tag}.{i - 1}.xout"] if i > 0 else B[f"{tag}.x0"]
+            # gradient buffers the side-stream wgrads read are per layer (no reuse hazards); dres16 enters as the
+            # previous LayerNorm backward's bf16 output
+            dh = buf(f"b.{tag}.{i}.dh", (rows, hid), bf16)
+            dqkv = buf(f"b.{tag}.{i}.dqkv", (rows, 3 * Dm), bf16)
+            d16a = buf(f"b.{tag}.{i}.d16a", (rows, Dm), bf16)
+            d16b = buf(f"b.{tag}.{i}.d16b", (rows, Dm), bf16)
             # MLP branch: x_out = x_mid + fc2(gelu(fc1(norm2(x_mid))))
-            call("csm_linear_wgrad", dres16, B[t + "act"], G[q + "mlp.fc2.weight"], rows, Dm, hid, nsm)
-            if i == nlayers - 1 and not top_bias_done:
-                call("csm_colsum_bf16", dres16, G[q + "mlp.fc2.bias"], rows, Dm, 0, nsm)
-            dh = buf(f"b.{tag}.dh", (rows, hid), bf16)
+            first_bias = (i == nlayers - 1 and not top_bias_done)
+
+            def side_fc2(dres16=dres16, t=t, q=q, hid=hid, first_bias=first_bias):
+                call("csm_linear_wgrad", dres16, B[t + "act"], G[q + "mlp.fc2.weight"], rows, Dm, hid, nsm)
+                if first_bias:
+                    call("csm_colsum_bf16", dres16, G[q + "mlp.fc2.bias"], rows, Dm, 0, nsm)
+            self._on_side(dev, side_fc2)
             call("csm_linear_dgrad", dres16, w16[q + "mlp.fc2.weight"], dh, B[t + "gp"], rows, Dm, hid, EPI_DGELU)
-            call("csm_linear_wgrad", dh, B[t + "ln2"], G[q + "mlp.fc1.weight"], rows, hid, Dm, nsm)
-            call("csm_colsum_bf16", dh, G[q + "mlp.fc1.bias"], rows, hid, 0, nsm)
+
+            def side_fc1(dh=dh, t=t, q=q, hid=hid):
+                call("csm_linear_wgrad", dh, B[t + "ln2"], G[q + "mlp.fc1.weight"], rows, hid, Dm, nsm)
+                call("csm_colsum_bf16", dh, G[q + "mlp.fc1.bias"], rows, hid, 0, nsm)
+            self._on_side(dev, side_fc1)
             dln = buf(f"b.{tag}.dln", (rows, Dm), bf16)
             call("csm_linear_dgrad", dh, w16[q + "mlp.fc1.weight"], dln, None, rows, hid, Dm, EPI_BF16)
             call("csm_layernorm_bwd", dln, None, B[t + "xmid"], B[t + "mean2"], B[t + "rstd2"],
-                 params[q + "norm2.weight"], dres, dres, dres16, G[q + "norm2.weight"], G[q + "norm2.bias"],
+                 params[q + "norm2.weight"], dres, dres, d16a, G[q + "norm2.weight"], G[q + "norm2.bias"],
                  G[q + "attn.proj.bias"], rows, Dm, nsm)
             # attention branch: x_mid = x_in + proj(attn(qkv(norm1(x_in))))
-            call("csm_linear_wgrad", dres16, B[t + "ao"], G[q + "attn.proj.weight"], rows, Dm, Dm, nsm)
+
+            def side_proj(d16a=d16a, t=t, q=q):
+                call("csm_linear_wgrad", d16a, B[t + "ao"], G[q + "attn.proj.weight"], rows, Dm, Dm, nsm)
+            self._on_side(dev, side_proj)
             d_ao = buf(f"b.{tag}.d_ao", (rows, Dm), bf16)
-            call("csm_linear_dgrad", dres16, w16[q + "attn.proj.weight"], d_ao, None, rows, Dm, Dm, EPI_BF16)
-            dqkv = buf(f"b.{tag}.dqkv", (rows, 3 * Dm), bf16)
+            call("csm_linear_dgrad", d16a, w16[q + "attn.proj.weight"], d_ao, None, rows, Dm, Dm, EPI_BF16)
             delta = buf(f"b.{tag}.delta", (NB * heads * S,), f32)
             # (the kernel can also emit the qkv.bias column sums itself -- measured slower than the separate
             #  pass on B200: the extra tail per CTA is not hidden at one CTA per SM)
             call("csm_attention_bwd", B[t + "qkv"], B[t + "ao"], d_ao, B[t + "lse"], delta, dqkv, None,
                  NB, S, heads, d)
-            call("csm_linear_wgrad", dqkv, B[t + "ln1"], G[q + "attn.qkv.weight"], rows, 3 * Dm, Dm, nsm)
-            call("csm_colsum_bf16", dqkv, G[q + "attn.qkv.bias"], rows, 3 * Dm, 0, nsm)
+
+            def side_qkv(dqkv=dqkv, t=t, q=q):
+                call("csm_linear_wgrad", dqkv, B[t + "ln1"], G[q + "attn.qkv.weight"], rows, 3 * Dm, Dm, nsm)
+                call("csm_colsum_bf16", dqkv, G[q + "attn.qkv.bias"], rows, 3 * Dm, 0, nsm)
+            self._on_side(dev, side_qkv)
             call("csm_linear_dgrad", dqkv, w16[q + "attn.qkv.weight"], dln, None, rows, 3 * Dm, Dm, EPI_BF16)
             below_fc2_bias = G[f"{pname}.{i - 1}.mlp.fc2.bias"] if i > 0 else None
             call("csm_layernorm_bwd", dln, None, x_in, B[t + "mean1"], B[t + "rstd1"], params[q + "norm1.weight"],
-                 dres, dres, dres16, G[q + "norm1.weight"], G[q + "norm1.bias"], below_fc2_bias, rows, Dm, nsm)
+                 dres, dres, d16b, G[q + "norm1.weight"], G[q + "norm1.bias"], below_fc2_bias, rows, Dm, nsm)
+            dres16 = d16b
             if after_layer is not None:
                 after_layer(i)
+        return dres16
 
 
 class CrossScaleStep(torch.autograd.Function):
