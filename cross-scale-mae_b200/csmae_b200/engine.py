@@ -120,7 +120,7 @@ class HotPathEngine:
         self._sync_enabled = False  # overlapped gradient all-reduce (parallel.py)
         self._sync_group = None     # its process group (None = the default group)
         self._sync_world = 1
-        self._sync_groups = 3       # encoder layer groups -> 2 + groups all-reduce segments
+        self._sync_groups = 3       # encoder layer groups -> 1 + groups all-reduce segments
 
     def enable_grad_sync(self, group, world, enc_groups=3):
         """Data-parallel gradient averaging inside the backward: the flat gradient buffer is all-reduced in
@@ -165,7 +165,9 @@ class HotPathEngine:
         import torch.distributed as dist
         start, end = seg
         if end > start:
-            pending.append(dist.all_reduce(flat[start:end], op=dist.ReduceOp.AVG, group=self._sync_group, async_op=True))
+            # SUM: the 1/world factor is folded into the loss gradient the chain starts from (every kernel of the
+            # backward is linear in it), so no pass over the buffer is spent on the division
+            pending.append(dist.all_reduce(flat[start:end], op=dist.ReduceOp.SUM, group=self._sync_group, async_op=True))
 
     # ------------------------------------------------------------------ parameters
     def param_names(self):
@@ -464,6 +466,8 @@ class HotPathEngine:
                 "same module (the workspace holds one step); call backward before the next forward")
         entry = getattr(self, "_active_graph", None)
         sync = self._sync_enabled
+        if sync:
+            grad_loss = grad_loss / self._sync_world          # gradients are averaged over the replicas
         if entry is None:
             pending = []
             segs_box = {}

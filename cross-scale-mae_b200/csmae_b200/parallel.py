@@ -7,7 +7,7 @@ main_pretrain.py:417-421) -- tools/ddp_smoke.py exercises that.  But the hand-wr
 gradients to autograd at once, so torch's bucketed all-reduce cannot overlap it and pays ~260 bucket copies in
 and out.  `DistributedDataParallel` below is the drop-in for that wrapper (same constructor call, `.module`,
 forward passthrough) that lets the engine do the exchange itself: the flat fp32 gradient buffer is all-reduced
-(AVG) in 2 + enc_groups segments as the backward chain completes them, on NCCL's stream, overlapping the rest of
+in 1 + enc_groups segments as the backward chain completes them, on NCCL's stream, overlapping the rest of
 the backward; no per-parameter hooks, no bucket copies.
 
 Semantics kept from the reference setup: rank 0's parameters and buffers are broadcast at construction (C2),

@@ -193,6 +193,88 @@ def test_ddp_gloo_world2():
     assert sorted(results) == [(0, True), (1, True)], results
 
 
+def _native_ddp_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    sys.path.insert(0, os.path.join(ROOT, "cross-scale-mae_b200"))
+    import csmae_b200
+    from csmae_b200.engine import grad_segments
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(100 + rank)
+    cfg = dict(dim_model=64, encoder_num_layers=4, encoder_num_heads=1, decoder_embed_dim=64, decoder_num_layers=2,
+               decoder_num_heads=2, input_size=64, patch_size=16, predictor_hidden_size=64)
+    m = csmae_b200.MAE_ViT_MsLdCeCd(**cfg, device="cpu")
+    eng = m._engine
+    eng.use_graphs = False
+    fired = []
+
+    def fake_forward(imgs_list, noises, mask_ratio, training):
+        eng.generation += 1
+        eng._state = dict(generation=eng.generation)
+        eng._active_graph = None
+        n = imgs_list[0].shape[0]
+        z = torch.zeros(n, 16, 768)
+        return dict(loss=torch.tensor(float(rank + 1)), pred=[z, z], mask=[z[..., 0], z[..., 0]],
+                    enc_emb=[z, z], dec_emb=[z, z])
+
+    def fake_chain(grad_loss, flat, boundary=None, segs_box=None):
+        # stands in for the kernel chain: fills the flat gradient buffer and reports the segment boundaries in
+        # completion order exactly as HotPathEngine._backward_eager does
+        names = eng.param_names()
+        pd = dict(m.named_parameters())
+        sizes = [pd[n].numel() for n in names]
+        offs, total = [], 0
+        for s_ in sizes:
+            offs.append(total)
+            total += (s_ + 3) // 4 * 4
+        flat = torch.zeros(total)
+        segs, _ = grad_segments(names, offs, total, len(m.encoder), eng._sync_groups)
+        segs_box["flat"], segs_box["segs"] = flat, segs
+        for k, (a, b) in enumerate(segs):
+            flat[a:b] = float(rank + 1) * float(grad_loss)
+            fired.append(k)
+            boundary(k)
+        return flat, [flat[o:o + s_].view(pd[n].shape) for n, o, s_ in zip(names, offs, sizes)]
+
+    eng.forward, eng._backward_eager = fake_forward, fake_chain
+    ddp = csmae_b200.DistributedDataParallel(m, device_ids=None, find_unused_parameters=True)
+    w0 = m.decoder_pred.weight.detach().clone()
+    loss, _, _ = ddp(torch.randn(2, 3, 64, 64), torch.randn(2, 3, 64, 64), 0.75)
+    (loss * 2.0).backward()
+    ok = fired == list(range(len(fired))) and len(fired) == 1 + min(3, 4)   # decoder tail + 2 encoder groups + head
+    for n, p in m.named_parameters():
+        if n.startswith("encoder_norm.") or not p.requires_grad:
+            ok &= p.grad is None
+        else:
+            ok &= bool(torch.allclose(p.grad, torch.full_like(p.grad, 2.0 * (1 + 2) / 2)))   # mean of 2*(rank+1)
+    gathered = [torch.zeros_like(w0) for _ in range(world)]
+    dist.all_gather(gathered, w0)
+    ok &= bool(torch.equal(gathered[0], gathered[1]))                             # rank-0 broadcast at construction
+    q.put((rank, bool(ok)))
+    dist.destroy_process_group()
+
+
+def test_native_ddp_gloo_world2():
+    """csmae_b200.DistributedDataParallel (engine-overlapped gradient all-reduce) on 2 CPU ranks over gloo: the
+    kernel chain is stubbed, the segment / all-reduce / averaging / broadcast plumbing is the real one."""
+    import socket
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_native_ddp_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(results) == [(0, True), (1, True)], results
+
+
 def test_grad_segments_cover_flat_buffer_in_completion_order():
     """Host logic of the overlapped gradient all-reduce (engine.grad_segments): segments are disjoint, cover
     the whole flat buffer, the decoder tail comes first and the head (cls/mask/patch_embed/decoder_embed +
