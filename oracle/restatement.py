@@ -287,7 +287,7 @@ FROZEN_KEYS = ("encoder_pos_embed", "decoder_pos_embed")
 
 
 def loss_and_grads(sd, imgs1, imgs2, noise1, noise2, mask_ratio, enc_heads, dec_heads,
-                   autocast_dtype=None, paired=True, loss_scale=1.0):
+                   autocast_dtype=None, paired=True, loss_scale=1.0, **forward_kwargs):
     """Runs the restatement with autograd; returns (outputs dict, grads dict keyed like sd)."""
     leaves = {k: v.detach().clone().requires_grad_(k not in FROZEN_KEYS) for k, v in sd.items()}
     dev = imgs1.device.type
@@ -296,7 +296,7 @@ def loss_and_grads(sd, imgs1, imgs2, noise1, noise2, mask_ratio, enc_heads, dec_
     with ctx:
         if paired:
             out = cross_scale_forward(leaves, imgs1, imgs2, noise1, noise2, mask_ratio,
-                                      enc_heads, dec_heads)
+                                      enc_heads, dec_heads, **forward_kwargs)
         else:
             out = baseline_pass(leaves, imgs1, noise1, mask_ratio, enc_heads, dec_heads)
     (out["loss"] * loss_scale).backward()

@@ -222,3 +222,46 @@ def test_cuda_graph_replay_matches_eager():
         loss.backward()
     k = "decoder.0.attn.qkv.weight"
     assert rel_l2(dict(m.named_parameters())[k].grad, 2 * eager[0][3][k]) < 1e-4
+
+
+EDGE_CASES = {
+    "batch1": dict(bs=1, size=96, ratio=0.75),
+    "keep1_of_16": dict(bs=3, size=64, ratio=0.9),            # int(16 * 0.1) = 1 kept patch -> encoder S = 2
+    "ratio0.25": dict(bs=5, size=96, ratio=0.25),
+    "norm_pix": dict(bs=4, size=96, ratio=0.75, model=dict(norm_pix_loss=True), oracle=dict(norm_pix_loss=True)),
+    "mean_reduction": dict(bs=4, size=96, ratio=0.75, model=dict(ms_decoder_loss_reduction="mean"),
+                           oracle=dict(reduction="mean")),
+    # BASELINE.json configs[4] geometry (448 px: L = 784, decoder S = 785, encoder S = 197) on a narrow model:
+    # the long-sequence attention paths (d = 32 with S > 256, d = 64 with S > 64)
+    "long_sequence_448": dict(bs=2, size=448, ratio=0.75),
+}
+
+
+@pytest.mark.parametrize("name", sorted(EDGE_CASES))
+def test_edge_cases_against_oracle(name):
+    """Ragged / extreme shapes and the non-default loss options through the whole forward + backward, against
+    the oracle in fp32 and under bf16 autocast (same acceptance rule as the full-size test)."""
+    import csmae_b200
+    case = EDGE_CASES[name]
+    bs, size, ratio = case["bs"], case["size"], case["ratio"]
+    torch.manual_seed(0)
+    cfg = dict(dim_model=128, encoder_num_layers=2, encoder_num_heads=2, decoder_embed_dim=64, decoder_num_layers=2,
+               decoder_num_heads=2, input_size=size, patch_size=16, predictor_hidden_size=128)
+    m = csmae_b200.MAE_ViT_MsLdCeCd(**cfg, **case.get("model", {}), device="cuda").cuda().train()
+    g = torch.Generator(device="cuda").manual_seed(7)
+    imgs1 = torch.randn(bs, 3, size, size, device="cuda", generator=g)
+    imgs2 = torch.randn(bs, 3, size, size, device="cuda", generator=g)
+    L = m.num_patches
+    n1, n2 = torch.rand(bs, L, device="cuda", generator=g), torch.rand(bs, L, device="cuda", generator=g)
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items() if "running" not in k and "num_batches" not in k}
+    loss, pred, mask = m(imgs1, imgs2, ratio, noise=[n1, n2])
+    loss.backward()
+    kw = case.get("oracle", {})
+    o32, g32 = R.loss_and_grads(sd, imgs1, imgs2, n1, n2, ratio, 2, 2, **kw)
+    o16, g16 = R.loss_and_grads(sd, imgs1, imgs2, n1, n2, ratio, 2, 2, autocast_dtype=bf16, **kw)
+    assert torch.equal(mask, o32["mask"]) and int(mask.sum()) == bs * (L - int(L * (1 - ratio)))
+    lf, l32, l16 = loss.item(), o32["loss"].item(), o16["loss"].item()
+    print(f"[{name}] loss ours {lf:.6f} oracle-fp32 {l32:.6f} oracle-bf16 {l16:.6f}")
+    assert abs(lf - l32) <= max(1e-3 * abs(l32) + 1e-5, 2 * abs(l16 - l32))
+    assert rel_l2(pred, o32["pred"]) <= max(1e-2, 3 * rel_l2(o16["pred"], o32["pred"]))
+    check_grads({n: p.grad for n, p in m.named_parameters()}, g32, g16, floor=3e-2)
