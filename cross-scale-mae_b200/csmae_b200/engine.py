@@ -481,8 +481,7 @@ class HotPathEngine:
             self._state = None
             return views
         # graphed step: the gradient chain is captured once over static buffers (in several graphs when the
-        # gradient all-reduce is overlapped: one per segment); what autograd receives is a copy of the flat
-        # gradient buffer (one 4 B/param device copy), so .grad never aliases graph memory
+        # gradient all-reduce is overlapped: one per segment)
         if entry["bwd"] is None:
             entry["g"] = torch.zeros(1, dtype=torch.float32, device=grad_loss.device)
             entry["g"].copy_(grad_loss.detach().reshape(1))
@@ -509,23 +508,36 @@ class HotPathEngine:
             entry["segs"] = segs_box.get("segs", [(0, total)])
             self._state = st                   # capture does not run the kernels; replay below does
         entry["g"].copy_(grad_loss.detach().reshape(1), non_blocking=True)
+        flat = entry["flat"]
+
+        def views_of(buf):
+            if entry["dense"]:
+                return list(torch._utils._unflatten_dense_tensors(buf, entry["like"]))
+            out_views, off = [], 0
+            for p in entry["like"]:
+                out_views.append(buf[off:off + p.numel()].view(p.shape))
+                off += (p.numel() + 3) // 4 * 4
+            return out_views
+
+        # The views handed to autograd alias the graph's gradient buffer (no 4 B/param copy per step); autograd
+        # adopts them as .grad when .grad is None.  If a .grad still aliases the buffer when the next backward
+        # starts (gradient accumulation without zero_grad), the accumulated values are moved out first.
+        first = entry["like"][0]
+        if first.grad is not None and first.grad.data_ptr() == flat.data_ptr():
+            saved = flat.clone()
+            for p, v in zip(entry["like"], views_of(saved)):
+                if p.grad is not None:
+                    p.grad = v
         pending = []
         for k, g in enumerate(entry["bwd"]):
             g.replay()
             if sync and k < len(entry["segs"]):
-                self._issue_allreduce(entry["flat"], entry["segs"][k], pending)
+                self._issue_allreduce(flat, entry["segs"][k], pending)
         for w in pending:
             w.wait()
         nat.launch_count += entry["bwd_launches"]
         self._state = None
-        out = entry["flat"].clone()
-        if entry["dense"]:
-            return list(torch._utils._unflatten_dense_tensors(out, entry["like"]))
-        views, off = [], 0
-        for p in entry["like"]:
-            views.append(out[off:off + p.numel()].view(p.shape))
-            off += (p.numel() + 3) // 4 * 4
-        return views
+        return views_of(flat)
 
     def _backward_eager(self, grad_loss, flat, boundary=None, segs_box=None):
         """The hand-written backward chain.  boundary(k), when given, is called right after the kernels that

@@ -281,7 +281,8 @@ def attn_ref(qkv, B, S, H, d):
 
 
 @pytest.mark.parametrize("B,S,H,d", [(8, 50, 12, 64), (4, 197, 16, 32), (2, 785, 4, 32), (3, 197, 2, 64),
-                                     (5, 5, 1, 64), (3, 17, 2, 32), (2, 64, 2, 32), (2, 65, 1, 64)])
+                                     (5, 5, 1, 64), (3, 17, 2, 32), (2, 64, 2, 32), (2, 65, 1, 64), (2, 100, 3, 32),
+                                     (1, 257, 2, 32)])
 def test_attention_fwd_bwd(nat, B, S, H, d):
     Dm = H * d
     qkv = rnd(B * S, 3 * Dm, dtype=bf16)
@@ -303,6 +304,12 @@ def test_attention_fwd_bwd(nat, B, S, H, d):
     assert err <= 3e-2 * g.abs().max().item() + 1e-3, f"attention bwd max err {err:.3e} vs max {g.abs().max():.3e}"
     rel = ((dqkv.float() - g).norm() / g.norm()).item()
     assert rel < 2e-2, f"attention bwd relative L2 error {rel:.3e}"
+    # without the fused bias sums the launcher may pick another kernel (two-pass at d = 32): same contract
+    dqkv2 = torch.full((B * S, 3 * Dm), float("nan"), device="cuda", dtype=bf16)
+    nat.call("csm_attention_bwd", qkv, out, d_out, lse, delta, dqkv2, None, B, S, H, d)
+    err2 = (dqkv2.float() - g).abs().max().item()
+    assert err2 <= 3e-2 * g.abs().max().item() + 1e-3, f"attention bwd (no bias sums) max err {err2:.3e}"
+    assert ((dqkv2.float() - g).norm() / g.norm()).item() < 2e-2
     # fused qkv.bias gradient: column sums of dqkv over the tokens
     bref = g.sum(0)
     berr = (dbias - bref).abs().max().item()

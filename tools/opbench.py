@@ -144,7 +144,7 @@ def main():
             dqkv = torch.empty_like(qkv)
             delta = torch.empty_like(lse)
             dbias = torch.zeros(3 * Dm, device=dev)
-            us = timeit(lambda: nat.call("csm_attention_bwd", qkv, o, do, lse, delta, dqkv, dbias, NB, S, H, d),
+            us = timeit(lambda: nat.call("csm_attention_bwd", qkv, o, do, lse, delta, dqkv, None, NB, S, H, d),
                         args.iters, flush)
             report("attn", f"attention_bwd {name}", [NB, S, H, d], us, flops=2.5 * fl,
                    nbytes=NB * S * Dm * 2 * 8 + NB * H * S * 8)
