@@ -141,12 +141,12 @@ def run_reference(args):
     sec = cpu_reference_step_time(args.arch, args.input_size, cpu_batch, args.steps, max(1, min(args.warmup, 1)))
     ips = cpu_batch / sec
     cores = torch.get_num_threads()
-    sample = (f"{args.steps} timed steps of fwd+bwd+AdamW at batch {cpu_batch} (images/s is batch-insensitive on "
-              f"CPU), fp32, oracle/restatement.py")
+    sample = (f"{args.steps} timed steps of fwd+bwd+AdamW, each on a {cpu_batch}-image sample of the workload's batch "
+              f"(images/s is batch-insensitive on CPU), fp32, all host threads, oracle/restatement.py")
     line = {"impl": "reference", "metric": METRIC, "value": ips, "unit": "images/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(args, cpu_batch, 1),
+            "config": workload_config(args, args.batch, max(1, args.gpus)),
             "cpu_baseline": {"value": ips, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)

@@ -597,12 +597,14 @@ attn_bwd_head_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16*
 }
 
 // ---------------------------------------------------------------------------------------------
-// long sequences (S16 > 256), two kernels.
+// long sequences (S16 > 256), two kernels; CTAs of blockDim/32 warps = RPC = 16 * warps rows each (16 warps at
+// d = 32, 8 at d = 64: the whole K/V or Q/dO of the head fills most of an SM's shared memory, so the CTA has
+// to bring its own occupancy).
 // backward, dQ: grid (B*H, ceil(S/64)); K,V of the head + the Q/dO/O rows of this block in smem.
 // Also writes delta[bh, s] = sum_j dO[s, j] * O[s, j] for the dK/dV kernel.
 // ---------------------------------------------------------------------------------------------
 template <int DH>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(DH == 32 ? 512 : 256)
 attn_bwd_dq_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ o_fwd,
                    const __nv_bfloat16* __restrict__ d_out, const float* __restrict__ lse,
                    float* __restrict__ delta, __nv_bfloat16* __restrict__ dqkv, int S, int H, int Dm, float c,
@@ -612,19 +614,20 @@ attn_bwd_dq_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* _
   const int S_pad = (S + 31) / 32 * 32;
   __nv_bfloat16* sK = reinterpret_cast<__nv_bfloat16*>(smem_attn);
   __nv_bfloat16* sV = sK + S_pad * LDS;
+  const int rpc = (blockDim.x >> 5) * 16;          // query rows per CTA
   __nv_bfloat16* sQ = sV + S_pad * LDS;
-  __nv_bfloat16* sdO = sQ + 64 * LDS;
-  __nv_bfloat16* sO = sdO + 64 * LDS;
+  __nv_bfloat16* sdO = sQ + rpc * LDS;
+  __nv_bfloat16* sO = sdO + rpc * LDS;
   const int bh = blockIdx.x, b = bh / H, h = bh % H;
-  const int q0 = blockIdx.y * 64;
+  const int q0 = blockIdx.y * rpc;
   const size_t ld = static_cast<size_t>(3) * Dm;
   const __nv_bfloat16* base = qkv + static_cast<size_t>(b) * S * ld + h * DH;
   const size_t obase = static_cast<size_t>(b) * S * Dm + h * DH;
   load_rows<DH>(sK, base + Dm, 0, S, S_pad, ld);
   load_rows<DH>(sV, base + 2 * Dm, 0, S, S_pad, ld);
-  load_rows<DH>(sQ, base, q0, S, 64, ld);
-  load_rows<DH>(sdO, d_out + obase, q0, S, 64, Dm);
-  load_rows<DH>(sO, o_fwd + obase, q0, S, 64, Dm);
+  load_rows<DH>(sQ, base, q0, S, rpc, ld);
+  load_rows<DH>(sdO, d_out + obase, q0, S, rpc, Dm);
+  load_rows<DH>(sO, o_fwd + obase, q0, S, rpc, Dm);
   __syncthreads();
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -695,7 +698,7 @@ attn_bwd_dq_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* _
 // backward, dK/dV: grid (B*H, ceil(S/64)); Q,dO of the head + the K/V rows of this block in smem.
 // ---------------------------------------------------------------------------------------------
 template <int DH>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(DH == 32 ? 512 : 256)
 attn_bwd_dkv_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ d_out,
                     const float* __restrict__ lse, const float* __restrict__ delta,
                     __nv_bfloat16* __restrict__ dqkv, int S, int H, int Dm, float c, float scale) {
@@ -704,19 +707,20 @@ attn_bwd_dkv_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* 
   const int S_pad = (S + 31) / 32 * 32;
   __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(smem_attn);
   __nv_bfloat16* sdO = sQ + S_pad * LDS;
+  const int rpc = (blockDim.x >> 5) * 16;          // key rows per CTA
   __nv_bfloat16* sK = sdO + S_pad * LDS;
-  __nv_bfloat16* sV = sK + 64 * LDS;
-  float* sLse = reinterpret_cast<float*>(sV + 64 * LDS);
+  __nv_bfloat16* sV = sK + rpc * LDS;
+  float* sLse = reinterpret_cast<float*>(sV + rpc * LDS);
   float* sDelta = sLse + S_pad;
   const int bh = blockIdx.x, b = bh / H, h = bh % H;
-  const int k0 = blockIdx.y * 64;
+  const int k0 = blockIdx.y * rpc;
   const size_t ld = static_cast<size_t>(3) * Dm;
   const __nv_bfloat16* base = qkv + static_cast<size_t>(b) * S * ld + h * DH;
   const size_t obase = static_cast<size_t>(b) * S * Dm + h * DH;
   load_rows<DH>(sQ, base, 0, S, S_pad, ld);
   load_rows<DH>(sdO, d_out + obase, 0, S, S_pad, Dm);
-  load_rows<DH>(sK, base + Dm, k0, S, 64, ld);
-  load_rows<DH>(sV, base + 2 * Dm, k0, S, 64, ld);
+  load_rows<DH>(sK, base + Dm, k0, S, rpc, ld);
+  load_rows<DH>(sV, base + 2 * Dm, k0, S, rpc, ld);
   for (int i = threadIdx.x; i < S_pad; i += blockDim.x) {
     sLse[i] = i < S ? lse[static_cast<size_t>(bh) * S + i] : INFINITY;
     sDelta[i] = i < S ? delta[static_cast<size_t>(bh) * S + i] : 0.f;
@@ -856,20 +860,22 @@ int attn_bwd_launch(const void* qkv, const void* o, const void* d_out, const flo
   }
   CSM_CHECK_ARG(delta != nullptr, "csm_attention_bwd: S=%d needs the delta scratch buffer", S);
   const int S_pad = (S + 31) / 32 * 32;
-  dim3 grid(B * H, (S + 63) / 64);
-  const size_t smem_dq = static_cast<size_t>(2 * S_pad + 3 * 64) * (DH + 8) * 2;
+  const int warps = DH == 32 ? 16 : 8;
+  const int rpc = warps * 16;
+  dim3 grid(B * H, (S + rpc - 1) / rpc);
+  const size_t smem_dq = static_cast<size_t>(2 * S_pad + 3 * rpc) * (DH + 8) * 2;
   static size_t cfg_dq = 0, cfg_dkv = 0;
   int rc = set_smem(attn_bwd_dq_kernel<DH>, smem_dq, &cfg_dq, "attention_bwd_dq");
   if (rc) return rc;
-  attn_bwd_dq_kernel<DH><<<grid, 128, smem_dq, stream>>>(
+  attn_bwd_dq_kernel<DH><<<grid, warps * 32, smem_dq, stream>>>(
       reinterpret_cast<const __nv_bfloat16*>(qkv), reinterpret_cast<const __nv_bfloat16*>(o),
       reinterpret_cast<const __nv_bfloat16*>(d_out), lse, delta, reinterpret_cast<__nv_bfloat16*>(dqkv), S, H, Dm, c,
       scale);
   CSM_CHECK_LAUNCH("attention_bwd_dq");
-  const size_t smem_dkv = static_cast<size_t>(2 * S_pad + 2 * 64) * (DH + 8) * 2 + static_cast<size_t>(2) * S_pad * 4;
+  const size_t smem_dkv = static_cast<size_t>(2 * S_pad + 2 * rpc) * (DH + 8) * 2 + static_cast<size_t>(2) * S_pad * 4;
   rc = set_smem(attn_bwd_dkv_kernel<DH>, smem_dkv, &cfg_dkv, "attention_bwd_dkv");
   if (rc) return rc;
-  attn_bwd_dkv_kernel<DH><<<grid, 128, smem_dkv, stream>>>(
+  attn_bwd_dkv_kernel<DH><<<grid, warps * 32, smem_dkv, stream>>>(
       reinterpret_cast<const __nv_bfloat16*>(qkv), reinterpret_cast<const __nv_bfloat16*>(d_out), lse, delta,
       reinterpret_cast<__nv_bfloat16*>(dqkv), S, H, Dm, c, scale);
   CSM_CHECK_LAUNCH("attention_bwd_dkv");
