@@ -265,3 +265,17 @@ def test_edge_cases_against_oracle(name):
     assert abs(lf - l32) <= max(1e-3 * abs(l32) + 1e-5, 2 * abs(l16 - l32))
     assert rel_l2(pred, o32["pred"]) <= max(1e-2, 3 * rel_l2(o16["pred"], o32["pred"]))
     check_grads({n: p.grad for n, p in m.named_parameters()}, g32, g16, floor=3e-2)
+
+
+def test_device_prefetcher_order_and_values():
+    """csmae_b200.DevicePrefetcher yields every pinned host batch once, in order, on the device, copied on a
+    side stream while the previous batch is being consumed."""
+    from csmae_b200 import DevicePrefetcher
+    host = [(torch.full((4, 3, 8, 8), float(i)).pin_memory(), torch.tensor([i])) for i in range(7)]
+    seen = []
+    for x, y in DevicePrefetcher(host, "cuda", depth=2):
+        assert x.is_cuda and y.is_cuda
+        (x * 2).sum()                          # consume on the compute stream
+        seen.append((int(x[0, 0, 0, 0].item()), int(y.item())))
+    assert seen == [(i, i) for i in range(7)]
+    assert len(DevicePrefetcher(host, "cuda")) == 7
