@@ -310,7 +310,7 @@ def main():
     ips_e2e = B * world / (ms_e2e * 1e-3)
     # DRAM bytes per GEMM launch from the committed ncu --set full capture of the same shapes (ViT-B only)
     traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r1c_gemm_dram_traffic.json")
+    tpath = os.path.join(ROOT, "profiles", "r1e_gemm_dram_traffic.json")
     if args.arch == "base" and args.input_size == 224 and B == 64 and os.path.exists(tpath):
         with open(tpath) as f:
             traffic = json.load(f)["avg_bytes_per_launch"]
