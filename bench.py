@@ -276,23 +276,38 @@ def main():
     # trains, and the loss is read back to the host
     from csmae_b200 import DevicePrefetcher
 
-    def e2e_run(k):
-        last = None
+    def e2e_run(k, lag):
+        # every step's loss is read back to the host; with lag=1 the read of step i is issued after step i+1 has
+        # been enqueued (asynchronous logging: the GPU never waits for the host between steps)
+        last, prev = None, None
         for x1, x2 in DevicePrefetcher(((host1, host2) for _ in range(k)), dev):
-            last = step(x1, x2).item()
+            loss_t = step(x1, x2)
+            if lag:
+                if prev is not None:
+                    last = prev.item()
+                prev = loss_t
+            else:
+                last = loss_t.item()
+        if prev is not None:
+            last = prev.item()
         return last
-    e2e_run(3)
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    e2e_run(args.steps)
-    e1.record()
-    barrier()
-    ms_e2e = e0.elapsed_time(e1) / args.steps
-    if world > 1:
-        t = torch.tensor([ms_e2e], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_e2e = t.item()
+
+    def e2e_timed(lag):
+        e2e_run(3, lag)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        e2e_run(args.steps, lag)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1) / args.steps
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = t.item()
+        return ms
+    ms_e2e_sync = e2e_timed(0)       # loss.item() right after every step, as engine_pretrain.py:55 does
+    ms_e2e = e2e_timed(1)            # same reads, one step late
     sampler.stop_flag.set()
 
     # per-kernel breakdown of one step with CUDA events on the launching stream (outside the timed region)
@@ -331,7 +346,10 @@ def main():
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": workload_config(args, B, world),
             "fwd_bwd_ms": ms_fwd_bwd, "host_enqueue_ms_per_step": host_ms, "gpu_launches": launches,
             "e2e": {"value": ips_e2e, "unit": "images/s", "ms_per_step": ms_e2e,
-                    "h2d_bytes_per_step": int(host1.numel() * 4 * 2), "d2h_bytes_per_step": 4},
+                    "h2d_bytes_per_step": int(host1.numel() * 4 * 2), "d2h_bytes_per_step": 4,
+                    "loss_read": "every step, issued after the next step is enqueued (1-step lag)",
+                    "immediate_read_ms_per_step": ms_e2e_sync,
+                    "immediate_read_value": B * world / (ms_e2e_sync * 1e-3)},
             "clocks": sampler.summary(), "roofline": roofline,
             "flops_per_image": fl, "kernel_ms": {k: round(v["ms"], 4) for k, v in sorted(
                 breakdown.items(), key=lambda kv: -kv[1]["ms"])}}

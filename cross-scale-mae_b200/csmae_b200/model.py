@@ -189,11 +189,11 @@ class MAE_ViT_Baseline(nn.Module):
         if noises is None:
             noises = [self._draw_noise(im.shape[0], im.device, mask_seed) for im in imgs_list]
         plist = eng.snapshot()["plist"]
+        # kernels first, autograd bookkeeping second (it then overlaps the GPU)
+        out = eng.forward(imgs_list, noises, mask_ratio, self.training)
         if torch.is_grad_enabled() and any(p.requires_grad for p in plist):
-            loss = CrossScaleStep.apply(eng, imgs_list, noises, mask_ratio, self.training, *plist)
-            out = eng._last_out
+            loss = CrossScaleStep.apply(eng, out["loss"], eng.generation, *plist)
         else:
-            out = eng.forward(imgs_list, noises, mask_ratio, self.training)
             loss = out["loss"].clone()
         return loss, out
 
