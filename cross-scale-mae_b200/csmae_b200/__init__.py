@@ -4,13 +4,13 @@ Drop-in for the reference's `models_mae` namespace on that path: the constructor
 nn.Modules with the reference's parameter names and forward signatures; all arithmetic runs in
 hand-written CUDA kernels behind the C-ABI declared in include/csmae_b200.h.
 """
-from .model import (MAE_ViT_Baseline, MAE_ViT_MsLd, MAE_ViT_MsLdCeCd, args_mae_vit_base, args_mae_vit_large,
-                    mae_vit_base, mae_vit_base_MsLd, mae_vit_base_MsLdCeCd, mae_vit_base_patch16, mae_vit_large,
+from .model import (MAE_ViT_Baseline, MAE_ViT_MsLd, MAE_ViT_MsLdCd, MAE_ViT_MsLdCeCd, args_mae_vit_base, args_mae_vit_large,
+                    mae_vit_base, mae_vit_base_MsLd, mae_vit_base_MsLdCd, mae_vit_base_MsLdCeCd, mae_vit_base_patch16, mae_vit_large,
                     mae_vit_large_MsLdCeCd, mae_vit_large_patch16)
 
 from .parallel import DistributedDataParallel
 from .prefetch import DevicePrefetcher
 
-__all__ = ["DevicePrefetcher", "DistributedDataParallel", "MAE_ViT_Baseline", "MAE_ViT_MsLd", "MAE_ViT_MsLdCeCd", "args_mae_vit_base", "args_mae_vit_large",
+__all__ = ["DevicePrefetcher", "DistributedDataParallel", "MAE_ViT_Baseline", "MAE_ViT_MsLd", "MAE_ViT_MsLdCd", "MAE_ViT_MsLdCeCd", "mae_vit_base_MsLdCd", "args_mae_vit_base", "args_mae_vit_large",
            "mae_vit_base", "mae_vit_large", "mae_vit_base_MsLd", "mae_vit_base_MsLdCeCd", "mae_vit_large_MsLdCeCd",
            "mae_vit_base_patch16", "mae_vit_large_patch16"]

@@ -30,6 +30,7 @@ SIGNATURES = {
     "csm_linear_wgrad": [_P, _P, _P, _I, _I, _I, _I, _P],
     "csm_colsum_bf16": [_P, _P, _I, _I, _I, _I, _P],
     "csm_random_masking": [_P, _I, _I, _I, _P, _P, _P, _P],
+    "csm_resized_crop": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P],
     "csm_patch_gather": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "csm_encoder_assemble": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
     "csm_decoder_assemble": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P],

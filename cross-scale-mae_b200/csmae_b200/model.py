@@ -59,6 +59,34 @@ class PatchEmbed(nn.Module):
         self.proj = nn.Conv2d(in_chans, embed_dim, kernel_size=patch_size, stride=patch_size)
 
 
+class BatchRandomResizedCrop(nn.Module):
+    """`self.crop` of the two-scale models: one random crop box per BATCH, resized back to the input size with
+    bilinear + antialias filtering (reference: nn.Sequential(T.RandomResizedCrop(size, scale=ms_range,
+    antialias=True)), MAE_ViT_MsLd.py:29-35).  The box is drawn by torchvision's own get_params (same CPU-generator
+    draws); the resize is one csm_resized_crop kernel instead of a slice copy + ATen's
+    _upsample_bilinear2d_aa."""
+
+    def __init__(self, size, scale, ratio=(3.0 / 4.0, 4.0 / 3.0)):
+        super().__init__()
+        self.size = int(size)
+        self.scale = tuple(scale)
+        self.ratio = tuple(ratio)
+
+    def forward(self, imgs):
+        from torchvision.transforms import RandomResizedCrop
+        from ._native import call
+        assert imgs.dim() == 4, "expected a [N, C, H, W] batch"
+        top, left, h, w = RandomResizedCrop.get_params(imgs, list(self.scale), list(self.ratio))
+        x = imgs.contiguous().float()
+        n, c, hh, ww = x.shape
+        out = torch.empty(n, c, self.size, self.size, dtype=torch.float32, device=x.device)
+        call("csm_resized_crop", x, out, n * c, hh, ww, top, left, h, w, self.size)
+        return out
+
+    def extra_repr(self):
+        return f"size={self.size}, scale={self.scale}, ratio={self.ratio}, interpolation=bilinear, antialias=True"
+
+
 class _FixedScale2(nn.Module):
     """Stands in for `self.crop` when the caller supplies the scale-2 batch (paired form)."""
 
@@ -217,11 +245,9 @@ class MAE_ViT_MsLd(MAE_ViT_Baseline):
         self.allowed_reductions = ["mean", "sum"]
         assert self.ms_decoder_loss_reduction in self.allowed_reductions, \
             f"ms_decoder_loss_reduction must be one of: {self.allowed_reductions}"
-        # one crop box per batch, bilinear + antialias, CPU RNG: torchvision, exactly as upstream
+        # one crop box per batch, bilinear + antialias, box drawn from the CPU generator exactly as upstream
         # (MAE_ViT_MsLd.py:29-35); not used by the paired form forward(imgs1, imgs2, ...)
-        from torchvision import transforms as T
-        self.crop = nn.Sequential(
-            T.RandomResizedCrop(size=(self.input_size, self.input_size), scale=ms_range, antialias=True))
+        self.crop = nn.Sequential(BatchRandomResizedCrop(self.input_size, ms_range))
 
     def _forward_two_scale(self, imgs, imgs2, mask_ratio, mask_seed, consistent_mask, noise):
         if mask_seed is not None:
@@ -256,6 +282,26 @@ class MAE_ViT_MsLd(MAE_ViT_Baseline):
         if not return_embeds:
             return loss, pred, mask
         return (loss, pred, mask, tuple(e.clone() for e in out["enc_emb"]), tuple(e.clone() for e in out["dec_emb"]))
+
+
+class MAE_ViT_MsLdCd(MAE_ViT_MsLd):
+    """Two scales + the cross-scale decoder loss through the predictor MLP only, no contrastive term
+    (reference: models_mae/MAE_ViT_MsLdCd.py:6-65) -- the same kernels with the NT-Xent branch switched off."""
+
+    _use_cd = True
+    _use_ce = False
+
+    def __init__(self, loss_cd=None, predictor_hidden_size=2048, **kwargs):
+        super().__init__(**kwargs)
+        self.loss_cd = loss_cd.lower() if loss_cd is not None else self.loss
+        if self.loss_cd != "mse":
+            raise NotImplementedError(f"loss_cd={loss_cd!r}: only 'mse' is on the hot path")
+        self.predictor = nn.Sequential(
+            nn.Linear(self.decoder_embed_dim, predictor_hidden_size),
+            nn.BatchNorm1d(self.num_patches),
+            nn.ReLU(inplace=True),
+            nn.Linear(predictor_hidden_size, self.decoder_embed_dim),
+        )
 
 
 class MAE_ViT_MsLdCeCd(MAE_ViT_MsLd):
@@ -298,6 +344,10 @@ def mae_vit_large(**kwargs):
 
 def mae_vit_base_MsLd(**kwargs):
     return MAE_ViT_MsLd(**args_mae_vit_base, **kwargs)
+
+
+def mae_vit_base_MsLdCd(**kwargs):
+    return MAE_ViT_MsLdCd(**args_mae_vit_base, **kwargs)
 
 
 def mae_vit_base_MsLdCeCd(**kwargs):

@@ -192,7 +192,73 @@ __global__ void cls_grad_kernel(const float* __restrict__ dx, float* __restrict_
   d_cls[i] = acc;
 }
 
+// In-model random-resized-crop of the two-scale models (models_mae/MAE_ViT_MsLd.py:29-35,52): ONE crop box
+// (top, left, h, w) for the whole batch, resized to S x S with torchvision's bilinear + antialias resize, i.e.
+// ATen's separable triangle filter (aten/src/ATen/native/cuda/UpSampleBilinear2d.cu, _upsample_bilinear2d_aa):
+//   scale = in / out; support = max(scale, 1); center = scale * (i + 0.5);
+//   taps [xmin, xmin + xsize), xmin = max(int(center - support + 0.5), 0), xsize = min(int(center + support + 0.5), in) - xmin;
+//   w_j = max(0, 1 - |(j + xmin - center + 0.5) / max(scale, 1)|), normalised to sum 1;
+//   out = sum_y wy * (sum_x wx * src)   (horizontal pass first, fp32).
+// The crop area is 25-75 % of the image, so this is (almost always) an up-sampling with 2-3 taps per axis, but
+// the general filter is implemented (taps capped at MAX_TAPS per axis; the launcher rejects larger scales).
+constexpr int CROP_MAX_TAPS = 8;
+
+__device__ __forceinline__ void aa_taps(int i, float scale, int in_size, int& xmin, int& xsize, float* w) {
+  const float support = scale >= 1.0f ? scale : 1.0f;
+  const float invscale = scale >= 1.0f ? 1.0f / scale : 1.0f;
+  const float center = scale * (static_cast<float>(i) + 0.5f);
+  xmin = max(static_cast<int>(center - support + 0.5f), 0);
+  xsize = min(static_cast<int>(center + support + 0.5f), in_size) - xmin;
+  xsize = min(max(xsize, 0), CROP_MAX_TAPS);
+  float total = 0.f;
+  for (int j = 0; j < xsize; ++j) {
+    const float x = (static_cast<float>(j + xmin) - center + 0.5f) * invscale;
+    const float v = fmaxf(0.f, 1.0f - fabsf(x));
+    w[j] = v;
+    total += v;
+  }
+  if (total != 0.f) {
+    for (int j = 0; j < xsize; ++j) w[j] /= total;
+  }
+}
+
+// one thread per output pixel, x fastest (coalesced stores; the 2-3 source rows of a warp's pixels are contiguous)
+__global__ void resized_crop_kernel(const float* __restrict__ imgs, float* __restrict__ out, int planes, int H, int W,
+                                    int top, int left, int h, int w, int S) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y;
+  if (x >= S) return;
+  float wx[CROP_MAX_TAPS], wy[CROP_MAX_TAPS];
+  int xmin, xsize, ymin, ysize;
+  aa_taps(x, static_cast<float>(w) / static_cast<float>(S), w, xmin, xsize, wx);
+  aa_taps(y, static_cast<float>(h) / static_cast<float>(S), h, ymin, ysize, wy);
+  for (int pl = blockIdx.z; pl < planes; pl += gridDim.z) {
+    const float* src = imgs + (static_cast<size_t>(pl) * H + top + ymin) * W + left + xmin;
+    float acc = 0.f;
+    for (int yy = 0; yy < ysize; ++yy) {
+      const float* row = src + static_cast<size_t>(yy) * W;
+      float t = row[0] * wx[0];
+      for (int xx = 1; xx < xsize; ++xx) t += row[xx] * wx[xx];
+      acc = yy == 0 ? t * wy[0] : acc + t * wy[yy];
+    }
+    out[(static_cast<size_t>(pl) * S + y) * S + x] = acc;
+  }
+}
+
 }  // namespace
+
+extern "C" int csm_resized_crop(const float* imgs, float* out, int planes, int H, int W, int top, int left, int h,
+                                int w, int S, cudaStream_t stream) {
+  CSM_CHECK_ARG(planes > 0 && S > 0 && h > 0 && w > 0 && top >= 0 && left >= 0 && top + h <= H && left + w <= W,
+                "csm_resized_crop: bad box top=%d left=%d h=%d w=%d in %dx%d", top, left, h, w, H, W);
+  CSM_CHECK_ARG(2 * h <= (CROP_MAX_TAPS - 1) * S && 2 * w <= (CROP_MAX_TAPS - 1) * S,
+                "csm_resized_crop: down-scaling factor too large for the %d-tap filter (box %dx%d -> %d)", CROP_MAX_TAPS,
+                h, w, S);
+  dim3 grid(csm_cdiv(S, 128), S, planes < 64 ? planes : 64);
+  resized_crop_kernel<<<grid, 128, 0, stream>>>(imgs, out, planes, H, W, top, left, h, w, S);
+  CSM_CHECK_LAUNCH("resized_crop");
+  return CSM_OK;
+}
 
 extern "C" int csm_random_masking(const float* noise, int nimg, int L, int keep, long long* ids_restore,
                                   int* ids_shuffle, float* mask, cudaStream_t stream) {

@@ -61,6 +61,10 @@ int csm_colsum_bf16(const void* dy_bf16, float* db, int rows, int N, int skip_pe
  * random_masking: MAE_ViT_Shared.py:57-84 (stable-by-index argsort of the caller's noise) */
 int csm_random_masking(const float* noise, int nimg, int L, int keep, long long* ids_restore, int* ids_shuffle,
                        float* mask, csm_stream_t stream);
+/* in-model random-resized-crop (MAE_ViT_MsLd.py:29-35,52): the batch-wide crop box (top, left, h, w) of
+ * imgs [planes = N*C, H, W] resized to [planes, S, S] with torchvision's bilinear + antialias filter */
+int csm_resized_crop(const float* imgs, float* out, int planes, int H, int W, int top, int left, int h, int w, int S,
+                     csm_stream_t stream);
 /* kept patches -> GEMM operand rows [(nimg*(keep+1)), C*p*p] in Conv2d (c,py,px) order; cls slot rows zero
  * (timm PatchEmbed conv, MAE_ViT_Baseline.py:75-77,245, fused with the masking gather :251) */
 int csm_patch_gather(const float* imgs, const int* ids_shuffle, void* out_bf16, int nimg, int C, int H, int p, int L,

@@ -421,3 +421,43 @@ def test_ntxent(nat, B, Se, D):
     f2 = f.detach().clone().requires_grad_(True)
     (R.ntxent(f2[:B], f2[B:]) * 1.5).backward()
     close(d_feat, f2.grad, 1e-3, 1e-6 * f2.grad.abs().max().item() + 1e-9, "ntxent d_feat")
+
+
+# ------------------------------------------------------------------------------------------------ in-model crop
+@pytest.mark.parametrize("size,box", [(224, (17, 30, 150, 190)), (224, (0, 0, 112, 112)), (96, (3, 5, 90, 71)),
+                                      (128, (10, 0, 118, 128)), (64, (0, 0, 64, 64)), (96, (0, 0, 96, 48)),
+                                      (48, (1, 2, 90, 100))])
+def test_resized_crop_matches_torchvision(nat, size, box):
+    """csm_resized_crop against torchvision.transforms.functional.resized_crop(bilinear, antialias=True) -- what
+    the reference's in-model RandomResizedCrop applies (MAE_ViT_MsLd.py:29-35,52); the last case down-scales."""
+    import torchvision.transforms.functional as TF
+    top, left, h, w = box
+    H, W = max(size, top + h), max(size, left + w)
+    imgs = rnd(3, 3, H, W, seed=size + top)
+    out = torch.full((3, 3, size, size), float("nan"), device="cuda")
+    nat.call("csm_resized_crop", imgs, out, 9, H, W, top, left, h, w, size)
+    # ATen's CPU kernel is the yardstick (same taps, weights and fp32 summation order: agreement to 1 ulp);
+    # ATen's own CUDA kernel evaluates the filter weights slightly differently and sits ~4e-5 away from both
+    ref_cpu = TF.resized_crop(imgs.cpu(), top, left, h, w, [size, size], TF.InterpolationMode.BILINEAR, antialias=True)
+    close(out.cpu(), ref_cpu, 1e-6, 1e-6, "resized crop vs ATen CPU")
+    ref = TF.resized_crop(imgs, top, left, h, w, [size, size], TF.InterpolationMode.BILINEAR, antialias=True)
+    close(out, ref, 1e-4, 1e-4, "resized crop vs ATen CUDA")
+
+
+def test_batch_crop_module_draws_like_torchvision():
+    """BatchRandomResizedCrop consumes the CPU generator exactly like T.RandomResizedCrop and produces the same
+    batch (one box for the whole batch)."""
+    import csmae_b200
+    from torchvision import transforms as T
+    x = rnd(4, 3, 96, 96, seed=3)
+    ours = csmae_b200.model.BatchRandomResizedCrop(96, (0.25, 0.75))
+    ref = T.RandomResizedCrop(size=(96, 96), scale=(0.25, 0.75), antialias=True)
+    for seed in (0, 1, 2, 3):
+        torch.manual_seed(seed)
+        a = ours(x)
+        sa = torch.get_rng_state()
+        torch.manual_seed(seed)
+        b = ref(x)
+        sb = torch.get_rng_state()
+        assert torch.equal(sa, sb), "RNG consumption differs"
+        close(a, b, 1e-4, 1e-4, "batch crop")

@@ -279,3 +279,37 @@ def test_device_prefetcher_order_and_values():
         seen.append((int(x[0, 0, 0, 0].item()), int(y.item())))
     assert seen == [(i, i) for i in range(7)]
     assert len(DevicePrefetcher(host, "cuda")) == 7
+
+
+@pytest.mark.parametrize("variant", ["MsLd", "MsLdCd"])
+def test_sibling_variants_against_oracle_terms(variant):
+    """MAE_ViT_MsLd (reconstruction only) and MAE_ViT_MsLdCd (+ cross-scale decoder loss, no contrastive term):
+    the loss equals the corresponding sum of the oracle's terms and the parameters outside the variant get no
+    gradient (reference: models_mae/MAE_ViT_MsLd.py:37-77, MAE_ViT_MsLdCd.py:26-65)."""
+    import csmae_b200
+    torch.manual_seed(0)
+    cfg = dict(dim_model=128, encoder_num_layers=2, encoder_num_heads=2, decoder_embed_dim=64, decoder_num_layers=2,
+               decoder_num_heads=2, input_size=96, patch_size=16)
+    if variant == "MsLdCd":
+        m = csmae_b200.MAE_ViT_MsLdCd(**cfg, predictor_hidden_size=128, device="cuda").cuda().train()
+    else:
+        m = csmae_b200.MAE_ViT_MsLd(**cfg, device="cuda").cuda().train()
+    full = csmae_b200.MAE_ViT_MsLdCeCd(**cfg, predictor_hidden_size=128, device="cuda").cuda()
+    sd_full = {k: v.detach().clone() for k, v in full.state_dict().items()}
+    sd_full.update({k: v.detach().clone() for k, v in m.state_dict().items()})      # same weights where shared
+    g = torch.Generator(device="cuda").manual_seed(11)
+    x1, x2 = torch.randn(4, 3, 96, 96, device="cuda", generator=g), torch.randn(4, 3, 96, 96, device="cuda", generator=g)
+    n1, n2 = torch.rand(4, 36, device="cuda", generator=g), torch.rand(4, 36, device="cuda", generator=g)
+    loss, pred, mask = m(x1, x2, 0.75, noise=[n1, n2])
+    loss.backward()
+    sd = {k: v for k, v in sd_full.items() if "running" not in k and "num_batches" not in k}
+    with torch.no_grad():
+        o = R.cross_scale_forward(sd, x1, x2, n1, n2, 0.75, 2, 2)
+    want = o["loss_orig"] + o["loss_crop"] + (o["loss_cd"] if variant == "MsLdCd" else 0.0)
+    assert torch.equal(mask, o["mask"])
+    assert abs(loss.item() - want.item()) <= 5e-3 * abs(want.item()), (loss.item(), want.item())
+    grads = {n: p.grad for n, p in m.named_parameters()}
+    assert grads["encoder_norm.weight"] is None
+    assert grads["decoder.0.attn.qkv.weight"] is not None and torch.isfinite(grads["decoder.0.attn.qkv.weight"]).all()
+    if variant == "MsLdCd":
+        assert grads["predictor.0.weight"] is not None and grads["predictor.0.weight"].abs().sum() > 0
