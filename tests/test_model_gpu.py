@@ -313,3 +313,57 @@ def test_sibling_variants_against_oracle_terms(variant):
     assert grads["decoder.0.attn.qkv.weight"] is not None and torch.isfinite(grads["decoder.0.attn.qkv.weight"]).all()
     if variant == "MsLdCd":
         assert grads["predictor.0.weight"] is not None and grads["predictor.0.weight"].abs().sum() > 0
+
+
+def test_reference_engine_step_protocol():
+    """The step protocol of the reference engine (engine_pretrain.py:50-72 + util/misc.py:299-329) driven against
+    our module: single-input call under fp16 autocast, loss.item(), loss /= accum_iter, GradScaler (scale 65536)
+    backward, unscale_, clip/grad-norm, step, update, zero_grad -- two accumulation micro-steps then an update.
+    The unscaled accumulated gradient must equal the sum of two unscaled micro-step gradients."""
+    import csmae_b200
+    torch.manual_seed(0)
+    cfg = dict(dim_model=128, encoder_num_layers=2, encoder_num_heads=2, decoder_embed_dim=64, decoder_num_layers=2,
+               decoder_num_heads=2, input_size=96, patch_size="16", predictor_hidden_size=128, device="cuda",
+               # keys of vars(args) the model must swallow silently (main_pretrain.py:398)
+               batch_size=4, epochs=1, blr=1e-3, output_dir="x", model="mae_vit_base_MsLdCeCd")
+    model = csmae_b200.MAE_ViT_MsLdCeCd(**cfg).cuda().train()
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-3, betas=(0.9, 0.95))
+    scaler = torch.amp.GradScaler("cuda")
+    g = torch.Generator(device="cuda").manual_seed(5)
+    batches = [torch.randn(4, 3, 96, 96, device="cuda", generator=g) for _ in range(2)]
+    accum_iter = 2
+
+    def micro_grads(x, seed):
+        for p in model.parameters():
+            p.grad = None
+        torch.manual_seed(seed)                     # crop box (CPU generator) and masking noise (device generator)
+        loss, _, _ = model(x, mask_ratio=0.75)
+        (loss / accum_iter).backward()
+        return {n: p.grad.clone() for n, p in model.named_parameters() if p.grad is not None}
+    ref = [micro_grads(b, 10 + i) for i, b in enumerate(batches)]
+    for p in model.parameters():
+        p.grad = None
+    w0 = model.decoder[0].attn.qkv.weight.detach().clone()
+    for i, samples in enumerate(batches):
+        torch.manual_seed(10 + i)
+        with torch.autocast("cuda", dtype=torch.float16):
+            loss, _, _ = model(samples, mask_ratio=0.75)
+        loss_value = loss.item()
+        assert torch.isfinite(torch.tensor(loss_value))
+        loss /= accum_iter
+        scaler.scale(loss).backward()
+        if (i + 1) % accum_iter == 0:
+            scaler.unscale_(opt)
+            norm = torch.norm(torch.stack([torch.norm(p.grad.detach(), 2.0) for p in model.parameters()
+                                           if p.grad is not None]), 2.0)
+            assert torch.isfinite(norm)
+            for n, p in model.named_parameters():
+                if p.grad is None:
+                    assert n.startswith("encoder_norm.") or not p.requires_grad
+                    continue
+                want = ref[0][n] + ref[1][n]
+                assert rel_l2(p.grad, want) < 2e-3, n          # 65536-scaled chain vs unscaled: fp32 rounding only
+            scaler.step(opt)
+            scaler.update()
+            opt.zero_grad()
+    assert not torch.equal(model.decoder[0].attn.qkv.weight.detach(), w0), "optimizer step did not update weights"
