@@ -158,6 +158,7 @@ def workload_config(args, batch, world):
             "global_batch": batch * world, "input_size": args.input_size,
             "parallelism": (f"dp{world} ({'torch DDP' if getattr(args, 'torch_ddp', False) else 'engine-overlapped NCCL all-reduce'})"
                             if world > 1 else "single"),
+            "optimizer": "torch.optim.AdamW(fused=True)" if getattr(args, "torch_adamw", False) else "csmae_b200.FusedAdamW",
             "l2_policy": "per-step working set (GBs of activations + 1.4 GB weights/grads/moments) exceeds the 126 MB L2"}
 
 
@@ -174,6 +175,7 @@ def main():
     ap.add_argument("--cpu-batch", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--torch-ddp", action="store_true", help="N>1: wrap with torch's DistributedDataParallel")
+    ap.add_argument("--torch-adamw", action="store_true", help="torch.optim.AdamW(fused=True) instead of FusedAdamW")
     ap.add_argument("--profile-kernels", action="store_true", help="print the per-kernel CUDA-event breakdown")
     args = ap.parse_args()
     if args.batch is None:
@@ -206,8 +208,12 @@ def main():
         step_model = wrapper(model, device_ids=[local_rank], find_unused_parameters=True)
     decay = [p for n, p in model.named_parameters() if p.requires_grad and not (p.ndim == 1 or n.endswith(".bias"))]
     no_decay = [p for n, p in model.named_parameters() if p.requires_grad and (p.ndim == 1 or n.endswith(".bias"))]
-    opt = torch.optim.AdamW([{"params": no_decay, "weight_decay": 0.0}, {"params": decay, "weight_decay": 0.05}],
-                            lr=1.5e-4, betas=(0.9, 0.95), fused=True)
+    groups = [{"params": no_decay, "weight_decay": 0.0}, {"params": decay, "weight_decay": 0.05}]
+    if args.torch_adamw:
+        opt = torch.optim.AdamW(groups, lr=1.5e-4, betas=(0.9, 0.95), fused=True)
+    else:
+        # row f1: one kernel for the whole AdamW step, which also rewrites the bf16 shadow weights
+        opt = csmae_b200.FusedAdamW(groups, lr=1.5e-4, betas=(0.9, 0.95), model=model)
 
     B, S = args.batch, args.input_size
     g = torch.Generator(device=dev).manual_seed(1000 + rank)

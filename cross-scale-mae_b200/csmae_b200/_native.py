@@ -51,6 +51,8 @@ SIGNATURES = {
     "csm_bn_patch_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P],
     "csm_ntxent_fwd": [_P, _P, _P, _P, _P, _I, _I, _I, _F, _F, _P],
     "csm_ntxent_bwd": [_P, _P, _P, _P, _P, _I, _I, _F, _F, _P],
+    "csm_adamw_multi": [_P, _P, _I, _I, _P],
+    "csm_sumsq_f32": [_P, _L, _P, _I, _P],
 }
 
 _lib = None

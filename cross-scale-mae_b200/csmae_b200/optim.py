@@ -1,0 +1,148 @@
+"""Fused optimizer step for the hot path.
+
+`FusedAdamW` is a drop-in for `torch.optim.AdamW(param_groups, lr=..., betas=(0.9, 0.95))` as the reference builds
+it (main_pretrain.py:426-427): same constructor, same `param_groups` (so `lr_sched.adjust_learning_rate` and
+`GradScaler.step/unscale_` work unchanged), same per-parameter state keys (`step`, `exp_avg`, `exp_avg_sq`).  The step
+itself is ONE kernel over all parameters (`csm_adamw_multi`) that also rewrites the bf16 shadow copies of the GEMM
+weights the engine's tcgen05 kernels read, so the separate fp32 -> bf16 cast pass before the next forward
+disappears.  `grad_norm()` is the global L2 norm the reference computes with one `torch.norm` per parameter
+(util/misc.py:338-355); when the gradients are views of the engine's flat buffer it is one reduction kernel.
+"""
+import math
+
+import numpy as np
+import torch
+
+from . import _native as nat
+
+_ENTRY = np.dtype([("p", "<u8"), ("g", "<u8"), ("m", "<u8"), ("v", "<u8"), ("w16", "<u8"), ("n", "<i8"),
+                   ("lr", "<f4"), ("wd", "<f4"), ("beta1", "<f4"), ("beta2", "<f4"),
+                   ("eps", "<f4"), ("bc1", "<f4"), ("bc2_sqrt", "<f4"), ("grad_scale", "<f4")])
+assert _ENTRY.itemsize == 80
+_CHUNK = 8192
+
+
+class FusedAdamW(torch.optim.Optimizer):
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, model=None):
+        if lr < 0 or eps < 0 or not 0 <= betas[0] < 1 or not 0 <= betas[1] < 1 or weight_decay < 0:
+            raise ValueError("invalid AdamW hyper-parameters")
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
+        self._engine = getattr(model, "_engine", None) if model is not None else None
+        self._cache = None          # pointer table of the last step (reused while no pointer moves)
+
+    # ------------------------------------------------------------------ helpers
+    def _shadow_ptrs(self):
+        """data_ptr of the master weight -> data_ptr of its bf16 shadow (engine-owned), if the shadows exist."""
+        eng = self._engine
+        if eng is None or not eng._w16_views:
+            return {}
+        params = dict(eng.model.named_parameters())
+        return {params[n].data_ptr(): v.data_ptr() for n, v in eng._w16_views.items() if n in params}
+
+    def _build(self, items, dev):
+        shadows = self._shadow_ptrs()
+        tab = np.zeros(len(items), dtype=_ENTRY)
+        chunks = []
+        for i, (group, p, st) in enumerate(items):
+            tab[i]["p"], tab[i]["g"] = p.data_ptr(), p.grad.data_ptr()
+            tab[i]["m"], tab[i]["v"] = st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr()
+            tab[i]["w16"] = shadows.get(p.data_ptr(), 0)
+            tab[i]["n"] = p.numel()
+            chunks += [(i, c) for c in range((p.numel() + _CHUNK - 1) // _CHUNK)]
+        host = torch.empty(tab.nbytes, dtype=torch.uint8).pin_memory()
+        cache = dict(tab=tab, host=host, host_np=host.numpy().view(_ENTRY),
+                     dev=torch.empty(tab.nbytes, dtype=torch.uint8, device=dev),
+                     chunks=torch.tensor(chunks, dtype=torch.int32).to(dev), nchunks=len(chunks),
+                     key=tuple((p.data_ptr(), p.grad.data_ptr()) for _, p, _ in items),
+                     shadowed=bool(shadows), items=items)
+        return cache
+
+    # ------------------------------------------------------------------ step
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        items = []
+        for group in self.param_groups:
+            for p in group["params"]:
+                if p.grad is None:
+                    continue
+                if not p.is_cuda or p.dtype != torch.float32 or p.grad.dtype != torch.float32:
+                    raise nat.NativeError("FusedAdamW handles fp32 CUDA parameters and gradients only")
+                if not p.grad.is_contiguous():
+                    p.grad = p.grad.contiguous()
+                st = self.state[p]
+                if not st:
+                    st["step"] = torch.zeros((), dtype=torch.float32)
+                    st["exp_avg"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
+                    st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
+                items.append((group, p, st))
+        if not items:
+            return loss
+        dev = items[0][1].device
+        cache = self._cache
+        if (cache is None or len(cache["items"]) != len(items)
+                or cache["key"] != tuple((p.data_ptr(), p.grad.data_ptr()) for _, p, _ in items)
+                or cache["shadowed"] != bool(self._engine is not None and self._engine._w16_views)):
+            cache = self._cache = self._build(items, dev)
+        tab = cache["tab"]
+        # hyper-parameters are per group and the step count is per parameter (state_dict format of torch.optim.AdamW);
+        # parameters of a group that have always stepped together share one vectorised fill
+        start = 0
+        while start < len(items):
+            group = items[start][0]
+            stop = start
+            while stop < len(items) and items[stop][0] is group:
+                stop += 1
+            steps = []
+            for _, _, st in items[start:stop]:
+                st["step"] += 1
+                steps.append(float(st["step"]))
+            b1, b2 = group["betas"]
+            sl = slice(start, stop)
+            tab["lr"][sl], tab["wd"][sl] = group["lr"], group["weight_decay"]
+            tab["beta1"][sl], tab["beta2"][sl], tab["eps"][sl] = b1, b2, group["eps"]
+            t = np.asarray(steps, dtype=np.float64)
+            tab["bc1"][sl] = 1.0 - b1 ** t
+            tab["bc2_sqrt"][sl] = np.sqrt(1.0 - b2 ** t)
+            tab["grad_scale"][sl] = 1.0
+            start = stop
+        cache["host_np"][:] = tab
+        cache["dev"].copy_(cache["host"], non_blocking=True)
+        nat.call("csm_adamw_multi", cache["dev"], cache["chunks"], cache["nchunks"], nat.sm_count(dev))
+        eng = self._engine
+        if eng is not None:
+            if cache["shadowed"]:
+                # the kernel rewrote the shadows and did not bump Tensor._version: the engine's version check
+                # keeps seeing "unchanged" and skips its cast pass -- which is the point
+                pass
+            else:
+                eng._w16_versions = None        # shadows did not exist yet: the next forward builds them
+        return loss
+
+    # ------------------------------------------------------------------ gradient norm
+    @torch.no_grad()
+    def grad_norm(self):
+        """Global L2 norm of all gradients (util/misc.py:338-355) as a 0-d device tensor."""
+        grads = [p.grad for g in self.param_groups for p in g["params"] if p.grad is not None]
+        if not grads:
+            return torch.zeros(())
+        dev = grads[0].device
+        out = torch.zeros(1, dtype=torch.float32, device=dev)
+        # gradients handed out by the engine are consecutive views of one flat buffer: one pass over it
+        base = min(grads, key=lambda t: t.data_ptr())
+        span_end = max(t.data_ptr() + t.numel() * 4 for t in grads)
+        span = (span_end - base.data_ptr()) // 4
+        same_storage = all(t.untyped_storage().data_ptr() == base.untyped_storage().data_ptr() for t in grads)
+        if same_storage and span <= sum((t.numel() + 3) // 4 * 4 for t in grads) and base.data_ptr() % 16 == 0:
+            flat = torch.as_strided(base, (span,), (1,))        # padding between views is zero
+            nat.call("csm_sumsq_f32", flat, span, out, nat.sm_count(dev))
+        else:
+            for t in grads:
+                if t.data_ptr() % 16 == 0 and t.is_contiguous():
+                    nat.call("csm_sumsq_f32", t, t.numel(), out, nat.sm_count(dev))
+                else:
+                    out += t.float().pow(2).sum()
+        return out.sqrt().reshape(())

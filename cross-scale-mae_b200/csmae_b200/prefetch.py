@@ -8,6 +8,11 @@ trains; the compute stream only waits on the copy's event.  Drop-in around a Dat
 
     for samples, target in DevicePrefetcher(data_loader, device):
         loss, _, _ = model(samples, mask_ratio=0.75)
+
+Device memory: a ring of depth + 1 persistent slots (no allocation per batch -- a cudaMalloc in the caching
+allocator would serialise against the GPU); a slot is overwritten only after the compute stream has passed the
+point where the batch after it was handed out.  A yielded batch is therefore valid until the next-but-`depth`
+batch is requested; keep a `.clone()` if it has to live longer.
 """
 import torch
 
@@ -18,48 +23,87 @@ class DevicePrefetcher:
         self.device = torch.device(device)
         self.stream = torch.cuda.Stream(device=self.device)
         self.depth = max(1, depth)
+        self._slots = [dict(bufs=None, free=None) for _ in range(self.depth + 1)]
 
     def __len__(self):
         return len(self.iterable)
 
-    def _to_device(self, obj):
-        if isinstance(obj, torch.Tensor):
-            return obj.to(self.device, non_blocking=True)
-        if isinstance(obj, (list, tuple)):
-            return type(obj)(self._to_device(o) for o in obj)
-        return obj
-
-    def _record(self, obj, stream):
-        if isinstance(obj, torch.Tensor):
-            if obj.is_cuda:
-                obj.record_stream(stream)
-        elif isinstance(obj, (list, tuple)):
-            for o in obj:
-                self._record(o, stream)
+    def _copy_into(self, slot, batch):
+        """Copies the (nested) host batch into the slot's persistent device tensors on the side stream."""
+        flat, spec = _flatten(batch)
+        bufs = slot["bufs"]
+        if bufs is None or len(bufs) != len(flat) or any(
+                isinstance(h, torch.Tensor) != isinstance(d, torch.Tensor)
+                or (isinstance(h, torch.Tensor) and (d.shape != h.shape or d.dtype != h.dtype))
+                for h, d in zip(flat, bufs)):
+            bufs = [torch.empty(h.shape, dtype=h.dtype, device=self.device) if isinstance(h, torch.Tensor) else h
+                    for h in flat]
+            slot["bufs"] = bufs
+        out = []
+        for h, d in zip(flat, bufs):
+            if isinstance(h, torch.Tensor):
+                d.copy_(h, non_blocking=True)
+                out.append(d)
+            else:
+                out.append(h)
+        return _unflatten(out, spec)
 
     def __iter__(self):
         it = iter(self.iterable)
         queue = []
+        state = dict(next_slot=0)
 
         def issue():
             try:
                 batch = next(it)
             except StopIteration:
                 return False
+            slot = self._slots[state["next_slot"]]
+            state["next_slot"] = (state["next_slot"] + 1) % len(self._slots)
             with torch.cuda.stream(self.stream):
-                dev_batch = self._to_device(batch)
+                if slot["free"] is not None:
+                    self.stream.wait_event(slot["free"])      # its previous batch is no longer in use
+                dev_batch = self._copy_into(slot, batch)
                 ev = torch.cuda.Event()
                 ev.record(self.stream)
-            queue.append((dev_batch, ev))
+            queue.append((dev_batch, ev, slot))
             return True
 
         for _ in range(self.depth):
             if not issue():
                 break
+        prev_slot = None
         while queue:
-            dev_batch, ev = queue.pop(0)
+            dev_batch, ev, slot = queue.pop(0)
             cur = torch.cuda.current_stream(self.device)
             cur.wait_event(ev)
-            self._record(dev_batch, cur)      # the caching allocator must not recycle it while `cur` uses it
+            if prev_slot is not None:
+                # the consumer has moved on from the previous batch: everything it enqueued so far precedes this
+                done = torch.cuda.Event()
+                done.record(cur)
+                prev_slot["free"] = done
+            prev_slot = slot
             issue()
             yield dev_batch
+
+
+def _flatten(obj):
+    if isinstance(obj, (list, tuple)):
+        flat, specs = [], []
+        for o in obj:
+            f, s = _flatten(o)
+            flat += f
+            specs.append((len(f), s))
+        return flat, (type(obj), specs)
+    return [obj], None
+
+
+def _unflatten(flat, spec):
+    if spec is None:
+        return flat[0]
+    typ, specs = spec
+    out, i = [], 0
+    for n, s in specs:
+        out.append(_unflatten(flat[i:i + n], s))
+        i += n
+    return typ(out)

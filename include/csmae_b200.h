@@ -126,6 +126,14 @@ int csm_ntxent_fwd(const float* enc_out, float* zhat, float* fnorm, float* neg, 
 int csm_ntxent_bwd(const float* zhat, const float* fnorm, const float* neg, const float* grad_scalar, float* d_feat,
                    int B, int D, float tau, float eps, csm_stream_t stream);
 
+/* ---- optimizer step (row f1: util/misc.py:299-355 + torch.optim.AdamW at main_pretrain.py:426-427) ------------
+ * table_dev: device array of 80-byte entries {float* p; const float* g; float* m; float* v; bf16* shadow_or_null;
+ * int64 n; float lr, wd, beta1, beta2, eps, bias_correction1, sqrt(bias_correction2), grad_scale};
+ * chunks_dev: device array of {int tensor_index, int chunk_index} work items of 8192 elements */
+int csm_adamw_multi(const void* table_dev, const void* chunks_dev, int num_chunks, int num_sms, csm_stream_t stream);
+/* out[0] += sum of squares of x[0..n)  (global gradient norm of the flat gradient buffer in one pass) */
+int csm_sumsq_f32(const float* x, long long n, float* out, int num_sms, csm_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

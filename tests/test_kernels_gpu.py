@@ -461,3 +461,43 @@ def test_batch_crop_module_draws_like_torchvision():
         sb = torch.get_rng_state()
         assert torch.equal(sa, sb), "RNG consumption differs"
         close(a, b, 1e-4, 1e-4, "batch crop")
+
+
+# ------------------------------------------------------------------------------------------------ optimizer (row f1)
+def test_fused_adamw_matches_torch():
+    """csmae_b200.FusedAdamW against torch.optim.AdamW (the reference's optimizer, main_pretrain.py:426-427): two
+    parameter groups (weight decay 0 / 0.05), ragged sizes, a learning-rate change between steps, a parameter that
+    only receives a gradient from the second step on."""
+    import csmae_b200
+    torch.manual_seed(0)
+    shapes = [(768, 768), (768,), (1, 1, 512), (37,), (5, 3, 16, 16), (2304, 768), (3,)]
+    ref_p = [torch.nn.Parameter(torch.randn(*s, device="cuda")) for s in shapes]
+    our_p = [torch.nn.Parameter(p.detach().clone()) for p in ref_p]
+    groups = lambda ps: [{"params": [p for p in ps if p.ndim == 1], "weight_decay": 0.0},
+                         {"params": [p for p in ps if p.ndim != 1], "weight_decay": 0.05}]
+    ref = torch.optim.AdamW(groups(ref_p), lr=1.5e-3, betas=(0.9, 0.95))
+    ours = csmae_b200.FusedAdamW(groups(our_p), lr=1.5e-3, betas=(0.9, 0.95))
+    for step in range(4):
+        for a, b in zip(ref_p, our_p):
+            if step == 0 and a.shape == (37,):
+                a.grad = b.grad = None
+                continue
+            g = torch.randn_like(a) * (10.0 if step == 2 else 1.0)
+            a.grad, b.grad = g.clone(), g.clone()
+        if step == 2:
+            for opt in (ref, ours):
+                for gr in opt.param_groups:
+                    gr["lr"] = 7e-4
+        ref.step()
+        ours.step()
+        for a, b in zip(ref_p, our_p):
+            close(b.detach(), a.detach(), 2e-6, 2e-7, f"FusedAdamW step {step} shape {tuple(a.shape)}")
+    sa, sb = ref.state_dict()["state"], ours.state_dict()["state"]
+    assert sa.keys() == sb.keys()
+    for k in sa:
+        assert set(sb[k].keys()) == {"step", "exp_avg", "exp_avg_sq"}
+        assert float(sa[k]["step"]) == float(sb[k]["step"])
+        close(sb[k]["exp_avg_sq"], sa[k]["exp_avg_sq"], 2e-6, 1e-9, "exp_avg_sq")
+    # global gradient norm (util/misc.py:338-355)
+    want = torch.norm(torch.stack([torch.norm(p.grad, 2.0) for p in ref_p]), 2.0)
+    close(ours.grad_norm().reshape(1), want.reshape(1), 1e-5, 0, "grad norm")

@@ -367,3 +367,50 @@ def test_reference_engine_step_protocol():
             scaler.update()
             opt.zero_grad()
     assert not torch.equal(model.decoder[0].attn.qkv.weight.detach(), w0), "optimizer step did not update weights"
+
+
+def test_fused_adamw_refreshes_bf16_shadows():
+    """With FusedAdamW(model=...) the optimizer kernel rewrites the engine's bf16 shadow weights itself: after a
+    step they equal bf16(master weight), the engine's refresh (cast) pass is skipped, and training with it matches
+    training with torch.optim.AdamW + the engine's own cast."""
+    import csmae_b200
+    from csmae_b200 import _native
+    cfg = dict(dim_model=128, encoder_num_layers=2, encoder_num_heads=2, decoder_embed_dim=64, decoder_num_layers=2,
+               decoder_num_heads=2, input_size=96, patch_size=16, predictor_hidden_size=128)
+    g = torch.Generator(device="cuda").manual_seed(2)
+    x1, x2 = torch.randn(4, 3, 96, 96, device="cuda", generator=g), torch.randn(4, 3, 96, 96, device="cuda", generator=g)
+    n1, n2 = torch.rand(4, 36, device="cuda", generator=g), torch.rand(4, 36, device="cuda", generator=g)
+    losses = {}
+    for kind in ("torch", "fused"):
+        torch.manual_seed(0)
+        m = csmae_b200.MAE_ViT_MsLdCeCd(**cfg, device="cuda").cuda().train()
+        params = [p for p in m.parameters() if p.requires_grad]
+        opt = (torch.optim.AdamW(params, lr=1e-3, betas=(0.9, 0.95)) if kind == "torch"
+               else csmae_b200.FusedAdamW(params, lr=1e-3, betas=(0.9, 0.95), model=m))
+        out = []
+        for step in range(5):
+            opt.zero_grad(set_to_none=True)
+            loss, _, _ = m(x1, x2, 0.75, noise=[n1, n2])
+            loss.backward()
+            opt.step()
+            out.append(loss.item())
+        losses[kind] = out
+        if kind == "fused":
+            eng = m._engine
+            for name, view in eng._w16_views.items():
+                w = dict(m.named_parameters())[name]
+                assert torch.equal(view.view(-1), w.detach().to(torch.bfloat16).view(-1)), name
+            calls = []
+            orig = _native.call
+            try:
+                _native.call = lambda n_, *a: (calls.append(n_), orig(n_, *a))[1]
+                import csmae_b200.engine as E
+                E.call = _native.call
+                with torch.no_grad():
+                    m(x1, x2, 0.75, noise=[n1, n2])
+            finally:
+                _native.call = orig
+                E.call = orig
+            assert "csm_cast_multi" not in calls, "the engine re-cast weights the optimizer had already refreshed"
+    for a, b in zip(losses["torch"], losses["fused"]):
+        assert abs(a - b) <= 2e-3 * abs(a), (losses["torch"], losses["fused"])
