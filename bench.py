@@ -68,28 +68,48 @@ def measured_peaks():
     return dict(tflops_burst=1590.0, tflops_sustained=1400.0, hbm_gbs=6650.0, source="fallback (B200_PROFILING.md)")
 
 
-class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled while the timed region runs: ONE long-running `nvidia-smi -lms 200`
+    (the recipe's clocks line, B200_PROFILING.md) started before and killed after.  (Spawning nvidia-smi per sample
+    re-initialises NVML every time, which stalls the driver for ~0.1 s and showed up as +5..8 ms per step in the
+    host-fed e2e region.)"""
 
     def __init__(self, index):
-        super().__init__(daemon=True)
         self.index = index
         self.rows = []
         self.stop_flag = threading.Event()
+        self.proc = None
+        self.reader = None
 
-    def run(self):
+    def start(self):
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
-        while not self.stop_flag.is_set():
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+            return
+        self.reader = threading.Thread(target=self._read, daemon=True)
+        self.reader.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            parts = [x.strip() for x in line.strip().split(",")]
+            if len(parts) >= 6:
+                self.rows.append(parts)
+
+    def stop(self):
+        self.stop_flag.set()
+        if self.proc is not None:
+            self.proc.terminate()            # the exact process started above
             try:
-                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                parts = [x.strip() for x in out.strip().split(",")]
-                if len(parts) >= 6:
-                    self.rows.append(parts)
+                self.proc.wait(timeout=5)
             except Exception:
-                pass
-            self.stop_flag.wait(0.2)
+                self.proc.kill()
+            if self.reader is not None:
+                self.reader.join(timeout=2)
 
     def summary(self):
         if not self.rows:
@@ -282,11 +302,20 @@ def main():
     # trains, and the loss is read back to the host
     from csmae_b200 import DevicePrefetcher
 
+    class HostBatches:                      # a re-iterable "loader" of k pinned host batches
+        k = 0
+
+        def __iter__(self):
+            return ((host1, host2) for _ in range(self.k))
+    loader = HostBatches()
+    prefetcher = DevicePrefetcher(loader, dev)          # one instance, as a training script keeps it across epochs
+
     def e2e_run(k, lag):
         # every step's loss is read back to the host; with lag=1 the read of step i is issued after step i+1 has
         # been enqueued (asynchronous logging: the GPU never waits for the host between steps)
         last, prev = None, None
-        for x1, x2 in DevicePrefetcher(((host1, host2) for _ in range(k)), dev):
+        loader.k = k
+        for x1, x2 in prefetcher:
             loss_t = step(x1, x2)
             if lag:
                 if prev is not None:
@@ -314,7 +343,7 @@ def main():
         return ms
     ms_e2e_sync = e2e_timed(0)       # loss.item() right after every step, as engine_pretrain.py:55 does
     ms_e2e = e2e_timed(1)            # same reads, one step late
-    sampler.stop_flag.set()
+    sampler.stop()
 
     # per-kernel breakdown of one step with CUDA events on the launching stream (outside the timed region)
     model._engine.use_graphs = False          # the breakdown times each C-ABI call eagerly

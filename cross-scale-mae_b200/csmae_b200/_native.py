@@ -28,6 +28,8 @@ SIGNATURES = {
     "csm_linear_fwd": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
     "csm_linear_dgrad": [_P, _P, _P, _P, _I, _I, _I, _I, _P],
     "csm_linear_wgrad": [_P, _P, _P, _I, _I, _I, _I, _P],
+    "csm_gemm_workspace_bytes": [_I],
+    "csm_gemm_set_workspace": [_P, _L],
     "csm_colsum_bf16": [_P, _P, _I, _I, _I, _I, _P],
     "csm_random_masking": [_P, _I, _I, _I, _P, _P, _P, _P],
     "csm_resized_crop": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P],
@@ -106,6 +108,27 @@ def sm_count(device=None):
     if dev not in _sm_count:
         _sm_count[dev] = _check(load().csm_device_check(dev), "csm_device_check")
     return _sm_count[dev]
+
+
+_gemm_ws = {}
+
+
+def enable_gemm_stream_k(device=None, enable=True):
+    """Registers (or drops) the stream-K workspace of the forward / dgrad GEMMs on this device: zeroed device memory
+    owned here.  Contract (include/csmae_b200.h): forward / dgrad GEMMs run on one stream at a time afterwards."""
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    lib = load()
+    if not enable:
+        _check(lib.csm_gemm_set_workspace(0, 0), "csm_gemm_set_workspace")
+        _gemm_ws.pop(dev.index or 0, None)
+        return None
+    key = dev.index or 0
+    if key not in _gemm_ws:
+        nbytes = _check(lib.csm_gemm_workspace_bytes(sm_count(dev)), "csm_gemm_workspace_bytes")
+        _gemm_ws[key] = torch.zeros(nbytes, dtype=torch.uint8, device=dev)
+    ws = _gemm_ws[key]
+    _check(lib.csm_gemm_set_workspace(ws.data_ptr(), ws.numel()), "csm_gemm_set_workspace")
+    return ws
 
 
 def _stream():

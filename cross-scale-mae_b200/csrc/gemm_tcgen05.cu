@@ -70,6 +70,8 @@ struct GemmParams {
   int bn;                // cluster tile width (multiple of 64, <= 256)
   int tiles_m, tiles_n;  // 256-row tiles, bn-col tiles
   const float* bias;     // [N] or nullptr
+  int sk;                // stream-K schedule: every cluster gets an equal run of k-blocks (see Sched)
+  unsigned* sk_flags;    // [clusters + 1] arrival counters of the partial tiles (zero between launches)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -173,8 +175,10 @@ __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16])
       : "memory");
 }
 
+enum Role : int { ROLE_FULL = 0, ROLE_TAIL = 1, ROLE_HEAD = 2 };
 struct WorkUnit {
   int m_tile, n_tile, kb0, nkb;
+  int role;
 };
 __device__ __forceinline__ WorkUnit decode_unit(const GemmParams& p, int u) {
   WorkUnit w;
@@ -184,7 +188,64 @@ __device__ __forceinline__ WorkUnit decode_unit(const GemmParams& p, int u) {
   const int split = r / p.tiles_m;
   w.kb0 = split * p.kb_per_split;
   w.nkb = min(p.kb_per_split, p.num_kb - w.kb0);
+  w.role = ROLE_FULL;
   return w;
+}
+
+// Work schedule of one cluster.  Data-parallel mode: whole units u = cluster, cluster + C, ...  Stream-K mode
+// (p.sk): the units' k-blocks are laid end to end and cluster c takes the run [bound(c), bound(c+1)), so a
+// cluster's FIRST piece may be the tail of a unit (its k-blocks kb0..end: the partial accumulator goes to the
+// fp32 workspace slot of this cluster) and its LAST piece the head of a unit (k-blocks 0..n: it adds the partial
+// that cluster c+1 wrote at the very start of its run -- long before -- and runs the fused epilogue).  Runs are
+// at least one unit long (units >= clusters), so a unit is cut at most once; cuts closer than SK_SNAP k-blocks to
+// a unit boundary are moved onto it.
+constexpr int SK_SNAP = 3;
+__device__ __forceinline__ int sk_bound(const GemmParams& p, int c, int num_clusters, int total_kb) {
+  if (c >= num_clusters) return total_kb;
+  int b = static_cast<int>(static_cast<long long>(c) * total_kb / num_clusters);
+  const int off = b % p.num_kb;
+  if (off < SK_SNAP) b -= off;
+  else if (p.num_kb - off < SK_SNAP) b += p.num_kb - off;
+  return b;
+}
+struct Sched {
+  int sk, u, step, total_units, pos, end, nkb, tiles_n;
+  __device__ __forceinline__ Sched(const GemmParams& p, int cluster_id, int num_clusters) {
+    sk = p.sk;
+    u = cluster_id;
+    step = num_clusters;
+    total_units = p.tiles_m * p.tiles_n * p.splits;
+    nkb = p.num_kb;
+    tiles_n = p.tiles_n;
+    pos = end = 0;
+    if (sk) {
+      const int total_kb = total_units * nkb;
+      pos = sk_bound(p, cluster_id, num_clusters, total_kb);
+      end = sk_bound(p, cluster_id + 1, num_clusters, total_kb);
+    }
+  }
+  __device__ __forceinline__ bool next(const GemmParams& p, WorkUnit& w) {
+    if (!sk) {
+      if (u >= total_units) return false;
+      w = decode_unit(p, u);
+      u += step;
+      return true;
+    }
+    if (pos >= end) return false;
+    const int unit = pos / nkb;
+    w.kb0 = pos - unit * nkb;
+    w.nkb = min(nkb - w.kb0, end - pos);
+    w.n_tile = unit % tiles_n;
+    w.m_tile = unit / tiles_n;
+    w.role = w.kb0 > 0 ? ROLE_TAIL : (w.nkb < nkb ? ROLE_HEAD : ROLE_FULL);
+    pos += w.nkb;
+    return true;
+  }
+};
+__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -192,7 +253,7 @@ template <bool A_MN, bool B_MN, int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
             const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_aux,
-            const GemmParams p) {
+            const __grid_constant__ CUtensorMap tmap_ws, const GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + SMEM_BAR_OFFSET);
@@ -200,14 +261,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   uint64_t* tmem_full = empty_bar + STAGES;        // [2]
   uint64_t* tmem_empty = tmem_full + 2;            // [2]
   uint64_t* aux_bar = tmem_empty + 2;              // [EPI_WARPS][STG_BUFS]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux_bar + EPI_WARPS * STG_BUFS);
+  uint64_t* part_bar = aux_bar + EPI_WARPS * STG_BUFS;   // [EPI_WARPS] stream-K partial tile loads (used once)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(part_bar + EPI_WARPS);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const int cluster_id = blockIdx.x >> 1;
   const int num_clusters = gridDim.x >> 1;
-  const int total_units = p.tiles_m * p.tiles_n * p.splits;
   const int half_bn = p.bn >> 1;
 
   if (threadIdx.x == 0) {
@@ -224,6 +285,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       mbar_init(&tmem_empty[a], 2 * EPI_WARPS);
     }
     for (int i = 0; i < EPI_WARPS * STG_BUFS; ++i) mbar_init(&aux_bar[i], 1);
+    for (int i = 0; i < EPI_WARPS; ++i) mbar_init(&part_bar[i], 1);
+    if (p.sk) tma_prefetch_desc(&tmap_ws);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -243,8 +306,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     if (lane == 0) {
       const uint32_t stage_tx = 2u * static_cast<uint32_t>(A_BYTES + half_bn * BK * 2);
       uint32_t it = 0;
-      for (int u = cluster_id; u < total_units; u += num_clusters) {
-        const WorkUnit w = decode_unit(p, u);
+      Sched sched(p, cluster_id, num_clusters);
+      WorkUnit w;
+      while (sched.next(p, w)) {
         const int m0 = w.m_tile * (2 * BM) + static_cast<int>(rank) * BM;
         const int n0 = w.n_tile * p.bn + static_cast<int>(rank) * half_bn;
         for (int i = 0; i < w.nkb; ++i, ++it) {
@@ -278,8 +342,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     if (rank == 0 && lane == 0) {
       const uint32_t idesc = umma_idesc_bf16(2 * BM, p.bn, A_MN ? 1 : 0, B_MN ? 1 : 0);
       uint32_t it = 0, tile_it = 0;
-      for (int u = cluster_id; u < total_units; u += num_clusters, ++tile_it) {
-        const WorkUnit w = decode_unit(p, u);
+      Sched sched(p, cluster_id, num_clusters);
+      WorkUnit w;
+      for (; sched.next(p, w); ++tile_it) {
         const uint32_t acc = tile_it & 1;
         const uint32_t acc_ph = (tile_it >> 1) & 1;
         mbar_wait(&tmem_empty[acc], acc_ph ^ 1);      // both CTAs' epilogues have drained this buffer
@@ -334,12 +399,68 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       ++aux_seq;
     };
 
-    for (int u = cluster_id; u < total_units; u += num_clusters, ++tile_it) {
-      const WorkUnit w = decode_unit(p, u);
+    Sched sched(p, cluster_id, num_clusters);
+    WorkUnit w;
+    uint8_t* part = smem + ew * 8192;              // stream-K head piece: this warp's share of the partial tile
+                                                   // (lands in the operand ring, idle by then)
+    for (; sched.next(p, w); ++tile_it) {
       const uint32_t acc = tile_it & 1;
       const uint32_t acc_ph = (tile_it >> 1) & 1;
       const int row0 = w.m_tile * (2 * BM) + static_cast<int>(rank) * BM + q * 32;
       const int col_tile = w.n_tile * p.bn;
+      const uint32_t tmem_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * ACC_COLS;
+      if (w.role == ROLE_TAIL) {
+        // ---- stream-K tail piece (always a cluster's first piece): fp32 partial -> workspace slot of this
+        //      cluster, then one arrival per warp on the slot's counter ----
+        mbar_wait(&tmem_full[acc], acc_ph);
+        tc_fence_after();
+        const int nch16 = p.bn >> 4;
+        const int ws_row = cluster_id * (2 * BM) + static_cast<int>(rank) * BM + q * 32;
+#pragma unroll 1
+        for (int c = quad; c < nch16; c += 4) {
+          uint32_t r[16];
+          tmem_ld_32x16(tmem_row + c * 16, r);
+          tmem_ld_wait();
+          if (c + 4 >= nch16) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(acc ? tmem_empty_leader1 : tmem_empty_leader0);
+          }
+          const uint32_t b = seq & 1;
+          if (lane == 0) bulk_wait_read<1>();
+          __syncwarp();
+          const uint32_t sbase = smem_u32(stg + b * STG_BYTES) + lane * 64;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            uint4 o;
+            o.x = r[g * 4 + 0]; o.y = r[g * 4 + 1]; o.z = r[g * 4 + 2]; o.w = r[g * 4 + 3];
+            st_shared_v4(sbase + ((static_cast<uint32_t>(g) ^ sw) << 4), o);
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&tmap_ws, stg + b * STG_BYTES, c * 16, ws_row);
+            bulk_commit();
+          }
+          ++seq;
+        }
+        if (lane == 0) {
+          bulk_wait_all();                          // the partial is written, not just read out of smem
+          asm volatile("fence.proxy.async;" ::: "memory");
+          __threadfence();
+          atomicAdd(p.sk_flags + cluster_id, 1u);
+        }
+        __syncwarp();
+        seq = 0;                                    // both staging buffers are idle again
+        continue;
+      }
+      const bool head = (w.role == ROLE_HEAD);
+      if (head && lane == 0) {
+        // the cluster after this one wrote the rest of this unit's reduction at the very start of its run
+        const unsigned* flag = p.sk_flags + cluster_id + 1;
+        while (ld_acquire_gpu(flag) < 2u * EPI_WARPS) __nanosleep(64);
+        asm volatile("fence.proxy.async;" ::: "memory");
+      }
       if (HAS_AUX && lane == 0 && quad < nchunks) {
         // the staging buffer the load lands in must have been read out by its previous TMA store
         bulk_wait_read<0>();
@@ -351,7 +472,21 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster(acc ? tmem_empty_leader1 : tmem_empty_leader0);
       }
-      const uint32_t tmem_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * ACC_COLS;
+      if (head && quad < nchunks) {
+        // all MMAs of this cluster are done (the head piece is its last), so the operand ring is free: fetch this
+        // warp's whole share of the partial tile (<= 4 groups of 32 rows x 16 f32 columns) in one go
+        if (lane == 0) {
+          int ngroups = 0;
+          for (int c = quad; c < nchunks; c += 4) ngroups += CW / 16;
+          mbar_expect_tx(&part_bar[ew], static_cast<uint32_t>(ngroups) * STG_BYTES);
+          const int ws_row = (cluster_id + 1) * (2 * BM) + static_cast<int>(rank) * BM + q * 32;
+          int gi = 0;
+          for (int c = quad; c < nchunks; c += 4)
+            for (int h = 0; h < CW / 16; ++h, ++gi)
+              tma_load_2d(part + gi * STG_BYTES, &tmap_ws, &part_bar[ew], c * CW + h * 16, ws_row);
+        }
+        mbar_wait(&part_bar[ew], 0);
+      }
 
 #pragma unroll 1
       for (int c = quad; c < nchunks; c += 4) {
@@ -371,6 +506,21 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         float v[CW];
 #pragma unroll
         for (int j = 0; j < CW; ++j) v[j] = __uint_as_float(r[j]);
+        if (head) {
+          const int gi0 = ((c - quad) >> 2) * (CW / 16);
+#pragma unroll
+          for (int h = 0; h < CW / 16; ++h) {
+            const uint32_t pbase = smem_u32(part + (gi0 + h) * STG_BYTES) + lane * 64;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const uint4 x = ld_shared_v4(pbase + ((static_cast<uint32_t>(g) ^ sw) << 4));
+              v[h * 16 + g * 4 + 0] += __uint_as_float(x.x);
+              v[h * 16 + g * 4 + 1] += __uint_as_float(x.y);
+              v[h * 16 + g * 4 + 2] += __uint_as_float(x.z);
+              v[h * 16 + g * 4 + 3] += __uint_as_float(x.w);
+            }
+          }
+        }
         if (EPI != EPI_DGELU && EPI != EPI_F32_ATOMIC && p.bias != nullptr) {
 #pragma unroll
           for (int g = 0; g < CW / 4; ++g) {
@@ -504,6 +654,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     tc_fence_after();
     tmem_dealloc2(tmem_base, 2 * ACC_COLS);
   }
+  if (p.sk && threadIdx.x == 0 && rank == 0) {
+    // this cluster consumed the partial of cluster + 1 (if its run ended inside a unit): re-arm the counter
+    const int total_kb = p.tiles_m * p.tiles_n * p.num_kb;
+    const int e = sk_bound(p, cluster_id + 1, num_clusters, total_kb);
+    if (e % p.num_kb != 0) p.sk_flags[cluster_id + 1] = 0u;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -608,6 +764,17 @@ int max_clusters(Kern kern, int num_sms) {
   return n;
 }
 
+// Stream-K workspace (registered by the host, csm_gemm_set_workspace): [4096 B of arrival counters][clusters x
+// 256 x 256 f32 partial tiles].  One stream at a time may run forward / dgrad GEMMs while it is registered.
+struct SkWorkspace {
+  unsigned* flags = nullptr;
+  float* tiles = nullptr;
+  int max_clusters = 0;
+};
+SkWorkspace g_sk_ws;
+constexpr size_t SK_FLAG_BYTES = 4096;
+constexpr size_t SK_TILE_BYTES = static_cast<size_t>(2 * BM) * MAX_BN * sizeof(float);
+
 // BN for a [M, N] output: the k-block time of a 256 x bn cluster tile is bound by the L2 -> SM feed
 // (~ 128 + bn/2 rows per SM), so the cost model is rounds(bn) * (256 + bn).
 int choose_bn(int M, int N, int num_clusters, bool b_mn) {
@@ -681,8 +848,34 @@ int launch_gemm(const void* a, uint64_t a_inner, uint64_t a_outer, const void* b
     p.tiles_n = csm_cdiv(N, p.bn);
     p.kb_per_split = p.num_kb;
     p.splits = 1;
+    // stream-K: when the units do not fill whole rounds of clusters, cut the k-block stream evenly instead.  Cost
+    // per cluster in k-block x (rows of operand traffic): data-parallel rounds * nkb * (256 + bn) against
+    // (units * nkb / clusters + SK_OVERHEAD_KB) * (256 + bn').  The overhead (measured, ~6 us ~ 14 k-blocks) is the
+    // partial tile's write -> flag -> read round trip at the end of the owner's run plus the slower k-block rate of
+    // clusters that no longer read the same operand tiles at the same time; reductions of 12 k-blocks never pay.
+    if (g_sk_ws.tiles != nullptr && g_sk_ws.max_clusters >= clusters && p.num_kb >= 2 * SK_SNAP) {
+      const long long dp_units = static_cast<long long>(p.tiles_m) * p.tiles_n;
+      const double dp_cost = static_cast<double>((dp_units + clusters - 1) / clusters) * p.num_kb * (256 + p.bn);
+      double best = dp_cost * 0.94;
+      const int cands[2] = {256, 128};
+      for (int i = 0; i < 2; ++i) {
+        const int bn = cands[i];
+        const long long units = static_cast<long long>(p.tiles_m) * csm_cdiv(N, bn);
+        if (units <= clusters || units % clusters == 0) continue;
+        const double cost = (static_cast<double>(units) * p.num_kb / clusters + 14.0) * (256 + bn);
+        if (cost < best) {
+          best = cost;
+          p.sk = 1;
+          p.bn = bn;
+        }
+      }
+      if (p.sk) {
+        p.tiles_n = csm_cdiv(N, p.bn);
+        p.sk_flags = g_sk_ws.flags;
+      }
+    }
   }
-  CUtensorMap ta, tb, to, tx;
+  CUtensorMap ta, tb, to, tx, tws;
   int rc;
   // A: K-major [M, red] box {64, 128};  MN-major [red, M] box {64, 64}
   rc = A_MN ? get_tensor_map(&ta, a, a_inner, a_outer, a_inner, 64, BK) : get_tensor_map(&ta, a, a_inner, a_outer, a_inner, BK, BM);
@@ -700,9 +893,15 @@ int launch_gemm(const void* a, uint64_t a_inner, uint64_t a_outer, const void* b
     rc = get_tensor_map(&tx, aux, N, M, N, 16, 32, 4, 64);
     if (rc) return rc;
   }
+  tws = to;
+  if (p.sk) {
+    rc = get_tensor_map(&tws, g_sk_ws.tiles, MAX_BN, static_cast<uint64_t>(g_sk_ws.max_clusters) * 2 * BM, MAX_BN, 16,
+                        32, 4, 64);
+    if (rc) return rc;
+  }
   const int units = p.tiles_m * p.tiles_n * p.splits;
   const int grid = 2 * (units < clusters ? units : clusters);
-  cudaError_t le = csm_launch_pdl(kern, dim3(grid), dim3(GEMM_THREADS), SMEM_TOTAL, stream, ta, tb, to, tx, p);
+  cudaError_t le = csm_launch_pdl(kern, dim3(grid), dim3(GEMM_THREADS), SMEM_TOTAL, stream, ta, tb, to, tx, tws, p);
   if (le != cudaSuccess) {
     csm_set_error("gemm_tcgen05: launch failed: %s", cudaGetErrorString(le));
     return CSM_ERR_CUDA;
@@ -715,6 +914,27 @@ int launch_gemm(const void* a, uint64_t a_inner, uint64_t a_outer, const void* b
 // ---------------------------------------------------------------------------------------------
 // C-ABI (declared in include/csmae_b200.h)
 // ---------------------------------------------------------------------------------------------
+extern "C" int csm_gemm_workspace_bytes(int num_sms) {
+  if (num_sms <= 0) num_sms = 148;
+  return static_cast<int>(SK_FLAG_BYTES + static_cast<size_t>(num_sms / 2) * SK_TILE_BYTES);
+}
+
+extern "C" int csm_gemm_set_workspace(void* ws, long long nbytes) {
+  const size_t bytes = nbytes > 0 ? static_cast<size_t>(nbytes) : 0;
+  if (ws == nullptr) {
+    g_sk_ws = SkWorkspace{};
+    return CSM_OK;
+  }
+  CSM_CHECK_ARG((reinterpret_cast<uintptr_t>(ws) & 255) == 0, "csm_gemm_set_workspace: pointer must be 256-byte aligned");
+  CSM_CHECK_ARG(bytes >= SK_FLAG_BYTES + SK_TILE_BYTES, "csm_gemm_set_workspace: %zu bytes is too small", bytes);
+  g_sk_ws.flags = reinterpret_cast<unsigned*>(ws);
+  g_sk_ws.tiles = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(ws) + SK_FLAG_BYTES);
+  g_sk_ws.max_clusters = static_cast<int>((bytes - SK_FLAG_BYTES) / SK_TILE_BYTES);
+  if (static_cast<size_t>(g_sk_ws.max_clusters) + 1 > SK_FLAG_BYTES / sizeof(unsigned))
+    g_sk_ws.max_clusters = static_cast<int>(SK_FLAG_BYTES / sizeof(unsigned)) - 1;
+  return CSM_OK;
+}
+
 extern "C" int csm_linear_fwd(const void* x_bf16, const void* w_bf16, const float* bias, void* out, void* aux,
                               int M, int N, int K, int epilogue, cudaStream_t stream) {
   CSM_CHECK_ARG(M > 0 && N > 0 && K > 0, "csm_linear_fwd: empty problem M=%d N=%d K=%d", M, N, K);

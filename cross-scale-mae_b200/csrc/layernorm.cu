@@ -225,6 +225,201 @@ layernorm_bwd_tile_kernel(const __nv_bfloat16* __restrict__ dy_bf16, const float
   }
 }
 
+// Same maths, deeper memory pipeline: every thread stages ITS OWN slice of the next LN_NST-1 rows in shared memory
+// with cp.async (no thread reads another thread's slice, so the only CTA barrier stays the one for the row
+// statistics), which keeps ~3 rows x 40 B per thread in flight without holding them in registers, and handles VPT
+// float4 column groups per thread so the shuffles / barrier / address arithmetic are amortised over more bytes.
+constexpr int LN_NST = 4;
+
+__device__ __forceinline__ void cp_async16(void* s, const void* g) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(s)), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void* s, const void* g) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(s)), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* s, const void* g) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(s)), "l"(g) : "memory");
+}
+
+__host__ __device__ constexpr int ln_pipe_threads(int tpr) { return tpr == 96 ? 192 : (tpr == 192 ? 384 : 256); }
+__host__ __device__ constexpr size_t ln_pipe_smem(int tpr, int vpt) {
+  return static_cast<size_t>(LN_NST) * vpt * ln_pipe_threads(tpr) * 40 + static_cast<size_t>(LN_NST) * (ln_pipe_threads(tpr) / 32) * 8;
+}
+
+template <int TPR, int VPT>
+__global__ void __launch_bounds__(ln_pipe_threads(TPR))
+layernorm_bwd_pipe_kernel(const __nv_bfloat16* __restrict__ dy_bf16, const float* __restrict__ dy2,
+                          const float* __restrict__ x, const float* __restrict__ mean_in,
+                          const float* __restrict__ rstd_in, const float* __restrict__ gamma,
+                          const float* __restrict__ dres_in, float* __restrict__ dres_out,
+                          __nv_bfloat16* __restrict__ dres_bf16, float* __restrict__ dgamma,
+                          float* __restrict__ dbeta, float* __restrict__ dcolsum, int rows) {
+  constexpr int D = TPR * 4 * VPT;
+  constexpr int WPR = TPR / 32;
+  constexpr int THREADS = ln_pipe_threads(TPR);
+  constexpr int RPI = THREADS / TPR;
+  constexpr int NW = THREADS / 32;
+  static_assert(THREADS % TPR == 0 && TPR % 32 == 0, "a row must be a whole number of warps");
+  extern __shared__ __align__(16) unsigned char ln_smem[];
+  float4* s_x = reinterpret_cast<float4*>(ln_smem);                       // [NST][VPT][THREADS]
+  float4* s_r = s_x + LN_NST * VPT * THREADS;
+  uint2* s_d = reinterpret_cast<uint2*>(s_r + LN_NST * VPT * THREADS);
+  float2* s_stat = reinterpret_cast<float2*>(s_d + LN_NST * VPT * THREADS);  // [NST][NW]
+  __shared__ float2 s_part[2][RPI][WPR];
+  const int tid = threadIdx.x;
+  const int rsub = tid / TPR;
+  const int ct = tid % TPR;
+  const int wir = ct >> 5;
+  const int warp = tid >> 5;
+  const int lane = tid & 31;
+  pdl_wait();
+  pdl_trigger();
+  float4 gm[VPT], ag[VPT], ab[VPT], ac[VPT];
+#pragma unroll
+  for (int v = 0; v < VPT; ++v) {
+    gm[v] = *reinterpret_cast<const float4*>(gamma + (v * TPR + ct) * 4);
+    ag[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+    ab[v] = ag[v];
+    ac[v] = ag[v];
+  }
+  const bool has_d = dy_bf16 != nullptr, has_r = dres_in != nullptr;
+
+  auto issue = [&](int st, int row) {
+    if (row < rows) {
+#pragma unroll
+      for (int v = 0; v < VPT; ++v) {
+        const size_t off = static_cast<size_t>(row) * D + (v * TPR + ct) * 4;
+        const int si = (st * VPT + v) * THREADS + tid;
+        cp_async16(s_x + si, x + off);
+        if (has_r) cp_async16(s_r + si, dres_in + off);
+        if (has_d) cp_async8(s_d + si, dy_bf16 + off);
+      }
+      if (lane == 0) {
+        cp_async4(&s_stat[st * NW + warp].x, mean_in + row);
+        cp_async4(&s_stat[st * NW + warp].y, rstd_in + row);
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  const int step = gridDim.x * RPI;
+  int row = blockIdx.x * RPI + rsub;
+#pragma unroll
+  for (int s = 0; s < LN_NST - 1; ++s) issue(s, row + s * step);
+  int st = 0, buf = 0;
+  for (int row0 = blockIdx.x * RPI; row0 < rows; row0 += step, row += step, buf ^= 1) {
+    issue(st == 0 ? LN_NST - 1 : st - 1, row + (LN_NST - 1) * step);
+    asm volatile("cp.async.wait_group %0;" ::"n"(LN_NST - 1) : "memory");
+    __syncwarp();
+    const bool valid = row < rows;
+    float4 xh[VPT], d[VPT], g[VPT], rin[VPT];
+    float mean = 0.f, rstd = 0.f;
+    if (valid) {
+      const float2 ms = s_stat[st * NW + warp];
+      mean = ms.x;
+      rstd = ms.y;
+    }
+    float c1 = 0.f, c2 = 0.f;
+#pragma unroll
+    for (int v = 0; v < VPT; ++v) {
+      const int si = (st * VPT + v) * THREADS + tid;
+      float4 xv = make_float4(0.f, 0.f, 0.f, 0.f);
+      d[v] = xv;
+      rin[v] = xv;
+      if (valid) {
+        xv = s_x[si];
+        if (has_r) rin[v] = s_r[si];
+        if (has_d) {
+          const uint2 ev = s_d[si];
+          const float2 e0 = unpack_bf16x2(ev.x), e1 = unpack_bf16x2(ev.y);
+          d[v] = make_float4(e0.x, e0.y, e1.x, e1.y);
+        }
+        if (dy2 != nullptr) {
+          const float4 d2 = *reinterpret_cast<const float4*>(dy2 + static_cast<size_t>(row) * D + (v * TPR + ct) * 4);
+          d[v].x += d2.x; d[v].y += d2.y; d[v].z += d2.z; d[v].w += d2.w;
+        }
+      }
+      xh[v] = make_float4((xv.x - mean) * rstd, (xv.y - mean) * rstd, (xv.z - mean) * rstd, (xv.w - mean) * rstd);
+      g[v] = make_float4(d[v].x * gm[v].x, d[v].y * gm[v].y, d[v].z * gm[v].z, d[v].w * gm[v].w);
+      c1 += g[v].x + g[v].y + g[v].z + g[v].w;
+      c2 += g[v].x * xh[v].x + g[v].y * xh[v].y + g[v].z * xh[v].z + g[v].w * xh[v].w;
+    }
+    c1 = warp_sum(c1);
+    c2 = warp_sum(c2);
+    if (WPR > 1) {
+      if (lane == 0) s_part[buf][rsub][wir] = make_float2(c1, c2);
+      __syncthreads();
+      c1 = 0.f; c2 = 0.f;
+#pragma unroll
+      for (int w = 0; w < WPR; ++w) {
+        const float2 pr = s_part[buf][rsub][w];
+        c1 += pr.x; c2 += pr.y;
+      }
+    }
+    c1 *= (1.0f / D);
+    c2 *= (1.0f / D);
+    if (valid) {
+#pragma unroll
+      for (int v = 0; v < VPT; ++v) {
+        const size_t base = static_cast<size_t>(row) * D + (v * TPR + ct) * 4;
+        float4 o;
+        o.x = rstd * (g[v].x - c1 - xh[v].x * c2) + rin[v].x;
+        o.y = rstd * (g[v].y - c1 - xh[v].y * c2) + rin[v].y;
+        o.z = rstd * (g[v].z - c1 - xh[v].z * c2) + rin[v].z;
+        o.w = rstd * (g[v].w - c1 - xh[v].w * c2) + rin[v].w;
+        *reinterpret_cast<float4*>(dres_out + base) = o;
+        uint2 pk;
+        pk.x = pack_bf16x2(o.x, o.y);
+        pk.y = pack_bf16x2(o.z, o.w);
+        if (dres_bf16 != nullptr) *reinterpret_cast<uint2*>(dres_bf16 + base) = pk;
+        const float2 r0 = unpack_bf16x2(pk.x), r1 = unpack_bf16x2(pk.y);
+        ac[v].x += r0.x; ac[v].y += r0.y; ac[v].z += r1.x; ac[v].w += r1.y;
+        ag[v].x += d[v].x * xh[v].x; ag[v].y += d[v].y * xh[v].y; ag[v].z += d[v].z * xh[v].z; ag[v].w += d[v].w * xh[v].w;
+        ab[v].x += d[v].x; ab[v].y += d[v].y; ab[v].z += d[v].z; ab[v].w += d[v].w;
+      }
+    }
+    st = st == LN_NST - 1 ? 0 : st + 1;
+  }
+  // fold the RPI row slots through the (now idle) staging area, then one vector atomic per thread and sum
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  if (RPI > 1) {
+    __syncthreads();
+    float4* s_col = s_x;                                    // [3][RPI-1][VPT][TPR]
+    if (rsub > 0) {
+#pragma unroll
+      for (int v = 0; v < VPT; ++v) {
+        s_col[((0 * (RPI - 1) + rsub - 1) * VPT + v) * TPR + ct] = ag[v];
+        s_col[((1 * (RPI - 1) + rsub - 1) * VPT + v) * TPR + ct] = ab[v];
+        s_col[((2 * (RPI - 1) + rsub - 1) * VPT + v) * TPR + ct] = ac[v];
+      }
+    }
+    __syncthreads();
+    if (rsub == 0) {
+#pragma unroll
+      for (int r = 0; r < RPI - 1; ++r) {
+#pragma unroll
+        for (int v = 0; v < VPT; ++v) {
+          const float4 a = s_col[((0 * (RPI - 1) + r) * VPT + v) * TPR + ct];
+          const float4 b = s_col[((1 * (RPI - 1) + r) * VPT + v) * TPR + ct];
+          const float4 c = s_col[((2 * (RPI - 1) + r) * VPT + v) * TPR + ct];
+          ag[v].x += a.x; ag[v].y += a.y; ag[v].z += a.z; ag[v].w += a.w;
+          ab[v].x += b.x; ab[v].y += b.y; ab[v].z += b.z; ab[v].w += b.w;
+          ac[v].x += c.x; ac[v].y += c.y; ac[v].z += c.z; ac[v].w += c.w;
+        }
+      }
+    }
+  }
+  if (rsub == 0) {
+#pragma unroll
+    for (int v = 0; v < VPT; ++v) {
+      const int col = (v * TPR + ct) * 4;
+      red_add_v4(dgamma + col, ag[v]);
+      red_add_v4(dbeta + col, ab[v]);
+      if (dcolsum != nullptr) red_add_v4(dcolsum + col, ac[v]);
+    }
+  }
+}
+
 // Generic-D fallback (D not a multiple of 128, D <= 1024): one warp per row, register-resident row.
 __global__ void layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy_bf16, const float* __restrict__ dy2,
                                      const float* __restrict__ x, const float* __restrict__ mean_in,
@@ -468,6 +663,32 @@ void launch_ln_bwd_tile(const void* dy_bf16, const float* dy2_f32, const float* 
                  reinterpret_cast<__nv_bfloat16*>(dres_bf16), dgamma, dbeta, dcolsum, rows);
 }
 
+template <int TPR, int VPT>
+void launch_ln_bwd_pipe(const void* dy_bf16, const float* dy2_f32, const float* x, const float* mean, const float* rstd,
+                        const float* gamma, const float* dres_in, float* dres_out, void* dres_bf16, float* dgamma,
+                        float* dbeta, float* dcolsum, int rows, int num_sms, cudaStream_t stream) {
+  constexpr int THREADS = ln_pipe_threads(TPR);
+  constexpr int RPI = THREADS / TPR;
+  constexpr size_t SMEM = ln_pipe_smem(TPR, VPT);
+  static int ctas_per_sm = 0;
+  if (ctas_per_sm == 0) {
+    cudaFuncSetAttribute(layernorm_bwd_pipe_kernel<TPR, VPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
+    cudaFuncSetAttribute(layernorm_bwd_pipe_kernel<TPR, VPT>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                         cudaSharedmemCarveoutMaxShared);
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, layernorm_bwd_pipe_kernel<TPR, VPT>, THREADS, SMEM) !=
+            cudaSuccess || occ < 1)
+      occ = 1;
+    ctas_per_sm = occ;
+  }
+  int grid = csm_cdiv(rows, RPI);
+  const int cap = num_sms * ctas_per_sm;               // exactly one resident wave
+  if (grid > cap) grid = cap;
+  csm_launch_pdl(layernorm_bwd_pipe_kernel<TPR, VPT>, dim3(grid), dim3(THREADS), SMEM, stream,
+                 reinterpret_cast<const __nv_bfloat16*>(dy_bf16), dy2_f32, x, mean, rstd, gamma, dres_in, dres_out,
+                 reinterpret_cast<__nv_bfloat16*>(dres_bf16), dgamma, dbeta, dcolsum, rows);
+}
+
 extern "C" int csm_layernorm_bwd(const void* dy_bf16, const float* dy2_f32, const float* x, const float* mean,
                                  const float* rstd, const float* gamma, const float* dres_in, float* dres_out,
                                  void* dres_bf16, float* dgamma, float* dbeta, float* dcolsum, int rows, int D,
@@ -479,13 +700,21 @@ extern "C" int csm_layernorm_bwd(const void* dy_bf16, const float* dy2_f32, cons
 #define CSM_LN_TILE(TPR)                                                                                         \
   launch_ln_bwd_tile<TPR>(dy_bf16, dy2_f32, x, mean, rstd, gamma, dres_in, dres_out, dres_bf16, dgamma, dbeta, \
                           dcolsum, rows, num_sms, stream)
+#define CSM_LN_PIPE(TPR, VPT)                                                                                    \
+  launch_ln_bwd_pipe<TPR, VPT>(dy_bf16, dy2_f32, x, mean, rstd, gamma, dres_in, dres_out, dres_bf16, dgamma,    \
+                               dbeta, dcolsum, rows, num_sms, stream)
+  // the production widths stage rows with cp.async (deeper memory pipeline); other widths keep the register pipeline
+  if (D == 512 || D == 768 || D == 1024) {
+    if (D == 512) CSM_LN_PIPE(64, 2);
+    else if (D == 768) CSM_LN_PIPE(96, 2);
+    else CSM_LN_PIPE(128, 2);
+    CSM_CHECK_LAUNCH("layernorm_bwd");
+    return CSM_OK;
+  }
   switch (D) {
     case 128: CSM_LN_TILE(32); break;
     case 256: CSM_LN_TILE(64); break;
     case 384: CSM_LN_TILE(96); break;
-    case 512: CSM_LN_TILE(128); break;
-    case 768: CSM_LN_TILE(192); break;
-    case 1024: CSM_LN_TILE(256); break;
     default: {
       const int wpb = 8;
       int grid = csm_cdiv(rows, wpb);
@@ -504,6 +733,7 @@ extern "C" int csm_layernorm_bwd(const void* dy_bf16, const float* dy2_f32, cons
     }
   }
 #undef CSM_LN_TILE
+#undef CSM_LN_PIPE
   CSM_CHECK_LAUNCH("layernorm_bwd");
   return CSM_OK;
 }

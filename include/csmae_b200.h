@@ -50,6 +50,15 @@ int csm_linear_fwd(const void* x_bf16, const void* w_bf16, const float* bias, vo
 /* dX[M,K] = dY[M,N] . W[N,K]  (W read in its stored [N,K] layout) ; epilogue 0, 3 or 5 */
 int csm_linear_dgrad(const void* dy_bf16, const void* w_bf16, void* dx, const void* aux, int M, int N, int K,
                      int epilogue, csm_stream_t stream);
+/* Optional stream-K workspace for csm_linear_fwd / csm_linear_dgrad (no reference counterpart: cuBLAS keeps its own).
+ * When the 256 x BN output tiles of a problem do not fill whole rounds of the 74 SM pairs, the k-block stream is cut
+ * evenly between the clusters instead and a unit cut in two is finished through an fp32 partial tile in this buffer.
+ * `ws` = csm_gemm_workspace_bytes(num_sms) bytes of ZEROED device memory, 256-byte aligned, owned by the caller and kept
+ * alive until csm_gemm_set_workspace(NULL, 0).  Contract: while a workspace is registered, forward / dgrad GEMMs must
+ * be issued on ONE stream at a time (csm_linear_wgrad never touches it and may run concurrently).  Without a
+ * workspace the GEMMs use whole-tile scheduling only. */
+int csm_gemm_workspace_bytes(int num_sms);
+int csm_gemm_set_workspace(void* ws, long long bytes);
 /* dW[N,K] += dY[rows,N]^T . X[rows,K]   (f32, split over the token rows, red.global.add) */
 int csm_linear_wgrad(const void* dy_bf16, const void* x_bf16, float* dw, int rows, int N, int K, int num_sms,
                      csm_stream_t stream);

@@ -125,6 +125,56 @@ def test_linear_wgrad(nat, rows, N, K):
     close(dw, 2 * ref, 2e-4, 4e-3 * math.sqrt(rows / 128), "wgrad accumulate")
 
 
+@pytest.fixture()
+def stream_k(nat):
+    nat.enable_gemm_stream_k("cuda:0", True)
+    yield
+    nat.enable_gemm_stream_k("cuda:0", False)
+
+
+# shapes whose 256 x BN tiles do not fill whole rounds of the 74 SM pairs (the encoder's M = 6400 ones, the decoder's
+# M = 25216 ones, ViT-L's M = 3200 with a half-empty last row tile, a ragged one)
+@pytest.mark.parametrize("M,N,K", [(6400, 768, 768), (6400, 2304, 768), (6400, 768, 3072), (6400, 3072, 768),
+                                   (25216, 512, 512), (25216, 1536, 512), (3200, 1024, 4096), (19000, 520, 328)])
+def test_linear_stream_k_all_epilogues(nat, stream_k, M, N, K):
+    """With the stream-K workspace registered the forward / dgrad GEMMs cut the k-block stream evenly between the
+    clusters; a unit cut in two is finished through an fp32 partial tile.  Same tolerances as the whole-tile path,
+    twice in a row (the arrival counters must be re-armed) and against the whole-tile result."""
+    x, w, b = rnd(M, K, dtype=bf16), rnd(N, K, scale=K ** -0.5, dtype=bf16), rnd(N)
+    ref = x.float() @ w.float().t() + b
+    resid = rnd(M, N, seed=5)
+    for rep in range(2):
+        o32 = torch.full((M, N), float("nan"), device="cuda")
+        nat.call("csm_linear_fwd", x, w, b, o32, None, M, N, K, nat.EPI_F32)
+        close(o32, ref, 1e-4, 1e-4, f"stream-K f32 (rep {rep})")
+        out = torch.full((M, N), float("nan"), device="cuda", dtype=bf16)
+        nat.call("csm_linear_fwd", x, w, b, out, None, M, N, K, nat.EPI_BF16)
+        close(out, ref, 1e-2, 1e-2, f"stream-K bf16 (rep {rep})")
+        o = torch.full((M, N), float("nan"), device="cuda")
+        nat.call("csm_linear_fwd", x, w, b, o, resid, M, N, K, nat.EPI_RESID)
+        close(o - resid, ref, 1e-2, 1e-2, f"stream-K residual (rep {rep})")
+        gp = torch.full((M, N), float("nan"), device="cuda", dtype=bf16)
+        act = torch.full((M, N), float("nan"), device="cuda", dtype=bf16)
+        nat.call("csm_linear_fwd", x, w, b, gp, act, M, N, K, nat.EPI_GELU)
+        close(act, F.gelu(ref.to(bf16).float()), 1e-2, 4e-3, f"stream-K gelu (rep {rep})")
+    # dgrad: dX[M,K] = dY[M,N] . W[N,K]
+    dy = rnd(M, N, dtype=bf16, seed=3)
+    wd = rnd(N, K, scale=N ** -0.5, dtype=bf16, seed=4)
+    dref = dy.float() @ wd.float()
+    d32 = torch.full((M, K), float("nan"), device="cuda")
+    nat.call("csm_linear_dgrad", dy, wd, d32, None, M, N, K, nat.EPI_F32)
+    close(d32, dref, 1e-4, 1e-4, "stream-K dgrad f32")
+    gpk = rnd(M, K, dtype=bf16, seed=9)
+    dh = torch.full((M, K), float("nan"), device="cuda", dtype=bf16)
+    nat.call("csm_linear_dgrad", dy, wd, dh, gpk, M, N, K, nat.EPI_DGELU)
+    close(dh, dref.to(bf16).float() * gpk.float(), 1e-2, 1e-2, "stream-K dgrad x gelu'")
+    # whole-tile scheduling gives the same f32 result up to summation order
+    nat.enable_gemm_stream_k("cuda:0", False)
+    o_dp = torch.empty(M, N, device="cuda")
+    nat.call("csm_linear_fwd", x, w, b, o_dp, None, M, N, K, nat.EPI_F32)
+    close(o32, o_dp, 1e-5, 1e-5, "stream-K vs whole-tile")
+
+
 def test_colsum(nat):
     dy = rnd(1234, 768, dtype=bf16)
     db = torch.zeros(768, device="cuda")

@@ -279,6 +279,20 @@ def test_device_prefetcher_order_and_values():
         seen.append((int(x[0, 0, 0, 0].item()), int(y.item())))
     assert seen == [(i, i) for i in range(7)]
     assert len(DevicePrefetcher(host, "cuda")) == 7
+    # one instance serves every epoch from the same ring of device buffers (no allocation after the first pass),
+    # also when the consumer leaves an epoch early and when the last batch is ragged
+    ragged = host[:4] + [(torch.full((2, 3, 8, 8), 9.0).pin_memory(), torch.tensor([9]))]
+    pf = DevicePrefetcher(ragged, "cuda", depth=2)
+    for epoch in range(3):
+        ptrs, vals = set(), []
+        for i, (x, y) in enumerate(pf):
+            ptrs.add(x.data_ptr())
+            vals.append((int(x[0, 0, 0, 0].item()), int(y.item()), x.shape[0]))
+            if epoch == 1 and i == 2:
+                break
+        want = [(0, 0, 4), (1, 1, 4), (2, 2, 4), (3, 3, 4), (9, 9, 2)]
+        assert vals == (want[:3] if epoch == 1 else want), vals
+        assert len(ptrs) <= 4
 
 
 @pytest.mark.parametrize("variant", ["MsLd", "MsLdCd"])

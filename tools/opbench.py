@@ -65,12 +65,17 @@ def main():
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--json", default="")
     ap.add_argument("--single", action="store_true", help="exactly one launch per op (for ncu)")
+    ap.add_argument("--stream-k", action="store_true", help="register the stream-K workspace of the GEMMs")
+    ap.add_argument("--cublas", action="store_true",
+                    help="also time torch.matmul (cuBLAS, no epilogue) on every GEMM shape: the library yardstick")
     args = ap.parse_args()
     global SINGLE
     SINGLE = args.single
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(dev)
     nsm = nat.sm_count(dev)
+    if args.stream_k:
+        nat.enable_gemm_stream_k(dev, True)
     flush = torch.zeros(64 * 1024 * 1024, device=dev)
     tf_peak, bw_peak = peaks()
     g = torch.Generator(device=dev).manual_seed(0)
@@ -113,6 +118,10 @@ def main():
                 o, aux = torch.empty(M, N, device=dev, dtype=bf16), None
             us = timeit(lambda: nat.call("csm_linear_fwd", x, w, b, o, aux, M, N, K, epi), args.iters, flush)
             report("gemm", f"linear_fwd[{epi}] {name}", [M, N, K], us, flops=2.0 * M * N * K)
+            if args.cublas:
+                y = torch.empty(M, N, device=dev, dtype=bf16)
+                us = timeit(lambda: torch.matmul(x, w.t(), out=y), args.iters, flush)
+                report("gemm", f"cublas fwd {name}", [M, N, K], us, flops=2.0 * M * N * K)
         dg = [("enc.qkv", Me, 3 * D, D, nat.EPI_BF16), ("enc.proj", Me, D, D, nat.EPI_BF16),
               ("enc.fc1", Me, 4 * D, D, nat.EPI_BF16), ("enc.fc2", Me, D, 4 * D, nat.EPI_DGELU),
               ("dec.qkv", Md, 3 * Dd, Dd, nat.EPI_BF16), ("dec.proj", Md, Dd, Dd, nat.EPI_BF16),
@@ -124,11 +133,18 @@ def main():
             aux = rnd(M, K) if epi == nat.EPI_DGELU else None
             us = timeit(lambda: nat.call("csm_linear_dgrad", dy, w, dx, aux, M, N, K, epi), args.iters, flush)
             report("gemm", f"linear_dgrad[{epi}] {name}", [M, N, K], us, flops=2.0 * M * N * K)
+            if args.cublas:
+                us = timeit(lambda: torch.matmul(dy, w, out=dx), args.iters, flush)
+                report("gemm", f"cublas dgrad {name}", [M, N, K], us, flops=2.0 * M * N * K)
         for name, M, N, K, _ in dg:
             dy, x = rnd(M, N), rnd(M, K)
             dw = torch.zeros(N, K, device=dev)
             us = timeit(lambda: nat.call("csm_linear_wgrad", dy, x, dw, M, N, K, nsm), args.iters, flush)
             report("gemm", f"linear_wgrad {name}", [M, N, K], us, flops=2.0 * M * N * K)
+            if args.cublas:
+                dw16 = torch.empty(N, K, device=dev, dtype=bf16)
+                us = timeit(lambda: torch.matmul(dy.t(), x, out=dw16), args.iters, flush)
+                report("gemm", f"cublas wgrad(bf16 out) {name}", [M, N, K], us, flops=2.0 * M * N * K)
 
     if not args.only or "attn" in args.only:
         for name, S, H, d in [("enc", Se, He, D // He), ("dec", Sd, Hd, Dd // Hd)]:
