@@ -117,11 +117,10 @@ class HotPathEngine:
         self.use_side_stream = os.environ.get("CSMAE_SIDE_STREAM", "1") != "0"
         # stream-K scheduling of the forward / dgrad GEMMs whose tiles do not fill whole rounds of SM pairs (they all
         # run on the caller's stream -- the side stream only carries wgrads and column sums -- as the workspace
-        # requires).  Opt-in: it wins 15-18 % on the long-reduction encoder GEMMs timed alone, but inside the step
-        # the side stream's wgrads already fill the SMs a partial last round leaves idle, and the step gets 1.5 %
-        # slower (13.71 -> 13.92 ms, ViT-B)
-        self.use_stream_k = os.environ.get("CSMAE_STREAM_K", "0") == "1"
-        self._stream_k_ready = False
+        # requires).  It wins 15-18 % on the long-reduction encoder GEMMs timed alone, but inside the backward the
+        # side stream's wgrads already fill the SMs a partial last round leaves idle and the step gets 1.5 % slower
+        # (13.71 -> 13.92 ms, ViT-B), hence "fwd": forward GEMMs only
+        self.stream_k_mode = os.environ.get("CSMAE_STREAM_K", "0")        # "0" | "1" (fwd + bwd) | "fwd"
         self._side = {}
         self._side_dirty = False
         self._sync_enabled = False  # overlapped gradient all-reduce (parallel.py)
@@ -313,9 +312,8 @@ class HotPathEngine:
         m = self.model
         dev = imgs_list[0].device
         nsm = nat.sm_count(dev)
-        if self.use_stream_k and not self._stream_k_ready:
-            nat.enable_gemm_stream_k(dev, True)
-            self._stream_k_ready = True
+        if self.stream_k_mode != "0":
+            nat.enable_gemm_stream_k(dev, True)       # host-side switch, read when a GEMM is launched / captured
         ns = len(imgs_list)
         N, C, H, W = imgs_list[0].shape
         assert H == W == m.input_size and C == m.input_channels, "input size mismatch"
@@ -558,6 +556,8 @@ class HotPathEngine:
         N, ns, NB, L, keep, Se, Sd = (st[k] for k in ("N", "ns", "NB", "L", "keep", "Se", "Sd"))
         D, Dd, C, H, p, P, nsm = (st[k] for k in ("D", "Dd", "C", "H", "p", "P", "nsm"))
         dev = st["imgs"][0].device
+        if self.stream_k_mode == "fwd":
+            nat.enable_gemm_stream_k(dev, False)      # the backward's partial rounds are filled by the side stream
         bf16, f32 = torch.bfloat16, torch.float32
         params = dict(m.named_parameters())
         w16 = self._w16_views
