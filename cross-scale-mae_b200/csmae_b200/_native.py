@@ -61,7 +61,7 @@ _lib = None
 _lock = threading.Lock()
 _sm_count = {}
 launch_count = 0   # kernels launched through the C-ABI so far (bench.py reports the delta)
-KERNELS_PER_CALL = {"csm_ntxent_fwd": 2}
+KERNELS_PER_CALL = {"csm_ntxent_fwd": 2, "csm_decoder_assemble_bwd": 2}
 
 
 class NativeError(RuntimeError):

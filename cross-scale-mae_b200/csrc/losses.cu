@@ -67,6 +67,37 @@ __global__ void recon_loss_kernel(const __nv_bfloat16* __restrict__ pred_full, c
   }
   const float g = BWD ? gptr[0] * coef * 2.0f : 0.f;
   float acc = 0.f;
+  if (p == 16 && C <= 4) {
+    // 16 x 16 patches (every config of BASELINE.json): a warp covers two pixel rows per step, no index divisions,
+    // all 8 x C steps unrolled so the loads of the whole patch are in flight together
+    const int px = lane & 15, half = lane >> 4;
+    float pix[4][8], prd[4][8];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      if (c < C) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int py = 2 * k + half;
+          pix[c][k] = ibase[(static_cast<size_t>(c) * H + py) * H + px];
+          prd[c][k] = __bfloat162float(pred_full[prow + (py * 16 + px) * C + c]);
+        }
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      if (c < C) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int py = 2 * k + half;
+          float diff;
+          if (norm_pix) diff = prd[c][k] - (pix[c][k] - mean) * inv_std;
+          else diff = bf16_round(prd[c][k] - bf16_round(pix[c][k]));
+          if (BWD) dpred[prow + (py * 16 + px) * C + c] = __float2bfloat16_rn(g * diff);
+          else acc += diff * diff;
+        }
+      }
+    }
+  } else
   // i runs in image order (c, py, px) so pixel reads are contiguous; e is the (py, px, c) slot of pred
   for (int i = lane; i < P; i += 32) {
     const int px = i % p, cy = i / p;
@@ -135,6 +166,8 @@ __global__ void cross_mse_kernel(const __nv_bfloat16* __restrict__ cp, const flo
 // BatchNorm1d(L) over [N, L, Hp] with channel = patch index l; rows are laid out n*Sd + 1 + l
 // (cls rows of the predictor GEMM output are ignored / zeroed).  One CTA per channel.
 // ---------------------------------------------------------------------------------------------
+// (512-thread CTAs, two per SM and all 196 channels in one wave, were measured equal: a channel's three dependent
+// passes bound the CTA, not the wave count; the next step would be several CTAs per channel)
 __global__ void bn_patch_fwd_kernel(const __nv_bfloat16* __restrict__ h, const float* __restrict__ gamma,
                                     const float* __restrict__ beta, __nv_bfloat16* __restrict__ out,
                                     float* __restrict__ mean_out, float* __restrict__ rstd_out,

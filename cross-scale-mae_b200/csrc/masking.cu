@@ -132,27 +132,67 @@ __global__ void decoder_assemble_kernel(const __nv_bfloat16* __restrict__ demb,
 // Backward of decoder_assemble.
 //   d_demb[n, 0]     = bf16(dy[n, 0])
 //   d_demb[n, 1 + r] = bf16(dy[n, 1 + ids_shuffle[n, r]])          r < keep
-//   d_mask_token    += sum over masked positions (and images) of dy (one CTA per image, then red.add)
+//   d_mask_token    += sum over masked positions (and images) of dy (second kernel below)
 __global__ void decoder_assemble_bwd_kernel(const float* __restrict__ dy, const int* __restrict__ ids_shuffle,
-                                            __nv_bfloat16* __restrict__ d_demb, float* __restrict__ d_mask_token,
-                                            int L, int keep, int Dd) {
+                                            __nv_bfloat16* __restrict__ d_demb, int L, int keep, int Dd) {
+  // one CTA per (image, kept token): gather + cast
   const int Sd = L + 1, Se = keep + 1;
-  const int n = blockIdx.x;
-  const float* dyn = dy + static_cast<size_t>(n) * Sd * Dd;
-  const int* sh = ids_shuffle + static_cast<size_t>(n) * L;
-  for (int idx = threadIdx.x; idx < Se * (Dd / 4); idx += blockDim.x) {
-    const int t = idx / (Dd / 4), i = (idx % (Dd / 4)) * 4;
-    const int src = t == 0 ? 0 : 1 + sh[t - 1];
-    const float4 v = *reinterpret_cast<const float4*>(dyn + static_cast<size_t>(src) * Dd + i);
+  const int n = blockIdx.x / Se, t = blockIdx.x % Se;
+  const int src = t == 0 ? 0 : 1 + ids_shuffle[static_cast<size_t>(n) * L + t - 1];
+  const float* s = dy + (static_cast<size_t>(n) * Sd + src) * Dd;
+  __nv_bfloat16* o = d_demb + static_cast<size_t>(blockIdx.x) * Dd;
+  for (int i = threadIdx.x * 4; i < Dd; i += blockDim.x * 4) {
+    const float4 v = *reinterpret_cast<const float4*>(s + i);
     uint2 pk;
     pk.x = pack_bf16x2(v.x, v.y);
     pk.y = pack_bf16x2(v.z, v.w);
-    *reinterpret_cast<uint2*>(d_demb + (static_cast<size_t>(n) * Se + t) * Dd + i) = pk;
+    *reinterpret_cast<uint2*>(o + i) = pk;
   }
-  for (int i = threadIdx.x; i < Dd; i += blockDim.x) {
-    float acc = 0.f;
-    for (int r = keep; r < L; ++r) acc += dyn[static_cast<size_t>(1 + sh[r]) * Dd + i];
-    atomicAdd(d_mask_token + i, acc);
+}
+
+// d_mask_token += column sums of the masked rows of all images: grid (128-column groups, row slabs), a warp per
+// row with four rows in flight, one atomic per column and CTA (same-address atomics serialise in L2: the first
+// version issued 2048 per column and spent 80 us on them)
+__global__ void mask_token_grad_kernel(const float* __restrict__ dy, const int* __restrict__ ids_shuffle,
+                                       float* __restrict__ d_mask_token, int nimg, int L, int keep, int Dd) {
+  __shared__ float4 s_part[8][32];
+  const int Sd = L + 1, nm = L - keep;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int col = blockIdx.x * 128 + lane * 4;
+  const int total = nimg * nm;
+  const int stride = gridDim.y * 8;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (col < Dd) {
+    for (int m0 = blockIdx.y * 8 + w; m0 < total; m0 += 4 * stride) {
+      float4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int m = m0 + u * stride;
+        v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (m < total) {
+          const int n = m / nm, j = m - n * nm;
+          const int src = 1 + ids_shuffle[static_cast<size_t>(n) * L + keep + j];
+          v[u] = *reinterpret_cast<const float4*>(dy + (static_cast<size_t>(n) * Sd + src) * Dd + col);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w;
+      }
+    }
+  }
+  s_part[w][lane] = acc;
+  __syncthreads();
+  if (w == 0 && col < Dd) {
+#pragma unroll
+    for (int k = 1; k < 8; ++k) {
+      const float4 v = s_part[k][lane];
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    atomicAdd(d_mask_token + col + 0, acc.x);
+    atomicAdd(d_mask_token + col + 1, acc.y);
+    atomicAdd(d_mask_token + col + 2, acc.z);
+    atomicAdd(d_mask_token + col + 3, acc.w);
   }
 }
 
@@ -307,8 +347,15 @@ extern "C" int csm_decoder_assemble(const void* demb_bf16, const long long* ids_
 extern "C" int csm_decoder_assemble_bwd(const float* dy, const int* ids_shuffle, void* d_demb_bf16,
                                         float* d_mask_token, int nimg, int L, int keep, int Dd, cudaStream_t stream) {
   CSM_CHECK_ARG(Dd % 4 == 0, "csm_decoder_assemble_bwd: Dd must be a multiple of 4 (Dd=%d)", Dd);
-  decoder_assemble_bwd_kernel<<<nimg, 256, 0, stream>>>(dy, ids_shuffle, reinterpret_cast<__nv_bfloat16*>(d_demb_bf16),
-                                                        d_mask_token, L, keep, Dd);
+  decoder_assemble_bwd_kernel<<<nimg * (keep + 1), 128, 0, stream>>>(
+      dy, ids_shuffle, reinterpret_cast<__nv_bfloat16*>(d_demb_bf16), L, keep, Dd);
+  if (L > keep) {
+    const int gx = csm_cdiv(Dd, 128);
+    int gy = csm_cdiv(2 * 148, gx);
+    const int max_gy = csm_cdiv(nimg * (L - keep), 8);
+    if (gy > max_gy) gy = max_gy;
+    mask_token_grad_kernel<<<dim3(gx, gy), 256, 0, stream>>>(dy, ids_shuffle, d_mask_token, nimg, L, keep, Dd);
+  }
   CSM_CHECK_LAUNCH("decoder_assemble_bwd");
   return CSM_OK;
 }
