@@ -136,6 +136,58 @@ __device__ __forceinline__ void gelu_and_grad(float x, float& g, float& gp) {
   gp = fmaf(x * e, 0.39894228040f, cdf);
 }
 
+// Two GELU / GELU' evaluations at once on packed FP32 pairs (FFMA2 / FMUL2 / FADD2, sm_100): same arithmetic as
+// gelu_and_grad, half the FP32-pipe instructions, so the MUFU, logic and shared-memory instructions of the fc1
+// epilogue find free issue slots.
+__device__ __forceinline__ unsigned long long f2_pack(float a, float b) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void f2_unpack(unsigned long long v, float& a, float& b) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long f2_fma(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ unsigned long long f2_mul(unsigned long long a, unsigned long long b) {
+  unsigned long long r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ unsigned long long f2_add(unsigned long long a, unsigned long long b) {
+  unsigned long long r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ void gelu_and_grad2(float x0, float x1, float& g0, float& g1, float& gp0, float& gp1) {
+  const unsigned long long X = f2_pack(x0, x1);
+  const unsigned long long AX = f2_pack(fabsf(x0), fabsf(x1));
+  float d0, d1, t0, t1, a0, a1, e0, e1;
+  f2_unpack(f2_fma(AX, f2_pack(0.2316419f, 0.2316419f), f2_pack(1.0f, 1.0f)), d0, d1);
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t0) : "f"(d0));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t1) : "f"(d1));
+  f2_unpack(f2_mul(f2_mul(X, X), f2_pack(-0.72134752044f, -0.72134752044f)), a0, a1);
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(a0));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(a1));
+  const unsigned long long T = f2_pack(t0, t1), E = f2_pack(e0, e1);
+  unsigned long long poly = f2_fma(T, f2_pack(0.53070271f, 0.53070271f), f2_pack(-0.72657601f, -0.72657601f));
+  poly = f2_fma(poly, T, f2_pack(0.71070688f, 0.71070688f));
+  poly = f2_fma(poly, T, f2_pack(-0.14224836f, -0.14224836f));
+  poly = f2_fma(poly, T, f2_pack(0.12741480f, 0.12741480f));
+  const unsigned long long Q = f2_mul(f2_mul(poly, T), E);                       // 1 - Phi(|x|)
+  // cdf = x >= 0 ? 1 - q : q  ==  0.5 + copysign(0.5 - q, x)
+  float h0, h1;
+  f2_unpack(f2_fma(Q, f2_pack(-1.0f, -1.0f), f2_pack(0.5f, 0.5f)), h0, h1);
+  h0 = __uint_as_float(__float_as_uint(h0) ^ (__float_as_uint(x0) & 0x80000000u));
+  h1 = __uint_as_float(__float_as_uint(h1) ^ (__float_as_uint(x1) & 0x80000000u));
+  const unsigned long long CDF = f2_add(f2_pack(h0, h1), f2_pack(0.5f, 0.5f));
+  f2_unpack(f2_mul(X, CDF), g0, g1);
+  f2_unpack(f2_fma(f2_mul(X, E), f2_pack(0.39894228040f, 0.39894228040f), CDF), gp0, gp1);
+}
+
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred = 0;
   asm volatile(

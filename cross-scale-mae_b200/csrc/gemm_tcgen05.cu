@@ -560,8 +560,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
               for (int j = 0; j < 4; ++j) {
                 float ga, gpa, gb, gpb;
                 bf16_round_pair(v[g * 8 + 2 * j], v[g * 8 + 2 * j + 1]);
-                gelu_and_grad(v[g * 8 + 2 * j], ga, gpa);
-                gelu_and_grad(v[g * 8 + 2 * j + 1], gb, gpb);
+                gelu_and_grad2(v[g * 8 + 2 * j], v[g * 8 + 2 * j + 1], ga, gb, gpa, gpb);
                 ow[j] = pack_bf16x2(gpa, gpb);
                 ow2[j] = pack_bf16x2(ga, gb);
               }
