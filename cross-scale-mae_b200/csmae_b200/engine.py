@@ -69,14 +69,17 @@ def grad_segments(names, offsets, total, enc_layers, enc_groups):
 class _GraphSequence:
     """Captures one call chain into several CUDA graphs: cut() ends the current capture and starts the next."""
 
-    def __init__(self):
+    def __init__(self, stream=None):
         self.graphs = []
         self._ctx = None
         self._pool = None
+        self._stream = stream
 
     def begin(self):
         g = torch.cuda.CUDAGraph()
         kw = {} if self._pool is None else {"pool": self._pool}
+        if self._stream is not None:
+            kw["stream"] = self._stream
         self._ctx = torch.cuda.graph(g, capture_error_mode="thread_local", **kw)
         self._ctx.__enter__()
         self.graphs.append(g)
@@ -143,7 +146,7 @@ class HotPathEngine:
     def _side_stream(self, dev):
         s = self._side.get(dev)
         if s is None:
-            s = torch.cuda.Stream(device=dev)
+            s = torch.cuda.Stream(device=dev)      # same priority as the chain: both orders of preference measured slower
             self._side[dev] = s
         return s
 
