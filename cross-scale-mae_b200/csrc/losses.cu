@@ -305,6 +305,191 @@ __global__ void bn_patch_bwd_kernel(const __nv_bfloat16* __restrict__ h, const _
 }
 
 // ---------------------------------------------------------------------------------------------
+// The same BatchNorm with a channel spread over a cluster of BN_CL CTAs (training mode): every CTA keeps its
+// N / BN_CL rows of the channel in shared memory (ONE global read), the per-channel sums cross the cluster through
+// distributed shared memory, and the three passes of the single-CTA kernels become passes over shared memory.
+// ---------------------------------------------------------------------------------------------
+constexpr int BN_CL = 8;
+
+__device__ __forceinline__ uint32_t bn_cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void bn_cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// sum over the cluster's CTAs of the float at the same shared-memory location
+__device__ __forceinline__ float bn_cluster_sum(const float* slot) {
+  float t = 0.f;
+#pragma unroll
+  for (uint32_t r = 0; r < BN_CL; ++r) {
+    uint32_t a;
+    float v;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(a) : "r"(smem_u32(slot)), "r"(r));
+    asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(a) : "memory");
+    t += v;
+  }
+  return t;
+}
+
+__global__ void __cluster_dims__(BN_CL, 1, 1) __launch_bounds__(256)
+bn_patch_fwd_cluster_kernel(const __nv_bfloat16* __restrict__ h, const float* __restrict__ gamma,
+                            const float* __restrict__ beta, __nv_bfloat16* __restrict__ out,
+                            float* __restrict__ mean_out, float* __restrict__ rstd_out,
+                            float* __restrict__ running_mean, float* __restrict__ running_var, int N, int Sd, int Hp,
+                            float eps, float momentum) {
+  extern __shared__ uint4 s_rows[];                   // [rows of this CTA][Hp / 8]
+  __shared__ float s_buf[32];
+  __shared__ float s_x[2];
+  const int l = blockIdx.x / BN_CL;
+  const int part = static_cast<int>(bn_cluster_rank());
+  const int rows_per = (N + BN_CL - 1) / BN_CL;
+  const int n0 = part * rows_per;
+  const int nrows = max(0, min(N, n0 + rows_per) - n0);
+  const int per_row = Hp / 8;
+  const int total = nrows * per_row;
+  float s = 0.f;
+#pragma unroll 4
+  for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+    const int n = n0 + idx / per_row, c = (idx % per_row) * 8;
+    const uint4 v = *reinterpret_cast<const uint4*>(h + (static_cast<size_t>(n) * Sd + 1 + l) * Hp + c);
+    s_rows[idx] = v;
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = unpack_bf16x2(w[j]);
+      s += f.x + f.y;
+    }
+  }
+  s = block_sum(s, s_buf);
+  if (threadIdx.x == 0) s_x[0] = s;
+  bn_cluster_sync();
+  const float cnt = static_cast<float>(N) * Hp;
+  const float mean = bn_cluster_sum(&s_x[0]) / cnt;
+  float ss = 0.f;
+  for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+    const uint4 v = s_rows[idx];
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = unpack_bf16x2(w[j]);
+      ss += (f.x - mean) * (f.x - mean) + (f.y - mean) * (f.y - mean);
+    }
+  }
+  ss = block_sum(ss, s_buf);
+  if (threadIdx.x == 0) s_x[1] = ss;
+  bn_cluster_sync();
+  const float var = bn_cluster_sum(&s_x[1]) / cnt;
+  const float rstd = rsqrtf(var + eps);
+  if (part == 0 && threadIdx.x == 0) {
+    mean_out[l] = mean;
+    rstd_out[l] = rstd;
+    if (running_mean != nullptr) {
+      running_mean[l] = (1.f - momentum) * running_mean[l] + momentum * mean;
+      running_var[l] = (1.f - momentum) * running_var[l] + momentum * var * (cnt / (cnt - 1.f));
+    }
+  }
+  const float a = rstd * gamma[l], b = beta[l] - mean * rstd * gamma[l];
+  for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+    const int n = n0 + idx / per_row, c = (idx % per_row) * 8;
+    const uint4 v = s_rows[idx];
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = unpack_bf16x2(w[j]);
+      o[j] = pack_bf16x2(fmaxf(bf16_round(f.x * a + b), 0.f), fmaxf(bf16_round(f.y * a + b), 0.f));
+    }
+    *reinterpret_cast<uint4*>(out + (static_cast<size_t>(n) * Sd + 1 + l) * Hp + c) = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+  if (l == 0) {                                       // cls rows of this CTA's images: zero
+    for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+      const int n = n0 + idx / per_row, c = (idx % per_row) * 8;
+      *reinterpret_cast<uint4*>(out + static_cast<size_t>(n) * Sd * Hp + c) = make_uint4(0, 0, 0, 0);
+    }
+  }
+  bn_cluster_sync();                                  // no CTA leaves while a peer may still read its s_x
+}
+
+__global__ void __cluster_dims__(BN_CL, 1, 1) __launch_bounds__(256)
+bn_patch_bwd_cluster_kernel(const __nv_bfloat16* __restrict__ h, const __nv_bfloat16* __restrict__ out,
+                            const __nv_bfloat16* __restrict__ d_out, const float* __restrict__ gamma,
+                            const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
+                            __nv_bfloat16* __restrict__ dh, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                            int N, int Sd, int Hp) {
+  extern __shared__ uint4 s_rows[];                   // [2][rows of this CTA][Hp / 8]: h, dy = d_out * (out > 0)
+  __shared__ float s_buf[32];
+  __shared__ float s_x[2];
+  const int l = blockIdx.x / BN_CL;
+  const int part = static_cast<int>(bn_cluster_rank());
+  const int rows_per = (N + BN_CL - 1) / BN_CL;
+  const int n0 = part * rows_per;
+  const int nrows = max(0, min(N, n0 + rows_per) - n0);
+  const int per_row = Hp / 8;
+  const int total = nrows * per_row;
+  uint4* s_h = s_rows;
+  uint4* s_dy = s_rows + rows_per * per_row;
+  const float mean = mean_in[l], rstd = rstd_in[l];
+  float s1 = 0.f, s2 = 0.f;
+#pragma unroll 2
+  for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+    const int n = n0 + idx / per_row, c = (idx % per_row) * 8;
+    const size_t off = (static_cast<size_t>(n) * Sd + 1 + l) * Hp + c;
+    const uint4 hv = *reinterpret_cast<const uint4*>(h + off);
+    const uint4 ov = *reinterpret_cast<const uint4*>(out + off);
+    const uint4 dv = *reinterpret_cast<const uint4*>(d_out + off);
+    const uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w}, ow[4] = {ov.x, ov.y, ov.z, ov.w}, dw[4] = {dv.x, dv.y, dv.z, dv.w};
+    uint32_t dyw[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 hf = unpack_bf16x2(hw[j]), of = unpack_bf16x2(ow[j]), df = unpack_bf16x2(dw[j]);
+      const float dy0 = of.x > 0.f ? df.x : 0.f, dy1 = of.y > 0.f ? df.y : 0.f;
+      s1 += dy0 + dy1;
+      s2 += dy0 * (hf.x - mean) * rstd + dy1 * (hf.y - mean) * rstd;
+      dyw[j] = pack_bf16x2(dy0, dy1);                 // exact: dy is d_out or 0
+    }
+    s_h[idx] = hv;
+    s_dy[idx] = make_uint4(dyw[0], dyw[1], dyw[2], dyw[3]);
+  }
+  s1 = block_sum(s1, s_buf);
+  s2 = block_sum(s2, s_buf);
+  if (threadIdx.x == 0) {
+    s_x[0] = s1;
+    s_x[1] = s2;
+  }
+  bn_cluster_sync();
+  s1 = bn_cluster_sum(&s_x[0]);
+  s2 = bn_cluster_sum(&s_x[1]);
+  if (part == 0 && threadIdx.x == 0) {
+    dgamma[l] = s2;
+    dbeta[l] = s1;
+  }
+  const float cnt = static_cast<float>(N) * Hp;
+  const float m1 = s1 / cnt, m2 = s2 / cnt, gr = gamma[l] * rstd;
+  for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+    const int n = n0 + idx / per_row, c = (idx % per_row) * 8;
+    const uint4 hv = s_h[idx], dv = s_dy[idx];
+    const uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w}, dw[4] = {dv.x, dv.y, dv.z, dv.w};
+    uint32_t r[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 hf = unpack_bf16x2(hw[j]), df = unpack_bf16x2(dw[j]);
+      r[j] = pack_bf16x2(gr * (df.x - m1 - (hf.x - mean) * rstd * m2), gr * (df.y - m1 - (hf.y - mean) * rstd * m2));
+    }
+    *reinterpret_cast<uint4*>(dh + (static_cast<size_t>(n) * Sd + 1 + l) * Hp + c) = make_uint4(r[0], r[1], r[2], r[3]);
+  }
+  if (l == 0) {
+    for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+      const int n = n0 + idx / per_row, c = (idx % per_row) * 8;
+      *reinterpret_cast<uint4*>(dh + static_cast<size_t>(n) * Sd * Hp + c) = make_uint4(0, 0, 0, 0);
+    }
+  }
+  bn_cluster_sync();
+}
+
+// ---------------------------------------------------------------------------------------------
 // NT-Xent.  feat[n] = mean over tokens 1.. of the un-normed encoder output, z = normalize(feat),
 // cos re-normalises z (CosineSimilarity), E = exp(cos / tau), positives (i, i +- B),
 // loss = mean_i -log(E_pos / (sum_{j not in {i, pos}} E_ij + eps)).
@@ -342,6 +527,49 @@ __global__ void token_mean_normalize_kernel(const float* __restrict__ x, float* 
     const int i = threadIdx.x + k * blockDim.x;
     if (i < D) zhat[static_cast<size_t>(n) * D + i] = local[k] / n2;
   }
+  if (threadIdx.x == 0) fnorm[n] = d1 * n2;
+}
+
+// Same result with the tokens spread over RL row lanes of D/4 float4 column groups (blockDim = RL * D/4, a multiple
+// of 32): every thread has its ~12 independent 16-byte loads in flight at once instead of walking 49 tokens per
+// column (27 us -> latency of one round).
+__global__ void token_mean_normalize_v4_kernel(const float* __restrict__ x, float* __restrict__ zhat,
+                                               float* __restrict__ fnorm, int Se, int D) {
+  extern __shared__ float4 s_acc[];                 // [RL][D/4]
+  __shared__ float s_buf[32];
+  const int n = blockIdx.x;
+  const int vec = D >> 2;
+  const int cg = threadIdx.x % vec, rl = threadIdx.x / vec, RL = blockDim.x / vec;
+  const float* xr = x + static_cast<size_t>(n) * Se * D + cg * 4;
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+  for (int t = 1 + rl; t < Se; t += RL) {
+    const float4 v = *reinterpret_cast<const float4*>(xr + static_cast<size_t>(t) * D);
+    a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+  }
+  s_acc[rl * vec + cg] = a;
+  __syncthreads();
+  float ss = 0.f;
+  if (rl == 0) {
+    for (int k = 1; k < RL; ++k) {
+      const float4 v = s_acc[k * vec + cg];
+      a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+    }
+    const float inv = 1.0f / static_cast<float>(Se - 1);
+    a.x *= inv; a.y *= inv; a.z *= inv; a.w *= inv;
+    ss = a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w;
+  }
+  const float norm = sqrtf(block_sum(ss, s_buf));
+  const float d1 = fmaxf(norm, 1e-12f);           // F.normalize eps
+  float ss2 = 0.f;
+  if (rl == 0) {
+    a.x /= d1; a.y /= d1; a.z /= d1; a.w /= d1;
+    ss2 = a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w;
+  }
+  const float n2 = fmaxf(sqrtf(block_sum(ss2, s_buf)), 1e-8f);  // CosineSimilarity eps
+  if (rl == 0)
+    *reinterpret_cast<float4*>(zhat + static_cast<size_t>(n) * D + cg * 4) =
+        make_float4(a.x / n2, a.y / n2, a.z / n2, a.w / n2);
   if (threadIdx.x == 0) fnorm[n] = d1 * n2;
 }
 
@@ -501,6 +729,19 @@ extern "C" int csm_bn_patch_fwd(const void* h_bf16, const float* gamma, const fl
   CSM_CHECK_ARG(N > 0 && L > 0 && Hp % 8 == 0, "csm_bn_patch_fwd: bad sizes N=%d L=%d Hp=%d", N, L, Hp);
   CSM_CHECK_ARG(training || (running_mean != nullptr && running_var != nullptr),
                 "csm_bn_patch_fwd: eval mode needs running statistics");
+  const size_t cl_smem = static_cast<size_t>((N + BN_CL - 1) / BN_CL) * Hp * 2;
+  if (training && N >= BN_CL && cl_smem <= 96 * 1024) {
+    static size_t configured = 0;
+    if (cl_smem > configured) {
+      cudaFuncSetAttribute(bn_patch_fwd_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cl_smem);
+      configured = cl_smem;
+    }
+    bn_patch_fwd_cluster_kernel<<<L * BN_CL, 256, cl_smem, stream>>>(
+        reinterpret_cast<const __nv_bfloat16*>(h_bf16), gamma, beta, reinterpret_cast<__nv_bfloat16*>(out_bf16), mean,
+        rstd, running_mean, running_var, N, L + 1, Hp, eps, momentum);
+    CSM_CHECK_LAUNCH("bn_patch_fwd");
+    return CSM_OK;
+  }
   bn_patch_fwd_kernel<<<L, 1024, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(h_bf16), gamma, beta,
                                              reinterpret_cast<__nv_bfloat16*>(out_bf16), mean, rstd, running_mean,
                                              running_var, N, L + 1, Hp, eps, momentum, training);
@@ -512,6 +753,20 @@ extern "C" int csm_bn_patch_bwd(const void* h_bf16, const void* out_bf16, const 
                                 const float* mean, const float* rstd, void* dh_bf16, float* dgamma, float* dbeta,
                                 int N, int L, int Hp, cudaStream_t stream) {
   CSM_CHECK_ARG(N > 0 && L > 0 && Hp % 8 == 0, "csm_bn_patch_bwd: bad sizes N=%d L=%d Hp=%d", N, L, Hp);
+  const size_t cl_smem = static_cast<size_t>((N + BN_CL - 1) / BN_CL) * Hp * 2 * 2;
+  if (N >= BN_CL && cl_smem <= 96 * 1024) {
+    static size_t configured = 0;
+    if (cl_smem > configured) {
+      cudaFuncSetAttribute(bn_patch_bwd_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cl_smem);
+      configured = cl_smem;
+    }
+    bn_patch_bwd_cluster_kernel<<<L * BN_CL, 256, cl_smem, stream>>>(
+        reinterpret_cast<const __nv_bfloat16*>(h_bf16), reinterpret_cast<const __nv_bfloat16*>(out_bf16),
+        reinterpret_cast<const __nv_bfloat16*>(d_out_bf16), gamma, mean, rstd, reinterpret_cast<__nv_bfloat16*>(dh_bf16),
+        dgamma, dbeta, N, L + 1, Hp);
+    CSM_CHECK_LAUNCH("bn_patch_bwd");
+    return CSM_OK;
+  }
   bn_patch_bwd_kernel<<<L, 1024, 0, stream>>>(
       reinterpret_cast<const __nv_bfloat16*>(h_bf16), reinterpret_cast<const __nv_bfloat16*>(out_bf16),
       reinterpret_cast<const __nv_bfloat16*>(d_out_bf16), gamma, mean, rstd, reinterpret_cast<__nv_bfloat16*>(dh_bf16),
@@ -524,7 +779,15 @@ extern "C" int csm_ntxent_fwd(const float* enc_out, float* zhat, float* fnorm, f
                               int Se, int D, float tau, float eps, cudaStream_t stream) {
   CSM_CHECK_ARG(B > 0 && Se >= 2 && D > 0 && D <= 1024 && D % 4 == 0, "csm_ntxent_fwd: bad sizes B=%d Se=%d D=%d", B, Se,
                 D);
-  token_mean_normalize_kernel<<<2 * B, 256, 0, stream>>>(enc_out, zhat, fnorm, Se, D);
+  const int vec = D / 4;
+  int RL = 1024 / vec;
+  if (RL > 4) RL = 4;
+  while (RL > 1 && (RL * vec) % 32 != 0) --RL;
+  if ((RL * vec) % 32 == 0 && (reinterpret_cast<uintptr_t>(enc_out) & 15) == 0)
+    token_mean_normalize_v4_kernel<<<2 * B, RL * vec, static_cast<size_t>(RL) * vec * sizeof(float4), stream>>>(
+        enc_out, zhat, fnorm, Se, D);
+  else
+    token_mean_normalize_kernel<<<2 * B, 256, 0, stream>>>(enc_out, zhat, fnorm, Se, D);
   CSM_CHECK_LAUNCH("token_mean_normalize");
   ntxent_fwd_kernel<<<2 * B, 128, 2 * B * sizeof(float), stream>>>(zhat, neg, loss_sum, B, D, 1.f / tau, eps);
   CSM_CHECK_LAUNCH("ntxent_fwd");

@@ -420,8 +420,11 @@ def test_cross_mse(nat):
     close(d_cp.view(N, Sd, Dd), ref, 1e-2, 1e-7, "cross mse d_cp")
 
 
-def test_bn_patch(nat):
-    N, L, Hp = 8, 16, 128
+# N >= 8 with N/8 rows x Hp x 2 B <= 96 KB (48 KB for the backward): the channel is spread over a cluster of 8 CTAs
+# (rows staged in shared memory, sums through DSMEM); (11, ...) leaves two CTAs of the cluster without rows;
+# N = 4 and the eval-mode call take the one-CTA-per-channel kernels
+@pytest.mark.parametrize("N,L,Hp", [(8, 16, 128), (11, 9, 256), (4, 16, 128), (64, 196, 2048)])
+def test_bn_patch(nat, N, L, Hp):
     Sd = L + 1
     h = rnd(N * Sd, Hp, dtype=bf16, scale=2.0)
     gamma, beta = 1 + 0.1 * rnd(L), 0.1 * rnd(L, seed=3)
