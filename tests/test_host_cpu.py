@@ -303,3 +303,32 @@ def test_grad_segments_cover_flat_buffer_in_completion_order():
         for k, l in enumerate(layers):
             assert segs[1 + k][0] == offs[names.index(f"encoder.{l}.norm1.weight")]
     assert grad_segments(["a", "b"], [0, 4], 8, 0, 3) == ([(0, 8)], [])
+
+
+def test_prefetcher_batch_structure_roundtrip():
+    """DevicePrefetcher copies arbitrarily nested (tuple / list) batches leaf by leaf: the flatten / unflatten pair
+    keeps container types, order and non-tensor leaves (pure host logic; the copies are covered by the GPU test)."""
+    import torch
+    from csmae_b200.prefetch import _flatten, _unflatten
+    batch = (torch.zeros(2, 3), [torch.ones(1), 7, (torch.full((2,), 5.0), "name")], None)
+    flat, spec = _flatten(batch)
+    assert len(flat) == 6 and flat[2] == 7 and flat[4] == "name" and flat[5] is None
+    back = _unflatten(flat, spec)
+    assert isinstance(back, tuple) and isinstance(back[1], list) and isinstance(back[1][2], tuple)
+    assert back[1][1] == 7 and back[1][2][1] == "name" and back[2] is None
+    assert torch.equal(back[0], batch[0]) and torch.equal(back[1][2][0], batch[1][2][0])
+    single, spec1 = _flatten(torch.arange(3))
+    assert spec1 is None and torch.equal(_unflatten(single, spec1), torch.arange(3))
+
+
+def test_tools_and_bench_compile():
+    """bench.py, __graft_entry__.py and every development tool are at least syntactically valid on the CPU box."""
+    import glob
+    import os
+    import py_compile
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    files = [os.path.join(root, "bench.py"), os.path.join(root, "__graft_entry__.py")] + \
+        sorted(glob.glob(os.path.join(root, "tools", "*.py")))
+    assert len(files) >= 6
+    for f in files:
+        py_compile.compile(f, doraise=True)
