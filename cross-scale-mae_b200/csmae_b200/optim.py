@@ -53,9 +53,25 @@ class FusedAdamW(torch.optim.Optimizer):
         cache = dict(tab=tab, host=host, host_np=host.numpy().view(_ENTRY),
                      dev=torch.empty(tab.nbytes, dtype=torch.uint8, device=dev),
                      chunks=torch.tensor(chunks, dtype=torch.int32).to(dev), nchunks=len(chunks),
-                     key=tuple((p.data_ptr(), p.grad.data_ptr()) for _, p, _ in items),
-                     shadowed=bool(shadows), items=items)
+                     key=self._key(items), shadowed=bool(shadows), items=items)
         return cache
+
+    @staticmethod
+    def _key(items):
+        # every pointer the device table holds: a parameter, gradient or moment tensor that was replaced (zero_grad
+        # with set_to_none, load_state_dict on resume, .to()) invalidates the table
+        return tuple((p.data_ptr(), p.grad.data_ptr(), st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr())
+                     for _, p, st in items)
+
+    def load_state_dict(self, state_dict):
+        """Resume (util/misc.py:393-411 calls optimizer.load_state_dict): accepts a torch.optim.AdamW or FusedAdamW
+        state dict; the moment tensors are new objects afterwards, so the cached pointer table is dropped."""
+        super().load_state_dict(state_dict)
+        self._cache = None
+        for st in self.state.values():
+            for k in ("exp_avg", "exp_avg_sq"):
+                if k in st and (st[k].dtype != torch.float32 or not st[k].is_contiguous()):
+                    st[k] = st[k].float().contiguous()
 
     # ------------------------------------------------------------------ step
     @torch.no_grad()
@@ -83,8 +99,7 @@ class FusedAdamW(torch.optim.Optimizer):
             return loss
         dev = items[0][1].device
         cache = self._cache
-        if (cache is None or len(cache["items"]) != len(items)
-                or cache["key"] != tuple((p.data_ptr(), p.grad.data_ptr()) for _, p, _ in items)
+        if (cache is None or len(cache["items"]) != len(items) or cache["key"] != self._key(items)
                 or cache["shadowed"] != bool(self._engine is not None and self._engine._w16_views)):
             cache = self._cache = self._build(items, dev)
         tab = cache["tab"]

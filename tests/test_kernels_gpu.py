@@ -554,3 +554,31 @@ def test_fused_adamw_matches_torch():
     # global gradient norm (util/misc.py:338-355)
     want = torch.norm(torch.stack([torch.norm(p.grad, 2.0) for p in ref_p]), 2.0)
     close(ours.grad_norm().reshape(1), want.reshape(1), 1e-5, 0, "grad norm")
+    # resume (util/misc.py:393-411: optimizer.load_state_dict(checkpoint["optimizer"])): a FusedAdamW that already
+    # stepped takes over torch.optim.AdamW's checkpoint -- the moment tensors are replaced, the cached device table
+    # must follow them -- and keeps tracking the reference optimizer afterwards
+    import copy
+    import io
+    buf = io.BytesIO()
+    torch.save(ref.state_dict(), buf)
+    buf.seek(0)
+    with torch.no_grad():
+        for a, b in zip(ref_p, our_p):
+            b.copy_(a)
+    ours.load_state_dict(torch.load(buf, map_location="cpu"))
+    del buf
+    junk = [torch.full((1 << 20,), float("nan"), device="cuda") for _ in range(8)]   # reuse freed moment storage
+    for step in range(2):
+        for a, b in zip(ref_p, our_p):
+            g = torch.randn_like(a)
+            a.grad, b.grad = g.clone(), g.clone()
+        ref.step()
+        ours.step()
+        for a, b in zip(ref_p, our_p):
+            close(b.detach(), a.detach(), 2e-6, 2e-7, f"FusedAdamW after resume, step {step}")
+    del junk
+    sa, sb = ref.state_dict()["state"], copy.deepcopy(ours.state_dict()["state"])
+    for k in sa:
+        assert float(sa[k]["step"]) == float(sb[k]["step"])
+        # (torch updates exp_avg with lerp, the kernel with beta1 * m + (1 - beta1) * g: same value, different rounding)
+        close(sb[k]["exp_avg"], sa[k]["exp_avg"], 1e-5, 1e-6, "exp_avg after resume")
