@@ -332,3 +332,44 @@ def test_tools_and_bench_compile():
     assert len(files) >= 6
     for f in files:
         py_compile.compile(f, doraise=True)
+
+
+def test_checkpoint_round_trip_and_finetune_key_remap(tmp_path):
+    """a checkpoint written the way util/misc.py:358-375 writes it ({"model", "optimizer", "epoch",
+    ...}) loads back with strict=True, and the key remap the fine-tune script applies to a pretraining checkpoint
+    (main_finetune.py:553-586, restated below: `encoder_X` -> `X`, `encoder.` -> `blocks.`, cls_token and the patch
+    embedding kept, everything else dropped) lands exactly on timm VisionTransformer's parameter names."""
+    import csmae_b200
+    cfg = dict(dim_model=64, encoder_num_layers=2, encoder_num_heads=1, decoder_embed_dim=64, decoder_num_layers=2,
+               decoder_num_heads=2, input_size=64, patch_size=16, predictor_hidden_size=128)
+    torch.manual_seed(3)
+    m = csmae_b200.MAE_ViT_MsLdCeCd(**cfg, device="cpu")
+    path = os.path.join(tmp_path, "checkpoint-0.pth")
+    torch.save({"model": m.state_dict(), "epoch": 0}, path)
+    ck = torch.load(path, map_location="cpu")
+    torch.manual_seed(4)
+    m2 = csmae_b200.MAE_ViT_MsLdCeCd(**cfg, device="cpu")
+    missing, unexpected = m2.load_state_dict(ck["model"], strict=True)
+    assert not missing and not unexpected
+    for (ka, a), (kb, b) in zip(m.state_dict().items(), m2.state_dict().items()):
+        assert ka == kb and torch.equal(a, b), ka
+
+    remapped = {}
+    for key, value in ck["model"].items():                       # main_finetune.py:567-586
+        if "encoder" in key:
+            if "encoder_" in key:
+                name = key.replace("encoder_", "")
+            else:
+                name = key.replace("encoder", "blocks")
+            remapped[name] = value
+        elif key in {"cls_token", "patch_embed.proj.weight", "patch_embed.proj.bias"}:
+            remapped[key] = value
+    want = {"cls_token", "pos_embed", "patch_embed.proj.weight", "patch_embed.proj.bias", "norm.weight", "norm.bias"}
+    for i in range(cfg["encoder_num_layers"]):
+        for mod in ("norm1", "attn.qkv", "attn.proj", "norm2", "mlp.fc1", "mlp.fc2"):
+            want |= {f"blocks.{i}.{mod}.weight", f"blocks.{i}.{mod}.bias"}
+    assert set(remapped) == want, set(remapped) ^ want
+    D, L = cfg["dim_model"], (cfg["input_size"] // cfg["patch_size"]) ** 2
+    assert remapped["pos_embed"].shape == (1, L + 1, D)          # what interpolate_pos_embed expects
+    assert remapped["blocks.0.attn.qkv.weight"].shape == (3 * D, D)
+    assert remapped["patch_embed.proj.weight"].shape == (D, 3, 16, 16)
