@@ -44,6 +44,8 @@ SIGNATURES = {
     "csm_cast_multi": [_P, _I, _I, _P],
     "csm_cast_f32_bf16": [_P, _P, _L, _P],
     "csm_attention_fwd": [_P, _P, _P, _I, _I, _I, _I, _P],
+    "csm_attention_fwd_tc": [_P, _P, _P, _I, _I, _I, _I, _I, _P],
+    "csm_attention_bwd_tc": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
     "csm_attention_bwd": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
     "csm_recon_loss_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "csm_recon_loss_bwd": [_P, _P, _P, _P, _P, _F, _I, _I, _I, _I, _I, _I, _P],

@@ -17,7 +17,7 @@ LIB_DIR = os.path.join(PKG_DIR, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libcsmae_b200.so")
 STAMP = os.path.join(LIB_DIR, "build.stamp")
 
-SOURCES = ["runtime.cu", "gemm_tcgen05.cu", "attention.cu", "layernorm.cu", "masking.cu", "losses.cu", "optim.cu"]
+SOURCES = ["runtime.cu", "gemm_tcgen05.cu", "attention.cu", "attention_tc.cu", "layernorm.cu", "masking.cu", "losses.cu", "optim.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC"]
 

@@ -39,6 +39,11 @@ void csm_set_error(const char* fmt, ...);
 
 static inline int csm_cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
+// Cached cuTensorMapEncodeTiled over a row-major matrix [outer, inner] (leading dimension ld elements) of bf16
+// (elem_bytes 2) or f32 (4), boxes {box_inner, box_outer}, 128- or 64-byte swizzle (gemm_tcgen05.cu).
+int csm_tensor_map_2d(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld,
+                      uint32_t box_inner, uint32_t box_outer, uint32_t elem_bytes, uint32_t swizzle_bytes);
+
 #ifdef __CUDACC__
 // Launch with programmatic dependent launch (PDL): the grid may be scheduled while the previous kernel of the
 // stream is still draining; every kernel launched this way calls csm::pdl_wait() before it touches global

@@ -910,6 +910,12 @@ int launch_gemm(const void* a, uint64_t a_inner, uint64_t a_outer, const void* b
 
 }  // namespace
 
+// shared with the attention kernels (declared in common.cuh)
+int csm_tensor_map_2d(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld,
+                      uint32_t box_inner, uint32_t box_outer, uint32_t elem_bytes, uint32_t swizzle_bytes) {
+  return get_tensor_map(out, ptr, inner, outer, ld, box_inner, box_outer, elem_bytes, swizzle_bytes);
+}
+
 // ---------------------------------------------------------------------------------------------
 // C-ABI (declared in include/csmae_b200.h)
 // ---------------------------------------------------------------------------------------------
