@@ -8,10 +8,10 @@ from .model import (MAE_ViT_Baseline, MAE_ViT_MsLd, MAE_ViT_MsLdCd, MAE_ViT_MsLd
                     mae_vit_base, mae_vit_base_MsLd, mae_vit_base_MsLdCd, mae_vit_base_MsLdCeCd, mae_vit_base_patch16, mae_vit_large,
                     mae_vit_large_MsLdCeCd, mae_vit_large_patch16)
 
-from .optim import FusedAdamW
+from .optim import FusedAdamW, NativeScalerWithGradNormCount
 from .parallel import DistributedDataParallel
 from .prefetch import DevicePrefetcher
 
-__all__ = ["DevicePrefetcher", "DistributedDataParallel", "FusedAdamW", "MAE_ViT_Baseline", "MAE_ViT_MsLd", "MAE_ViT_MsLdCd", "MAE_ViT_MsLdCeCd", "mae_vit_base_MsLdCd", "args_mae_vit_base", "args_mae_vit_large",
+__all__ = ["DevicePrefetcher", "DistributedDataParallel", "FusedAdamW", "NativeScalerWithGradNormCount", "MAE_ViT_Baseline", "MAE_ViT_MsLd", "MAE_ViT_MsLdCd", "MAE_ViT_MsLdCeCd", "mae_vit_base_MsLdCd", "args_mae_vit_base", "args_mae_vit_large",
            "mae_vit_base", "mae_vit_large", "mae_vit_base_MsLd", "mae_vit_base_MsLdCeCd", "mae_vit_large_MsLdCeCd",
            "mae_vit_base_patch16", "mae_vit_large_patch16"]

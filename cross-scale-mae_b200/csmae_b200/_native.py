@@ -44,26 +44,34 @@ SIGNATURES = {
     "csm_cast_multi": [_P, _I, _I, _P],
     "csm_cast_f32_bf16": [_P, _P, _L, _P],
     "csm_attention_fwd": [_P, _P, _P, _I, _I, _I, _I, _P],
-    "csm_attention_fwd_tc": [_P, _P, _P, _I, _I, _I, _I, _I, _P],
-    "csm_attention_bwd_tc": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
     "csm_attention_bwd": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
     "csm_recon_loss_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "csm_recon_loss_bwd": [_P, _P, _P, _P, _P, _F, _I, _I, _I, _I, _I, _I, _P],
     "csm_cross_mse_fwd": [_P, _P, _P, _I, _I, _I, _P],
     "csm_cross_mse_bwd": [_P, _P, _P, _P, _P, _F, _I, _I, _I, _P],
     "csm_bn_patch_fwd": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _F, _I, _P],
-    "csm_bn_patch_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P],
+    "csm_bn_patch_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
     "csm_ntxent_fwd": [_P, _P, _P, _P, _P, _I, _I, _I, _F, _F, _P],
     "csm_ntxent_bwd": [_P, _P, _P, _P, _P, _I, _I, _F, _F, _P],
-    "csm_adamw_multi": [_P, _P, _I, _I, _P],
+    "csm_adamw_multi": [_P, _P, _I, _P, _I, _P],
+    "csm_grad_stats_f32": [_P, _L, _P, _P, _I, _P],
+    "csm_amp_update": [_P, _P, _P, _P, _F, _F, _F, _I, _P],
     "csm_sumsq_f32": [_P, _L, _P, _I, _P],
+}
+
+# development-only exports (not part of the C-ABI in include/csmae_b200.h): the mma.sync attention kernels kept as the
+# A/B baseline and the forward variant switch, used by tools/attn_tc_check.py
+DEV_SIGNATURES = {
+    "csm_attention_fwd_tc": [_P, _P, _P, _I, _I, _I, _I, _I, _P],
+    "csm_attention_fwd_legacy": [_P, _P, _P, _I, _I, _I, _I, _P],
+    "csm_attention_bwd_legacy": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
 }
 
 _lib = None
 _lock = threading.Lock()
 _sm_count = {}
 launch_count = 0   # kernels launched through the C-ABI so far (bench.py reports the delta)
-KERNELS_PER_CALL = {"csm_ntxent_fwd": 2, "csm_decoder_assemble_bwd": 2}
+KERNELS_PER_CALL = {"csm_ntxent_fwd": 2, "csm_decoder_assemble_bwd": 2, "csm_attention_bwd": 2}
 
 
 class NativeError(RuntimeError):
@@ -90,7 +98,7 @@ def load():
         lib = ctypes.CDLL(path)
         lib.csm_last_error.restype = ctypes.c_char_p
         lib.csm_last_error.argtypes = []
-        for name, argtypes in SIGNATURES.items():
+        for name, argtypes in {**SIGNATURES, **DEV_SIGNATURES}.items():
             fn = getattr(lib, name)
             fn.restype = _c_int
             fn.argtypes = argtypes

@@ -101,7 +101,11 @@ class HotPathEngine:
         self.use_cd = use_cd
         self.use_ce = use_ce
         self.generation = 0
-        self._bufs = {}
+        # Workspaces: captured CUDA graphs bake in the raw pointers of every buffer they touch, so each graph entry OWNS
+        # the buffers it was captured over (entry["bufs"], allocated inside the capture from the graph's pool); eager
+        # steps use their own dictionary, which may reallocate freely when shapes change.
+        self._eager_bufs = {}
+        self._bufs = self._eager_bufs     # the active workspace
         self._state = None          # what the last forward saved for the backward
         self._w16 = None            # flat bf16 shadow of every GEMM weight
         self._w16_views = {}
@@ -109,8 +113,7 @@ class HotPathEngine:
         self._w16_versions = None
         self._cast_table = None
         self._names = None
-        self._coefs = None
-        self._coefs_key = None
+        self._coefs = {}            # loss coefficient tensors by (values, device)
         self._last_out = None
         self._snap = None
         self.use_graphs = os.environ.get("CSMAE_CUDA_GRAPHS", "1") != "0"
@@ -256,16 +259,27 @@ class HotPathEngine:
         return t
 
     def workspace_bytes(self):
-        return sum(t.numel() * t.element_size() for t in self._bufs.values())
+        seen, total = set(), 0
+        for d in [self._eager_bufs] + [e["bufs"] for e in self._graphs.values()]:
+            for t in d.values():
+                if t.data_ptr() not in seen:
+                    seen.add(t.data_ptr())
+                    total += t.numel() * t.element_size()
+        return total
 
     # ------------------------------------------------------------------ forward
     def forward(self, imgs_list, noises, mask_ratio, training):
         dev = imgs_list[0].device
         if dev.type != "cuda":
             raise nat.NativeError("csmae_b200 runs on sm_100 CUDA devices only (no CPU fallback): got " + str(dev))
+        with torch.cuda.device(dev):             # _native.call launches on the current device's current stream
+            return self._forward(imgs_list, noises, mask_ratio, training)
+
+    def _forward(self, imgs_list, noises, mask_ratio, training):
         snap = self.snapshot()
         self._refresh_weights(snap)              # outside any graph: runs only when a master weight changed
         if not self.use_graphs or torch.cuda.is_current_stream_capturing():
+            self._bufs = self._eager_bufs
             return self._forward_eager(imgs_list, noises, mask_ratio, training)
         key = self._graph_key(imgs_list, noises, mask_ratio, training, snap)
         entry = self._graphs.get(key)
@@ -273,8 +287,10 @@ class HotPathEngine:
             seen = self._warm.get(key, 0)
             if seen < self.graph_warmup_steps:
                 self._warm[key] = seen + 1
+                self._bufs = self._eager_bufs
                 return self._forward_eager(imgs_list, noises, mask_ratio, training)
             entry = self._capture_forward(key, imgs_list, noises, mask_ratio, training)
+        self._bufs = entry["bufs"]
         for dst, src in zip(entry["imgs"], imgs_list):
             dst.copy_(src, non_blocking=True)
         for dst, src in zip(entry["noise"], noises):
@@ -295,7 +311,13 @@ class HotPathEngine:
         if len(self._graphs) >= 4:               # shapes keep changing: stop hoarding graphs
             self._graphs.clear()
         entry = dict(imgs=[torch.empty_like(im, dtype=torch.float32).contiguous() for im in imgs_list],
-                     noise=[torch.empty_like(nz, dtype=torch.float32).contiguous() for nz in noises], bwd=None)
+                     noise=[torch.empty_like(nz, dtype=torch.float32).contiguous() for nz in noises], bwd=None,
+                     bufs={})
+        # the eager warm-up workspace is not needed once the step replays from graphs: give its memory back
+        self._eager_bufs.clear()
+        self._bufs = entry["bufs"]
+        # the H2D copy of the loss coefficients must not happen inside the capture
+        self._coefs_tensor(self._coef_values(len(imgs_list), imgs_list[0].shape[0], mask_ratio)[0], imgs_list[0].device)
         for dst, src in zip(entry["imgs"], imgs_list):
             dst.copy_(src)
         for dst, src in zip(entry["noise"], noises):
@@ -385,9 +407,7 @@ class HotPathEngine:
         norm_pix = 1 if m.norm_pix_loss else 0
         for s, im in enumerate(imgs_list):
             call("csm_recon_loss_fwd", pred_full[s * N * Sd:], im, mask[s * N:], loss_acc[s:], N, C, H, p, L, norm_pix)
-        n_masked = N * (L - keep)
-        red = 0.5 if (ns == 2 and getattr(m, "ms_decoder_loss_reduction", "sum") == "mean") else 1.0
-        coefs = [red / n_masked if n_masked > 0 else float("nan")] * ns + [0.0] * (8 - ns)
+        coefs, red = self._coef_values(ns, N, mask_ratio)
         if ns == 2 and self.use_cd:
             Hp = m.predictor[0].out_features
             h1 = buf("pred.h1", (N * Sd, Hp), bf16)
@@ -405,19 +425,13 @@ class HotPathEngine:
             call("csm_linear_fwd", a1, w16["predictor.3.weight"], params["predictor.3.bias"], cp, None,
                  N * Sd, Dd, Hp, EPI_BF16)
             call("csm_cross_mse_fwd", cp, dec_f32, loss_acc[2:], N * Sd, Sd, Dd)
-            coefs[2] = 1.0 / (N * L * Dd)
             st["Hp"] = Hp
         if ns == 2 and self.use_ce:
             zhat = buf("ntx.zhat", (NB, D), f32)
             fnorm = buf("ntx.fnorm", (NB,), f32)
             neg = buf("ntx.neg", (NB,), f32)
             call("csm_ntxent_fwd", x, zhat, fnorm, neg, loss_acc[3:], N, Se, D, NTXENT_TAU, NTXENT_EPS)
-            coefs[3] = 1.0
-        ck = (tuple(coefs), dev)
-        if self._coefs_key != ck:
-            self._coefs = torch.tensor(coefs, dtype=f32).to(dev)
-            self._coefs_key = ck
-        loss = (loss_acc * self._coefs).sum()
+        loss = (loss_acc * self._coefs_tensor(coefs, dev)).sum()
         st["coefs"] = coefs
         st["red"] = red
         self._state = st
@@ -431,6 +445,31 @@ class HotPathEngine:
                    enc_emb=[enc[s * N:(s + 1) * N] for s in range(ns)],
                    dec_emb=[dec[s * N:(s + 1) * N] for s in range(ns)])
         return out
+
+    def _coef_values(self, ns, N, mask_ratio):
+        m = self.model
+        L = m.num_patches
+        keep = int(L * (1 - mask_ratio))
+        n_masked = N * (L - keep)
+        red = 0.5 if (ns == 2 and getattr(m, "ms_decoder_loss_reduction", "sum") == "mean") else 1.0
+        coefs = [red / n_masked if n_masked > 0 else float("nan")] * ns + [0.0] * (8 - ns)
+        if ns == 2 and self.use_cd:
+            coefs[2] = 1.0 / (N * L * m.decoder_embed_dim)
+        if ns == 2 and self.use_ce:
+            coefs[3] = 1.0
+        return coefs, red
+
+    def _coefs_tensor(self, coefs, dev):
+        """Device copy of the loss coefficients, cached per (values, device): never created inside a stream capture."""
+        key = (tuple(coefs), dev)
+        t = self._coefs.get(key)
+        if t is None:
+            if torch.cuda.is_current_stream_capturing():
+                raise RuntimeError("csmae_b200: loss coefficients must be staged before a CUDA-graph capture")
+            if len(self._coefs) > 64:
+                self._coefs.clear()
+            t = self._coefs[key] = torch.tensor(coefs, dtype=torch.float32).to(dev)
+        return t
 
     def _blocks_fwd(self, tag, pname, nlayers, x, NB, S, Dm, heads, params, w16, dev):
         bf16, f32 = torch.bfloat16, torch.float32
@@ -470,6 +509,12 @@ class HotPathEngine:
 
     # ------------------------------------------------------------------ backward
     def backward(self, grad_loss, generation):
+        if not grad_loss.is_cuda:                # host-logic tests stub the kernel chain on CPU tensors
+            return self._backward(grad_loss, generation)
+        with torch.cuda.device(grad_loss.device):
+            return self._backward(grad_loss, generation)
+
+    def _backward(self, grad_loss, generation):
         st = self._state
         if st is None or st["generation"] != generation or generation != self.generation:
             raise RuntimeError(
@@ -533,11 +578,11 @@ class HotPathEngine:
         # The views handed to autograd alias the graph's gradient buffer (no 4 B/param copy per step); autograd
         # adopts them as .grad when .grad is None.  If a .grad still aliases the buffer when the next backward
         # starts (gradient accumulation without zero_grad), the accumulated values are moved out first.
-        first = entry["like"][0]
-        if first.grad is not None and first.grad.data_ptr() == flat.data_ptr():
+        lo, hi = flat.data_ptr(), flat.data_ptr() + flat.numel() * 4
+        if any(p.grad is not None and lo <= p.grad.data_ptr() < hi for p in entry["like"]):
             saved = flat.clone()
-            for p, v in zip(entry["like"], views_of(saved)):
-                if p.grad is not None:
+            for p, v, a in zip(entry["like"], views_of(saved), views_of(flat)):
+                if p.grad is not None and p.grad.data_ptr() == a.data_ptr():
                     p.grad = v
         pending = []
         for k, g in enumerate(entry["bwd"]):
@@ -615,7 +660,7 @@ class HotPathEngine:
             call("csm_linear_dgrad", d_cp, w16["predictor.3.weight"], d_a1, None, N * Sd, Dd, Hp, EPI_BF16)
             dh1 = buf("b.dh1", (N * Sd, Hp), bf16)
             call("csm_bn_patch_bwd", B["pred.h1"], B["pred.a1"], d_a1, bn.weight, B["pred.bn_mean"], B["pred.bn_rstd"],
-                 dh1, G["predictor.1.weight"], G["predictor.1.bias"], N, L, Hp)
+                 dh1, G["predictor.1.weight"], G["predictor.1.bias"], N, L, Hp, 1 if st["training"] else 0)
             call("csm_linear_wgrad", dh1, B["dec_bf16"][N * Sd:], G["predictor.0.weight"], N * Sd, Hp, Dd, nsm)
             call("csm_colsum_bf16", dh1, G["predictor.0.bias"], N * Sd, Hp, 0, nsm)
             call("csm_linear_dgrad", dh1, w16["predictor.0.weight"], dy2[N * Sd:], None, N * Sd, Hp, Dd, EPI_F32)

@@ -258,8 +258,11 @@ class MAE_ViT_MsLd(MAE_ViT_Baseline):
         assert imgs_crop.shape == imgs.shape, "both scales must have the model's input size"
         return self._run([imgs, imgs_crop], mask_ratio, mask_seed, noise)
 
-    def forward(self, imgs, *args, mask_ratio=None, contr_bs=None, mask_seed=None, return_embeds=False,
-                consistent_mask=False, noise=None, **kwargs):
+    # positional order after the image tensor(s), as in the reference class of the same name
+    # (MAE_ViT_MsLd.py:37-44 / MAE_ViT_MsLdCd.py:26-33; MAE_ViT_MsLdCeCd.py:27-35 inserts contr_bs)
+    _positional = ("mask_ratio", "mask_seed", "return_embeds", "consistent_mask")
+
+    def forward(self, imgs, *args, noise=None, **kwargs):
         """forward(imgs, mask_ratio=0.75, ...)            single input, scale 2 = in-model random crop
         forward(imgs_scale1, imgs_scale2, mask_ratio)  paired form (BASELINE.json north_star)
         -> (loss, pred_orig, mask_orig) or the 5-tuple with ((enc1, enc2), (dec1, dec2))."""
@@ -267,19 +270,22 @@ class MAE_ViT_MsLd(MAE_ViT_Baseline):
         args = list(args)
         if args and isinstance(args[0], torch.Tensor) and args[0].dim() == 4:
             imgs2 = args.pop(0)
-        if args and mask_ratio is None:
-            mask_ratio = args.pop(0)
-        if args and contr_bs is None:
-            contr_bs = args.pop(0)
-        if args and mask_seed is None:
-            mask_seed = args.pop(0)
-        if mask_ratio is None:
-            mask_ratio = 0.75
-        if contr_bs:
-            assert contr_bs == imgs.shape[0], "contr_bs must equal the batch size (NT-Xent masks are per batch)"
-        loss, out = self._forward_two_scale(imgs, imgs2, mask_ratio, mask_seed, consistent_mask, noise)
+        if len(args) > len(self._positional):
+            raise TypeError(f"forward() takes at most {len(self._positional)} positional arguments after the images")
+        opts = dict(mask_ratio=0.75, contr_bs=None, mask_seed=None, return_embeds=False, consistent_mask=False)
+        for name, value in zip(self._positional, args):
+            if name in kwargs:
+                raise TypeError(f"forward() got multiple values for argument {name!r}")
+            opts[name] = value
+        for name in list(kwargs):
+            if name in opts:
+                opts[name] = kwargs.pop(name)          # anything else is swallowed, as the reference's **kwargs does
+        mask_ratio = 0.75 if opts["mask_ratio"] is None else opts["mask_ratio"]
+        if opts["contr_bs"]:
+            assert opts["contr_bs"] == imgs.shape[0], "contr_bs must equal the batch size (NT-Xent masks are per batch)"
+        loss, out = self._forward_two_scale(imgs, imgs2, mask_ratio, opts["mask_seed"], opts["consistent_mask"], noise)
         pred, mask = out["pred"][0].clone(), out["mask"][0].clone()
-        if not return_embeds:
+        if not opts["return_embeds"]:
             return loss, pred, mask
         return (loss, pred, mask, tuple(e.clone() for e in out["enc_emb"]), tuple(e.clone() for e in out["dec_emb"]))
 
@@ -310,6 +316,7 @@ class MAE_ViT_MsLdCeCd(MAE_ViT_MsLd):
 
     _use_cd = True
     _use_ce = True
+    _positional = ("mask_ratio", "contr_bs", "mask_seed", "return_embeds", "consistent_mask")
 
     def __init__(self, loss_cd=None, predictor_hidden_size=2048, **kwargs):
         super().__init__(**kwargs)

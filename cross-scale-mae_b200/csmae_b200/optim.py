@@ -7,6 +7,13 @@ itself is ONE kernel over all parameters (`csm_adamw_multi`) that also rewrites 
 weights the engine's tcgen05 kernels read, so the separate fp32 -> bf16 cast pass before the next forward
 disappears.  `grad_norm()` is the global L2 norm the reference computes with one `torch.norm` per parameter
 (util/misc.py:338-355); when the gradients are views of the engine's flat buffer it is one reduction kernel.
+
+`NativeScalerWithGradNormCount` is the drop-in for the reference's loss scaler of the same name
+(util/misc.py:299-335): same call signature, same state_dict (GradScaler's keys), but with a FusedAdamW the whole
+unscale_ / inf check / grad norm / clip / step / scale update chain is three launches with NO host synchronisation:
+one pass over the flat gradient buffer (`csm_grad_stats_f32`: norm of the unscaled gradients + found_inf), one scalar
+kernel (`csm_amp_update`) and `csm_adamw_multi`, which multiplies the gradients by 1 / scale (x clip coefficient) on
+the fly and skips the update when an inf / nan was found.
 """
 import math
 
@@ -75,7 +82,9 @@ class FusedAdamW(torch.optim.Optimizer):
 
     # ------------------------------------------------------------------ step
     @torch.no_grad()
-    def step(self, closure=None):
+    def step(self, closure=None, ctl=None):
+        """ctl (optional, device f32[2]): {gradient multiplier, found_inf} read by the kernel from device memory
+        (NativeScalerWithGradNormCount below); without it this is torch.optim.AdamW.step."""
         loss = None
         if closure is not None:
             with torch.enable_grad():
@@ -126,7 +135,8 @@ class FusedAdamW(torch.optim.Optimizer):
             start = stop
         cache["host_np"][:] = tab
         cache["dev"].copy_(cache["host"], non_blocking=True)
-        nat.call("csm_adamw_multi", cache["dev"], cache["chunks"], cache["nchunks"], nat.sm_count(dev))
+        nat.call("csm_adamw_multi", cache["dev"], cache["chunks"], cache["nchunks"], ctl, nat.sm_count(dev))
+        self._last_stepped = [st for _, _, st in items]
         eng = self._engine
         if eng is not None:
             if cache["shadowed"]:
@@ -137,27 +147,165 @@ class FusedAdamW(torch.optim.Optimizer):
                 eng._w16_versions = None        # shadows did not exist yet: the next forward builds them
         return loss
 
+    def rollback_step(self):
+        """Undo the step COUNT of the last step() (the kernel skipped the update because found_inf was set):
+        torch.optim.AdamW under GradScaler never sees a skipped step, so its bias corrections do not advance."""
+        for st in getattr(self, "_last_stepped", []):
+            st["step"] -= 1
+        self._last_stepped = []
+
     # ------------------------------------------------------------------ gradient norm
-    @torch.no_grad()
-    def grad_norm(self):
-        """Global L2 norm of all gradients (util/misc.py:338-355) as a 0-d device tensor."""
+    def _grad_spans(self):
+        """The gradients as the fewest 16-byte-aligned flat fp32 spans: the engine hands out consecutive views of
+        ONE flat buffer (padding between views is zero), which is then a single span."""
         grads = [p.grad for g in self.param_groups for p in g["params"] if p.grad is not None]
         if not grads:
-            return torch.zeros(())
-        dev = grads[0].device
-        out = torch.zeros(1, dtype=torch.float32, device=dev)
-        # gradients handed out by the engine are consecutive views of one flat buffer: one pass over it
+            return [], []
         base = min(grads, key=lambda t: t.data_ptr())
         span_end = max(t.data_ptr() + t.numel() * 4 for t in grads)
         span = (span_end - base.data_ptr()) // 4
         same_storage = all(t.untyped_storage().data_ptr() == base.untyped_storage().data_ptr() for t in grads)
-        if same_storage and span <= sum((t.numel() + 3) // 4 * 4 for t in grads) and base.data_ptr() % 16 == 0:
-            flat = torch.as_strided(base, (span,), (1,))        # padding between views is zero
-            nat.call("csm_sumsq_f32", flat, span, out, nat.sm_count(dev))
-        else:
-            for t in grads:
-                if t.data_ptr() % 16 == 0 and t.is_contiguous():
-                    nat.call("csm_sumsq_f32", t, t.numel(), out, nat.sm_count(dev))
-                else:
-                    out += t.float().pow(2).sum()
+        if (same_storage and all(t.dtype == torch.float32 for t in grads)
+                and span <= sum((t.numel() + 3) // 4 * 4 for t in grads) and base.data_ptr() % 16 == 0):
+            return [torch.as_strided(base, (span,), (1,))], []
+        ok = [t for t in grads if t.dtype == torch.float32 and t.data_ptr() % 16 == 0 and t.is_contiguous()]
+        return [t.view(-1) for t in ok], [t for t in grads if not any(t is o for o in ok)]
+
+    @torch.no_grad()
+    def grad_norm(self):
+        """Global L2 norm of all gradients (util/misc.py:338-355) as a 0-d device tensor."""
+        spans, odd = self._grad_spans()
+        if not spans and not odd:
+            return torch.zeros(())
+        dev = (spans + odd)[0].device
+        out = torch.zeros(1, dtype=torch.float32, device=dev)
+        for t in spans:
+            nat.call("csm_sumsq_f32", t, t.numel(), out, nat.sm_count(dev))
+        for t in odd:
+            out += t.float().pow(2).sum()
         return out.sqrt().reshape(())
+
+
+class NativeScalerWithGradNormCount:
+    """Drop-in for util/misc.py:299-335 (same name, call signature, `state_dict_key` and state_dict keys).
+
+    With a FusedAdamW optimizer nothing between `backward()` and the end of the step touches the host: the gradients
+    stay scaled in memory (the reference's `unscale_` rewrites them in place; here the optimizer kernel applies
+    1 / scale x clip on the fly, so `p.grad` read AFTER the call still carries the loss scale), the inf check
+    and the skip decision live in device memory, and the scale update is `csm_amp_update`.  The returned norm is a
+    0-d device tensor of the UNSCALED gradient norm, as the reference returns.  The step count of a skipped update
+    is rolled back at the next call (the found_inf flag is copied to pinned memory asynchronously and looked at one
+    step late), so bias corrections match torch.optim.AdamW under GradScaler exactly.
+    With any other optimizer the stock torch GradScaler sequence of the reference runs unchanged."""
+    state_dict_key = "amp_scaler"
+
+    def __init__(self, init_scale=2.0 ** 16, growth_factor=2.0, backoff_factor=0.5, growth_interval=2000):
+        self._init = (float(init_scale), float(growth_factor), float(backoff_factor), int(growth_interval))
+        self._growth_factor, self._backoff_factor, self._growth_interval = self._init[1:]
+        self._state = None          # device f32[4]: scale, growth_tracker, 1 / scale, unused
+        self._pending = None        # state to upload at first use (load_state_dict before any step)
+        self._work = None           # device f32[8]: stats[2], ctl[2], norm[1]
+        self._host_flag = None
+        self._flag_event = None
+        self._flag_opt = None
+        self._stock = None          # torch GradScaler for optimizers other than FusedAdamW
+
+    # ---- state
+    def _ensure(self, dev):
+        if self._state is None or self._state.device != dev:
+            scale, tracker = self._pending if self._pending is not None else (self._init[0], 0)
+            self._state = torch.tensor([scale, float(tracker), 1.0 / scale, 0.0], dtype=torch.float32).to(dev)
+            self._work = torch.zeros(8, dtype=torch.float32, device=dev)
+            self._host_flag = torch.zeros(2, dtype=torch.float32).pin_memory()
+            self._pending = None
+        return self._state
+
+    def get_scale(self):
+        if self._stock is not None:
+            return self._stock.get_scale()
+        if self._state is None:
+            return (self._pending or (self._init[0],))[0]
+        return float(self._state[0].item())
+
+    def state_dict(self):
+        if self._stock is not None:
+            return self._stock.state_dict()
+        if self._state is None:
+            scale, tracker = self._pending if self._pending is not None else (self._init[0], 0)
+        else:
+            scale, tracker = (float(x) for x in self._state[:2].tolist())
+        return {"scale": scale, "growth_factor": self._growth_factor, "backoff_factor": self._backoff_factor,
+                "growth_interval": self._growth_interval, "_growth_tracker": int(tracker)}
+
+    def load_state_dict(self, state_dict):
+        if self._stock is not None:
+            self._stock.load_state_dict(state_dict)
+            return
+        self._growth_factor = float(state_dict["growth_factor"])
+        self._backoff_factor = float(state_dict["backoff_factor"])
+        self._growth_interval = int(state_dict["growth_interval"])
+        self._pending = (float(state_dict["scale"]), int(state_dict["_growth_tracker"]))
+        self._state = None
+
+    # ---- the step
+    def _reconcile(self):
+        """Looks at the previous step's found_inf flag (already on the host in any loop that reads the loss) and takes
+        back the step count of a skipped update."""
+        if self._flag_event is not None:
+            self._flag_event.synchronize()
+            if self._host_flag[1].item() != 0.0 and self._flag_opt is not None:
+                self._flag_opt.rollback_step()
+            self._flag_event = None
+            self._flag_opt = None
+
+    def __call__(self, loss, optimizer, clip_grad=None, parameters=None, create_graph=False, update_grad=True):
+        if not isinstance(optimizer, FusedAdamW):
+            if self._stock is None:
+                self._stock = torch.amp.GradScaler("cuda", init_scale=self.get_scale() if self._state is not None or
+                                                   self._pending is not None else self._init[0],
+                                                   growth_factor=self._growth_factor,
+                                                   backoff_factor=self._backoff_factor,
+                                                   growth_interval=self._growth_interval)
+            sc = self._stock
+            sc.scale(loss).backward(create_graph=create_graph)
+            if not update_grad:
+                return None
+            sc.unscale_(optimizer)
+            if clip_grad is not None:
+                assert parameters is not None
+                norm = torch.nn.utils.clip_grad_norm_(parameters, clip_grad)
+            else:
+                ps = [p for p in ([parameters] if isinstance(parameters, torch.Tensor) else parameters)
+                      if p.grad is not None]
+                norm = (torch.norm(torch.stack([torch.norm(p.grad.detach(), 2.0) for p in ps]), 2.0)
+                        if ps else torch.tensor(0.0))
+            sc.step(optimizer)
+            sc.update()
+            return norm
+        state = self._ensure(loss.device)
+        (loss * state[0]).backward(create_graph=create_graph)
+        if not update_grad:
+            return None
+        if clip_grad is not None:
+            assert parameters is not None
+        self._reconcile()
+        dev = loss.device
+        work = self._work
+        stats, ctl, norm = work[0:2], work[2:4], work[4:5]
+        with torch.no_grad():
+            stats.zero_()
+            spans, odd = optimizer._grad_spans()
+            for t in spans:
+                nat.call("csm_grad_stats_f32", t, t.numel(), state[2:3], stats, nat.sm_count(dev))
+            for t in odd:
+                u = t.float() * state[2]
+                stats[0] += u.pow(2).sum()
+                stats[1] = torch.maximum(stats[1], (~torch.isfinite(u)).any().float())
+            nat.call("csm_amp_update", stats, state, ctl, norm, float(clip_grad) if clip_grad is not None else 0.0,
+                     self._growth_factor, self._backoff_factor, self._growth_interval)
+            optimizer.step(ctl=ctl)
+            self._host_flag.copy_(ctl, non_blocking=True)
+            self._flag_event = torch.cuda.Event()
+            self._flag_event.record()
+            self._flag_opt = optimizer
+        return norm.clone().reshape(())

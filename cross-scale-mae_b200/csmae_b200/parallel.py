@@ -7,12 +7,12 @@ main_pretrain.py:417-421) -- tools/ddp_smoke.py exercises that.  But the hand-wr
 gradients to autograd at once, so torch's bucketed all-reduce cannot overlap it and pays ~260 bucket copies in
 and out.  `DistributedDataParallel` below is the drop-in for that wrapper (same constructor call, `.module`,
 forward passthrough) that lets the engine do the exchange itself: the flat fp32 gradient buffer is all-reduced
-in 1 + enc_groups segments as the backward chain completes them, on NCCL's stream, overlapping the rest of
+in 1 + enc_groups segments (one per encoder layer by default) as the backward chain completes them, on NCCL's stream, overlapping the rest of
 the backward; no per-parameter hooks, no bucket copies.
 
 Semantics kept from the reference setup: rank 0's parameters and buffers are broadcast at construction (C2),
 BatchNorm running statistics are re-broadcast from rank 0 before every training forward (torch DDP's default
-`broadcast_buffers=True`, C4), BatchNorm batch statistics and NT-Xent negatives stay per rank, each rank's loss
+`broadcast_buffers=True`, C4; here as ONE collective over a flat buffer the BatchNorm buffers are views of), BatchNorm batch statistics and NT-Xent negatives stay per rank, each rank's loss
 is its own (the engine's logger all-reduces it separately, C5).
 """
 import torch
@@ -22,7 +22,7 @@ import torch.nn as nn
 
 class DistributedDataParallel(nn.Module):
     def __init__(self, module, device_ids=None, output_device=None, find_unused_parameters=True,
-                 broadcast_buffers=True, process_group=None, enc_groups=3, **_unused):
+                 broadcast_buffers=True, process_group=None, enc_groups=None, **_unused):
         super().__init__()
         if not dist.is_available() or not dist.is_initialized():
             raise RuntimeError("csmae_b200.DistributedDataParallel needs an initialised torch.distributed process group")
@@ -33,13 +33,47 @@ class DistributedDataParallel(nn.Module):
         with torch.no_grad():
             for t in list(module.parameters()) + list(module.buffers()):
                 dist.broadcast(t.data, 0, group=process_group)
+        # one all-reduce segment per encoder layer (at most 12): the exposed tail after the backward is then the
+        # embeddings + the lowest encoder layer(s) (~30 MB for ViT-B) instead of a third of the encoder
+        if enc_groups is None:
+            enc_groups = max(1, min(12, len(getattr(module, "encoder", []))))
         module._engine.enable_grad_sync(process_group, self.world_size, enc_groups)
+        self._flat_buffers = None
+        self._flat_views = None
+
+    def _coalesced_buffers(self):
+        """The module's buffers (BatchNorm running_mean / running_var / num_batches_tracked) re-homed as views of ONE
+        flat byte buffer, so that the per-forward rank-0 broadcast (torch DDP's broadcast_buffers=True, C4) is a
+        single collective instead of one per buffer.  Rebuilt if the module's buffers were moved or replaced."""
+        bufs = [b for b in self.module.buffers() if b.numel() > 0]
+        if not bufs:
+            return None
+        if self._flat_buffers is not None and len(bufs) == len(self._flat_views) and all(
+                b.data_ptr() == v.data_ptr() for b, v in zip(bufs, self._flat_views)):
+            return self._flat_buffers
+        dev = bufs[0].device
+        offs, total = [], 0
+        for b in bufs:
+            total = (total + 15) // 16 * 16
+            offs.append(total)
+            total += b.numel() * b.element_size()
+        flat = torch.zeros(total, dtype=torch.uint8, device=dev)
+        views = []
+        with torch.no_grad():
+            for b, o in zip(bufs, offs):
+                v = flat[o:o + b.numel() * b.element_size()].view(b.dtype).view(b.shape)
+                v.copy_(b)
+                b.data = v
+                views.append(v)
+        self._flat_buffers, self._flat_views = flat, views
+        return flat
 
     def forward(self, *args, **kwargs):
         if self.broadcast_buffers and self.module.training and self.world_size > 1:
             with torch.no_grad():
-                for b in self.module.buffers():
-                    dist.broadcast(b, 0, group=self.process_group)
+                flat = self._coalesced_buffers()
+                if flat is not None:
+                    dist.broadcast(flat, 0, group=self.process_group)
         return self.module(*args, **kwargs)
 
     def no_sync(self):

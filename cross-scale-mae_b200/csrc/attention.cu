@@ -1,3 +1,6 @@
+// LEGACY mma.sync path, kept only as the A/B baseline of tools/attn_tc_check.py (csm_attention_*_legacy; not
+// declared in include/csmae_b200.h and not called by the product).  The product kernels are in attention_tc.cu.
+//
 // Fused multi-head self-attention forward / backward for the timm Block attention of the MAE
 // encoder (S = keep+1, d = 64) and decoder (S = L+1, d = 32): softmax((q k^T) * d^-1/2) v, no mask,
 // no dropout (timm 0.4.12 Attention as restated in oracle/timm_shim.py; call sites
@@ -886,8 +889,8 @@ int attn_bwd_launch(const void* qkv, const void* o, const void* d_out, const flo
 
 }  // namespace
 
-extern "C" int csm_attention_fwd(const void* qkv_bf16, void* out_bf16, float* lse, int B, int S, int H, int head_dim,
-                                 cudaStream_t stream) {
+extern "C" int csm_attention_fwd_legacy(const void* qkv_bf16, void* out_bf16, float* lse, int B, int S, int H,
+                                        int head_dim, cudaStream_t stream) {
   CSM_CHECK_ARG(B > 0 && S > 0 && H > 0, "csm_attention_fwd: bad sizes B=%d S=%d H=%d", B, S, H);
   if (head_dim == 32) return attn_fwd_launch<32>(qkv_bf16, out_bf16, lse, B, S, H, stream);
   if (head_dim == 64) return attn_fwd_launch<64>(qkv_bf16, out_bf16, lse, B, S, H, stream);
@@ -895,9 +898,9 @@ extern "C" int csm_attention_fwd(const void* qkv_bf16, void* out_bf16, float* ls
   return CSM_ERR_ARG;
 }
 
-extern "C" int csm_attention_bwd(const void* qkv_bf16, const void* out_bf16, const void* d_out_bf16, const float* lse,
-                                 float* delta_scratch, void* dqkv_bf16, float* dbias, int B, int S, int H,
-                                 int head_dim, cudaStream_t stream) {
+extern "C" int csm_attention_bwd_legacy(const void* qkv_bf16, const void* out_bf16, const void* d_out_bf16,
+                                        const float* lse, float* delta_scratch, void* dqkv_bf16, float* dbias, int B,
+                                        int S, int H, int head_dim, cudaStream_t stream) {
   CSM_CHECK_ARG(B > 0 && S > 0 && H > 0, "csm_attention_bwd: bad sizes B=%d S=%d H=%d", B, S, H);
   if (head_dim == 32)
     return attn_bwd_launch<32>(qkv_bf16, out_bf16, d_out_bf16, lse, delta_scratch, dqkv_bf16, dbias, B, S, H, stream);

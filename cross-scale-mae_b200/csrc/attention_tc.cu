@@ -27,7 +27,7 @@
 // c = d^-1/2 * log2(e): p = exp2(s*c - L2).
 #include "common.cuh"
 
-#include <cstdio>
+#include <algorithm>
 
 namespace {
 using namespace csm;
@@ -35,7 +35,6 @@ using namespace csm;
 constexpr int AT_SM_WARPS = 8;
 constexpr int AT_THREADS = 32 * (4 + AT_SM_WARPS);   // 384: warp group 0 = {TMA, MMA, 2 idle}, groups 1-2 = softmax
 constexpr int AT_QBYTES = 128 * 128;                 // one Q tile: 128 rows x 64 bf16
-constexpr int AT_MAXCH = 13;                         // 8-column chunks per softmax thread: BN / 2 / 8, BN <= 208
 constexpr int AT_XCH_BYTES = 2 * 2 * 2 * 128 * 4;    // {max, sum} x parity x half x row
 
 struct FwdParams {
@@ -48,15 +47,12 @@ struct FwdParams {
   float* lse;
 };
 
+// bounded wait: a protocol error traps (the launch fails with an error) instead of hanging the device
 __device__ __forceinline__ void mbar_wait_wd(uint64_t* bar, uint32_t parity) {
-  // bounded wait: a protocol error traps (the launch fails) instead of hanging the device
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000ll) {
-      printf("csmae_b200 attention: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
-      __trap();
-    }
+    if (clock64() - t0 > 4000000000ll) __trap();
   }
 }
 
@@ -84,7 +80,6 @@ __device__ __forceinline__ void sts_v4(uint32_t addr, uint4 v) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
                : "memory");
 }
-__device__ __forceinline__ void softmax_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 template <int N>
 struct IC {
@@ -94,22 +89,49 @@ struct IC {
 // ---------------------------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------------------------
-template <int DH, int VN>
+__device__ __forceinline__ void tmem_st_32x8(uint32_t taddr, const uint32_t* r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]),
+               "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// D[tmem] (+)= A[tmem, bf16 pairs packed along K] * B[smem desc]
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// DH: head dim (32: two heads per 64-column group, 64: one).  NG0 / NG1: 16-key groups of the two softmax threads of a
+// query row; the key block is BN = 16 * (NG0 + NG1) keys (208 = 96 + 112, so that the 197 keys of the decoder split
+// 96 / 101, or 128 = 64 + 64).  PTMEM: the probabilities go back to TMEM (over the score columns they came from) and
+// feed the P.V product as its TMEM A operand; otherwise they go through a 128-byte-swizzled shared-memory tile.
+template <int DH, int NG0, int NG1, bool PTMEM>
 __global__ void __launch_bounds__(AT_THREADS, 1)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv,
                    const FwdParams p) {
   constexpr int NH = 64 / DH;          // heads per 64-column group
   constexpr int KS = DH / 16;          // 16-wide k-steps of one head in the Q / K rows
   constexpr int OC = DH / 2;           // output columns owned by one softmax thread
+  constexpr int NG = NG0 > NG1 ? NG0 : NG1;
+  constexpr int BN = 16 * (NG0 + NG1); // keys per block
+  constexpr int BNH0 = 16 * NG0;       // keys of the first half
+  constexpr int KV_BYTES = BN * 128;   // one K (or V) block
+  constexpr int PSLABS = PTMEM ? 0 : (BN + 63) / 64;
+  constexpr uint32_t COL_O = 2 * BN;   // O of key half h at COL_O + h * DH
+  static_assert(2 * BN + 2 * DH <= 512, "TMEM budget");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const int BN = p.BN;
-  const int kv_bytes = BN * 128;                       // one K (or V) block
-  const int pslabs = (BN + 63) >> 6;
   uint8_t* sQ = smem;                                  // [2][16 KB]
   uint8_t* sKV = smem + 2 * AT_QBYTES;                 // [2][K | V]
-  uint8_t* sP = sKV + 4 * kv_bytes;                    // [pslabs][128 rows][128 B]
-  float* xch = reinterpret_cast<float*>(sP + pslabs * 16384);
+  uint8_t* sP = sKV + 4 * KV_BYTES;                    // [PSLABS][128 rows][128 B]
+  float* xch = reinterpret_cast<float*>(sP + PSLABS * 16384);   // {max, sum} x parity x half x row
   uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(xch) + AT_XCH_BYTES);
   uint64_t* q_full = bars;            // [2]
   uint64_t* q_empty = bars + 2;       // [2]
@@ -148,10 +170,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
   pdl_wait();
   pdl_trigger();
 
-  // register budget: the softmax threads hold half a score row (up to 104 values) in registers
-  // Iteration order inside a work item: heads of the group outermost, key blocks innermost, so one set of online-
-  // softmax state is live at a time.  With a single key block both heads share one K/V load; with several blocks the
-  // blocks are re-fetched per head (L2 hits).
+  // Iteration order inside a work item: heads of the group outermost, key blocks innermost.  With a single key block
+  // both heads share one K/V load; with several blocks the blocks are re-fetched per head (L2 hits).
   const bool shared_kv = (p.nb == 1);
   if (warp < 4) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
@@ -187,9 +207,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
             const int j = shared_kv ? 0 : l % p.nb;
             const uint32_t ks = kvc & 1;
             mbar_wait_wd(&kv_empty[ks], ((kvc >> 1) & 1) ^ 1);
-            mbar_expect_tx(&kv_full[ks], 2u * kv_bytes);
-            uint8_t* k = sKV + ks * 2 * kv_bytes;
-            uint8_t* v = k + kv_bytes;
+            mbar_expect_tx(&kv_full[ks], 2u * KV_BYTES);
+            uint8_t* k = sKV + ks * 2 * KV_BYTES;
+            uint8_t* v = k + KV_BYTES;
             tma_load_2d(k, &tmap_kv, &kv_full[ks], p.Dm + hg * 64, row_k0 + j * BN);
             tma_load_2d(v, &tmap_kv, &kv_full[ks], 2 * p.Dm + hg * 64, row_k0 + j * BN);
             if (p.pack) {
@@ -202,10 +222,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
     } else if (warp == 1) {
       // ------------------------------ MMA issuer (one thread) ------------------------------
       if (lane == 0) {
-        const uint32_t idesc_s = umma_idesc_bf16(128, BN, 0, 0);
-        const uint32_t idesc_o = umma_idesc_bf16(128, VN, 0, 1);
+        constexpr uint32_t idesc_s = umma_idesc_bf16(128, BN, 0, 0);
+        constexpr uint32_t idesc_o = umma_idesc_bf16(128, DH, 0, 1);
         const uint32_t p_addr = smem_u32(sP);
-        const int ksteps = BN >> 4;
         uint32_t it = 0, ic = 0, kvc = 0;
         // the P.V product of an iteration is issued after the NEXT S = Q K^T, so the softmax warps always find their
         // next score tile ready
@@ -216,13 +235,19 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
         auto issue_pv = [&]() {
           mbar_wait_wd(p_full, pv_it & 1);
           tc_fence_after();
-          const uint32_t v_addr =
-              smem_u32(sKV + pv_ks * 2 * kv_bytes + kv_bytes) + ((DH == 32 && VN == 32) ? pv_hh * 64 : 0);
-          const uint32_t tmem_o = tmem_base + 2 * BN;
-          for (int k = 0; k < ksteps; ++k) {
-            const uint64_t da = umma_smem_desc_sw128(p_addr + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024);
+          const uint32_t v_addr = smem_u32(sKV + pv_ks * 2 * KV_BYTES + KV_BYTES) + (DH == 32 ? pv_hh * 64 : 0);
+          const uint32_t tmem_p = tmem_base + (pv_it & 1) * BN;
+#pragma unroll
+          for (int k = 0; k < NG0 + NG1; ++k) {        // each key half accumulates into its own O
+            const int hf = k >= NG0 ? 1 : 0, kh = k - hf * NG0;
             const uint64_t db = umma_smem_desc_sw128(v_addr + k * 2048, 8192, 1024);
-            umma_f16(tmem_o, da, db, idesc_o, k > 0 ? 1u : 0u);
+            const uint32_t tmem_o = tmem_base + COL_O + hf * DH;
+            if (PTMEM) {
+              umma_f16_ts(tmem_o, tmem_p + hf * BNH0 + kh * 8, db, idesc_o, kh > 0 ? 1u : 0u);
+            } else {
+              const uint64_t da = umma_smem_desc_sw128(p_addr + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024);
+              umma_f16(tmem_o, da, db, idesc_o, kh > 0 ? 1u : 0u);
+            }
           }
           umma_commit(o_full);
           if (pv_last_kv) umma_commit(&kv_empty[pv_ks]);
@@ -243,7 +268,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
                 ++kvc;
               }
               tc_fence_after();
-              const uint32_t k_addr = smem_u32(sKV + ks * 2 * kv_bytes);
+              const uint32_t k_addr = smem_u32(sKV + ks * 2 * KV_BYTES);
               const uint32_t tmem_s = tmem_base + (it & 1) * BN;
 #pragma unroll
               for (int kk = 0; kk < KS; ++kk) {
@@ -266,57 +291,73 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
   } else {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
     // ------------------------------ softmax warps ------------------------------
-    const int sw = warp - 4;
-    const int half = sw >> 2;                 // which half of the key block
+    const int half = (warp - 4) >> 2;         // which half of the key block
     const int quarter = warp & 3;             // TMEM lane quarter this warp may access
     const int row = quarter * 32 + lane;
     const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
-    const int BNh = BN >> 1;
-    const int nch = BNh >> 3;
-    const int colbase = half * BNh;
+    const int colbase = half * BNH0;
+    const int bnh = half ? 16 * NG1 : 16 * NG0;   // keys of this thread's half
     const float c = p.c;
-    float* xmax = xch;                        // [parity][half][row]
-    float* xsum = xch + 512;
+    float* xm = xch;                          // [parity][half][row]
+    float* xl = xch + 512;
     const uint32_t p_row = smem_u32(sP) + row * 128;
     const uint32_t sw7 = static_cast<uint32_t>(row & 7);
 
-    float m_run = -INFINITY, l_part = 0.f, alpha_pend = 0.f;
+    // online-softmax state of the head in flight; owned by drain()
+    float m_run = -INFINITY, l_run = 0.f;
     float o_acc[OC];
 #pragma unroll
     for (int i = 0; i < OC; ++i) o_acc[i] = 0.f;
     uint32_t it = 0;
-    bool have_prev = false, prev_last = false, prev_valid = false;
+    uint32_t have_prev;      // opaque to the compiler: keeps it from peeling the first iteration of the item loops
+    asm volatile("mov.u32 %0, 0;" : "=r"(have_prev));
+    bool prev_first = false, prev_last = false, prev_valid = false;
     uint32_t prev_it = 0;
-    int prev_hh = 0;
     __nv_bfloat16* prev_out = nullptr;
     float* prev_lse = nullptr;
 
-    // read back O of iteration prev_it (its P.V product is complete: the P tile may be rewritten afterwards)
+    // Fold the P.V result of iteration prev_it into the running output.  The two key halves were exponentiated
+    // against their OWN row maximum (no exchange before the exp): their partial outputs O_h and partial sums l_h are
+    // combined here with the factors exp2((m_h - m) * c).
     auto drain = [&]() {
       mbar_wait_wd(o_full, prev_it & 1);
       tc_fence_after();
-      uint32_t o[OC];
-      const uint32_t oaddr = tmem_base + lane_off + 2 * BN + ((DH == 32 && VN == 64) ? prev_hh * 32 : 0) + half * OC;
-      tmem_ld_32x16(oaddr, o);
-      if (OC == 32) tmem_ld_32x16(oaddr + 16, o + (OC == 32 ? 16 : 0));
+      uint32_t o0[OC], o1[OC];
+      const uint32_t oaddr = tmem_base + lane_off + COL_O + half * OC;
+      tmem_ld_32x16(oaddr, o0);
+      tmem_ld_32x16(oaddr + DH, o1);
+      if (OC == 32) {
+        tmem_ld_32x16(oaddr + 16, o0 + (OC == 32 ? 16 : 0));
+        tmem_ld_32x16(oaddr + DH + 16, o1 + (OC == 32 ? 16 : 0));
+      }
+      const uint32_t xo = (prev_it & 1) * 256 + row;
+      const float m0 = xm[xo], m1 = xm[xo + 128], l0 = xl[xo], l1 = xl[xo + 128];
+      if (prev_first) {
+        m_run = -INFINITY;
+        l_run = 0.f;
+#pragma unroll
+        for (int i = 0; i < OC; ++i) o_acc[i] = 0.f;
+      }
+      const float m_new = fmaxf(m_run, fmaxf(m0, m1));
+      const float a = ex2f((m_run - m_new) * c), b0 = ex2f((m0 - m_new) * c), b1 = ex2f((m1 - m_new) * c);
+      l_run = fmaf(l_run, a, fmaf(l0, b0, l1 * b1));
+      m_run = m_new;
       tmem_ld_wait();
 #pragma unroll
-      for (int i = 0; i < OC; ++i) o_acc[i] = fmaf(o_acc[i], alpha_pend, __uint_as_float(o[i]));
-      if (prev_last) {
-        const float l_tot = l_part + xsum[(prev_it & 1) * 256 + (half ^ 1) * 128 + row];
-        if (prev_valid) {
-          const float inv = 1.0f / l_tot;
+      for (int i = 0; i < OC; ++i)
+        o_acc[i] = fmaf(o_acc[i], a, fmaf(__uint_as_float(o0[i]), b0, __uint_as_float(o1[i]) * b1));
+      if (prev_last && prev_valid) {
+        const float inv = 1.0f / l_run;
 #pragma unroll
-          for (int g = 0; g < OC / 8; ++g) {
-            uint4 pk;
-            pk.x = pack_bf16x2(o_acc[g * 8 + 0] * inv, o_acc[g * 8 + 1] * inv);
-            pk.y = pack_bf16x2(o_acc[g * 8 + 2] * inv, o_acc[g * 8 + 3] * inv);
-            pk.z = pack_bf16x2(o_acc[g * 8 + 4] * inv, o_acc[g * 8 + 5] * inv);
-            pk.w = pack_bf16x2(o_acc[g * 8 + 6] * inv, o_acc[g * 8 + 7] * inv);
-            *reinterpret_cast<uint4*>(prev_out + g * 8) = pk;
-          }
-          if (half == 0) *prev_lse = m_run * c + log2f(l_tot);
+        for (int g = 0; g < OC / 8; ++g) {
+          uint4 pk;
+          pk.x = pack_bf16x2(o_acc[g * 8 + 0] * inv, o_acc[g * 8 + 1] * inv);
+          pk.y = pack_bf16x2(o_acc[g * 8 + 2] * inv, o_acc[g * 8 + 3] * inv);
+          pk.z = pack_bf16x2(o_acc[g * 8 + 4] * inv, o_acc[g * 8 + 5] * inv);
+          pk.w = pack_bf16x2(o_acc[g * 8 + 6] * inv, o_acc[g * 8 + 7] * inv);
+          *reinterpret_cast<uint4*>(prev_out + g * 8) = pk;
         }
+        if (half == 0) *prev_lse = m_run * c + log2f(l_run);
       }
     };
 
@@ -335,96 +376,109 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
       }
       const int nh = min(NH, p.H - hg * NH);
       const bool row_valid = (srow < p.S) && (b < p.B);
+#pragma unroll 1
       for (int hh = 0; hh < nh; ++hh) {
         const int h = hg * NH + hh;
+#pragma unroll 1
         for (int j = 0; j < p.nb; ++j, ++it) {
-          const bool last_blk = (j == p.nb - 1);
-          const int kvalid = p.pack ? (((row >> 6) == half) ? p.S : 0) : (p.S - j * BN - colbase);
+          // valid keys of this thread's half (warp-uniform): nfull whole 16-key groups, then one partial group of
+          // rem keys (handled by its own 16 registers so that the unrolled loops carry no per-element masking), then
+          // groups that only receive zero probabilities
+          int kvalid = p.pack ? (((row >> 6) == half) ? p.S : 0) : (p.S - j * BN - colbase);
+          kvalid = max(0, min(kvalid, bnh));
+          const int nfull = kvalid >> 4;
+          const int rem = kvalid & 15;
           const uint32_t buf = it & 1;
           mbar_wait_wd(&s_full[buf], (it >> 1) & 1);
           tc_fence_after();
-          uint32_t su[AT_MAXCH * 8];
+          uint32_t su[NG * 16], tu[16];
           const uint32_t taddr = tmem_base + lane_off + buf * BN + colbase;
 #pragma unroll
-          for (int g = 0; g < AT_MAXCH; ++g)
-            if (g < nch) tmem_ld_32x8(taddr + g * 8, su + g * 8);
+          for (int g = 0; g < NG; ++g)
+            if (g < nfull) tmem_ld_32x16(taddr + g * 16, su + g * 16);
+          if (rem) tmem_ld_32x16(taddr + nfull * 16, tu);
           tmem_ld_wait();
-          float pm = -INFINITY;
-          if (kvalid >= BNh) {
+          float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+          if (rem) {
 #pragma unroll
-            for (int g = 0; g < AT_MAXCH; ++g) {
-              if (g < nch) {
-#pragma unroll
-                for (int e = 0; e < 8; ++e) pm = fmaxf(pm, __uint_as_float(su[g * 8 + e]));
-              }
+            for (int e = 0; e < 16; ++e) {
+              if (e >= rem) tu[e] = 0xff800000u;                   // -inf: p = 0
+              mx[e & 3] = fmaxf(mx[e & 3], __uint_as_float(tu[e]));
             }
+          }
+#pragma unroll
+          for (int g = 0; g < NG; ++g) {
+            if (g < nfull) {
+#pragma unroll
+              for (int e = 0; e < 16; ++e) mx[e & 3] = fmaxf(mx[e & 3], __uint_as_float(su[g * 16 + e]));
+            }
+          }
+          const float m_h = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+          const float mc = m_h * c;
+          if (!PTMEM && have_prev) drain();              // also: the P tile in shared memory is free again
+          float ls[4] = {0.f, 0.f, 0.f, 0.f};
+          auto store_p = [&](int g, const uint32_t* pk) {
+            if (PTMEM) {
+              tmem_st_32x8(taddr + g * 8, pk);
+            } else {
+              const uint32_t gc = static_cast<uint32_t>((colbase >> 3) + 2 * g);
+              sts_v4(p_row + (gc >> 3) * 16384 + (((gc & 7) ^ sw7) << 4), make_uint4(pk[0], pk[1], pk[2], pk[3]));
+              sts_v4(p_row + ((gc + 1) >> 3) * 16384 + ((((gc + 1) & 7) ^ sw7) << 4),
+                     make_uint4(pk[4], pk[5], pk[6], pk[7]));
+            }
+          };
+#pragma unroll
+          for (int g = 0; g < NG; ++g) {
+            uint32_t pk[8];
+            if (g < nfull) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                const float e0 = ex2f(fmaf(__uint_as_float(su[g * 16 + 2 * e]), c, -mc));
+                const float e1 = ex2f(fmaf(__uint_as_float(su[g * 16 + 2 * e + 1]), c, -mc));
+                ls[e & 3] += e0 + e1;
+                pk[e] = pack_bf16x2(e0, e1);
+              }
+              store_p(g, pk);
+            } else if (g * 16 < bnh && (g > nfull || rem == 0)) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) pk[e] = 0u;
+              store_p(g, pk);
+            }
+          }
+          if (rem) {
+            uint32_t pk[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const float e0 = ex2f(fmaf(__uint_as_float(tu[2 * e]), c, -mc));
+              const float e1 = ex2f(fmaf(__uint_as_float(tu[2 * e + 1]), c, -mc));
+              ls[e & 3] += e0 + e1;
+              pk[e] = pack_bf16x2(e0, e1);
+            }
+            store_p(nfull, pk);
+          }
+          const uint32_t xo = buf * 256 + half * 128 + row;
+          xm[xo] = m_h;
+          xl[xo] = (ls[0] + ls[1]) + (ls[2] + ls[3]);
+          if (PTMEM) {
+            if (have_prev) drain();
+            tmem_st_wait();
           } else {
-#pragma unroll
-            for (int g = 0; g < AT_MAXCH; ++g) {
-              if (g < nch) {
-#pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                  if (g * 8 + e >= kvalid) su[g * 8 + e] = 0xff800000u;   // -inf: p = 0
-                  pm = fmaxf(pm, __uint_as_float(su[g * 8 + e]));
-                }
-              }
-            }
+            fence_proxy_async();
           }
-          const uint32_t par = it & 1;
-          xmax[par * 256 + half * 128 + row] = pm;
-          softmax_bar();
-          pm = fmaxf(pm, xmax[par * 256 + (half ^ 1) * 128 + row]);
-          if (have_prev) drain();
-          if (j == 0) {
-            m_run = -INFINITY;
-            l_part = 0.f;
-#pragma unroll
-            for (int i = 0; i < OC; ++i) o_acc[i] = 0.f;
-          }
-          const float m_new = fmaxf(m_run, pm);
-          const float alpha = ex2f((m_run - m_new) * c);
-          m_run = m_new;
-          const float mc = m_new * c;
-          float lb = 0.f;
-#pragma unroll
-          for (int g = 0; g < AT_MAXCH; ++g) {
-            if (g < nch) {
-              float e[8];
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                e[i] = ex2f(fmaf(__uint_as_float(su[g * 8 + i]), c, -mc));
-                lb += e[i];
-              }
-              uint4 pk;
-              pk.x = pack_bf16x2(e[0], e[1]);
-              pk.y = pack_bf16x2(e[2], e[3]);
-              pk.z = pack_bf16x2(e[4], e[5]);
-              pk.w = pack_bf16x2(e[6], e[7]);
-              const uint32_t gc = static_cast<uint32_t>((colbase >> 3) + g);
-              sts_v4(p_row + (gc >> 3) * 16384 + (((gc & 7) ^ sw7) << 4), pk);
-            }
-          }
-          l_part = fmaf(l_part, alpha, lb);
-          alpha_pend = alpha;
-          if (last_blk) xsum[par * 256 + half * 128 + row] = l_part;
-          fence_proxy_async();
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(p_full);
-          have_prev = true;
+          have_prev = 1;
           prev_it = it;
-          prev_hh = hh;
-          prev_last = last_blk;
+          prev_first = (j == 0);
+          prev_last = (j == p.nb - 1);
           prev_valid = row_valid;
           prev_out = p.out + (static_cast<size_t>(b) * p.S + srow) * p.Dm + h * DH + half * OC;
           prev_lse = p.lse + (static_cast<size_t>(b) * p.H + h) * p.S + srow;
         }
       }
     }
-    if (have_prev) {
-      softmax_bar();
-      drain();
-    }
+    if (have_prev) drain();
   }
 
   __syncwarp();
@@ -446,42 +500,42 @@ int device_sms() {
   return sms;
 }
 
-template <int DH, int VN>
+template <int DH, int NG0, int NG1, bool PTMEM>
 int attn_fwd_tc_launch(const void* qkv, void* out, float* lse, int B, int S, int H, cudaStream_t stream) {
+  constexpr int BN = 16 * (NG0 + NG1);
   const int Dm = H * DH;
   FwdParams p{};
   p.B = B; p.S = S; p.H = H; p.Dm = Dm;
   p.HG = (Dm + 63) / 64;
   p.pack = S <= 64 ? 1 : 0;
+  p.BN = BN;
   if (p.pack) {
-    p.BN = 128; p.nb = 1; p.QT = 1;
+    p.nb = 1; p.QT = 1;
     p.items = ((B + 1) / 2) * p.HG;
   } else {
-    const int bn_max = DH == 64 ? 192 : 208;
-    p.nb = (S + bn_max - 1) / bn_max;
-    p.BN = (((S + p.nb - 1) / p.nb) + 15) & ~15;
+    p.nb = (S + BN - 1) / BN;
     p.QT = (S + 127) / 128;
     p.items = B * p.HG * p.QT;
   }
   p.c = 1.4426950408889634f / sqrtf(static_cast<float>(DH));
   p.out = reinterpret_cast<__nv_bfloat16*>(out);
   p.lse = lse;
-  const int pslabs = (p.BN + 63) / 64;
-  const size_t smem = 1024 + 2 * AT_QBYTES + 4 * static_cast<size_t>(p.BN) * 128 + pslabs * 16384 + AT_XCH_BYTES + 128;
-  auto kern = attn_fwd_tc_kernel<DH, VN>;
-  static size_t configured = 0;
-  if (smem > configured) {
+  constexpr int PSLABS = PTMEM ? 0 : (BN + 63) / 64;
+  const size_t smem = 1024 + 2 * AT_QBYTES + 4 * static_cast<size_t>(BN) * 128 + PSLABS * 16384 + AT_XCH_BYTES + 128;
+  auto kern = attn_fwd_tc_kernel<DH, NG0, NG1, PTMEM>;
+  static bool configured = false;
+  if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) {
       csm_set_error("attention_fwd: cudaFuncSetAttribute(%zu) failed: %s", smem, cudaGetErrorString(e));
       return CSM_ERR_CUDA;
     }
-    configured = smem;
+    configured = true;
   }
   CUtensorMap tq, tkv;
   int rc = csm_tensor_map_2d(&tq, qkv, 3ull * Dm, static_cast<uint64_t>(B) * S, 3ull * Dm, 64, p.pack ? 64 : 128, 2, 128);
   if (rc) return rc;
-  rc = csm_tensor_map_2d(&tkv, qkv, 3ull * Dm, static_cast<uint64_t>(B) * S, 3ull * Dm, 64, p.pack ? 64 : p.BN, 2, 128);
+  rc = csm_tensor_map_2d(&tkv, qkv, 3ull * Dm, static_cast<uint64_t>(B) * S, 3ull * Dm, 64, p.pack ? 64 : BN, 2, 128);
   if (rc) return rc;
   const int grid = p.items < device_sms() ? p.items : device_sms();
   cudaError_t le = csm_launch_pdl(kern, dim3(grid), dim3(AT_THREADS), smem, stream, tq, tkv, p);
@@ -492,61 +546,129 @@ int attn_fwd_tc_launch(const void* qkv, void* out, float* lse, int B, int S, int
   return CSM_OK;
 }
 
-
 // ---------------------------------------------------------------------------------------------
-// backward (S <= 256): one CTA walks work items = (image or image pair, 64-column head group); per head it visits the
-// 128 x 128 sub-blocks (key block kb outer, query tile i inner) of the score matrix once:
-//   MMA   S  = Q_i K_kb^T,  dP = dO_i V_kb^T                         -> TMEM (128 + 128 columns)
+// backward: a persistent CTA per SM walks work items = (image or image pair, 64-column head group, 128-key block).
+// The K / V tiles of the block stay in shared memory while the 128-row Q / dO tiles stream past (both double-buffered
+// by the TMA producer, across work items too); per (query tile i, head) the 128 x 128 sub-block of the score matrix is
+// visited once:
+//   MMA   S  = Q_i K^T,  dP = dO_i V^T                               -> TMEM (128 + 128 columns)
 //   warps P  = exp2(S*c - L2),  dS = P * (dP - delta)                -> shared memory, bf16, [query][key] tiles
-//   MMA   dV_kb += P^T dO_i,  dK_kb += dS^T Q_i,  dQ_i += dS K_kb    -> TMEM accumulators
+//   MMA   dV += P^T dO_i,  dK += dS^T Q_i,  dQ_i(partial) = dS K     -> TMEM
 // The [query][key] tiles of P / dS serve as the MN-major A operand of the dV / dK products and as the K-major A operand
 // of dQ; the Q / K / V / dO tiles TMA brought in (128-byte swizzle) are K-major operands of the first two products and
-// MN-major B operands of the last three -- nothing is transposed or copied.  dK / dV leave TMEM after the last query
-// tile of their key block, dQ after the last key block (x d^-1/2, bf16), so every gradient is written exactly once and
-// there are no atomics.  delta = rowsum(dO * O) is recomputed per (head, query tile) from global memory.
+// MN-major B operands of the last three -- nothing is transposed or copied.  dK / dV accumulate in TMEM over the query
+// tiles and are written once per work item; the dQ partial of a sub-block is read back one sub-block later (x d^-1/2)
+// and stored directly when the sequence is a single key block, else reduced into the (zeroed) dQ columns with
+// red.global.add.bf16x2.  The softmax warps release the S / dP tiles as soon as they hold them in registers, so the
+// next sub-block's first two products run under the exp / dS arithmetic of the current one.
+// delta = rowsum(dO * O) comes from attn_delta_kernel.
 // ---------------------------------------------------------------------------------------------
 struct BwdParams {
   int B, S, H, Dm, HG;
   int pack;          // two images per 128-row tile (S <= 64)
-  int NT;            // 128-row query tiles == 128-key blocks per image (1 or 2)
-  int bn_last;       // keys in the last key block (multiple of 16)
+  int NT;            // 128-row query tiles == 128-key blocks per image
+  int bn_last;       // keys in the last key block (multiple of 64)
   int items;
   float c, scale;
-  const __nv_bfloat16* o_fwd;
-  const __nv_bfloat16* d_out;
   const float* lse;
+  const float* delta;      // rowsum(dO * O) per (image, head, token), attn_delta_kernel
   __nv_bfloat16* dqkv;
 };
 
+// delta[(b*H + h)*S + s] = sum_j dO[b*S + s, h*DH + j] * O[b*S + s, h*DH + j]: one thread per (token, head),
+// consecutive threads read consecutive 2*DH-byte pieces of a row
 template <int DH>
-__global__ void __launch_bounds__(AT_THREADS, 1)
+__global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ d_out,
+                                  float* __restrict__ delta, int B, int S, int H) {
+  pdl_wait();
+  pdl_trigger();
+  const long long total = static_cast<long long>(B) * S * H;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int h = static_cast<int>(idx % H);
+    const long long r = idx / H;                         // b * S + s
+    const uint4* op = reinterpret_cast<const uint4*>(o + idx * DH);
+    const uint4* dp = reinterpret_cast<const uint4*>(d_out + idx * DH);
+    float acc = 0.f;
+#pragma unroll
+    for (int c8 = 0; c8 < DH / 8; ++c8) {
+      const uint4 a = __ldg(dp + c8), bb = __ldg(op + c8);
+      const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 x = unpack_bf16x2(aw[e]), y = unpack_bf16x2(bw[e]);
+        acc = fmaf(x.x, y.x, acc);
+        acc = fmaf(x.y, y.y, acc);
+      }
+    }
+    const long long b = r / S, s_ = r % S;
+    delta[(b * H + h) * S + s_] = acc;
+  }
+}
+
+__device__ __forceinline__ void red_add_bf16x2_v4(void* gptr, uint4 v) {
+  asm volatile("red.global.add.noftz.v4.bf16x2 [%0], {%1, %2, %3, %4};" ::"l"(gptr), "r"(v.x), "r"(v.y), "r"(v.z),
+               "r"(v.w)
+               : "memory");
+}
+
+// the sub-block sequence of one CTA: items (stride gridDim.x) x query tiles x heads of the group
+struct BwdIter {
+  int item, i, hh, nh, hg, bi, kb;
+  __device__ __forceinline__ void set_item(const BwdParams& p, int NH) {
+    kb = item % p.NT;
+    const int r = item / p.NT;
+    hg = r % p.HG;
+    bi = r / p.HG;
+    nh = min(NH, p.H - hg * NH);
+  }
+  __device__ __forceinline__ void init(const BwdParams& p, int NH) {
+    item = blockIdx.x;
+    i = hh = 0;
+    if (item < p.items) set_item(p, NH);
+  }
+  __device__ __forceinline__ bool valid(const BwdParams& p) const { return item < p.items; }
+  __device__ __forceinline__ bool last_of_item(const BwdParams& p) const { return hh == nh - 1 && i == p.NT - 1; }
+  __device__ __forceinline__ void next(const BwdParams& p, int NH) {
+    if (++hh < nh) return;
+    hh = 0;
+    if (++i < p.NT) return;
+    i = 0;
+    item += gridDim.x;
+    if (item < p.items) set_item(p, NH);
+  }
+};
+
+constexpr int ATB_SM_WARPS = 16;
+constexpr int ATB_THREADS = 32 * (4 + ATB_SM_WARPS);   // 640
+
+template <int DH>
+__global__ void __launch_bounds__(ATB_THREADS, 1)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_do,
                    const BwdParams p) {
   constexpr int NH = 64 / DH;
   constexpr int KS = DH / 16;
   constexpr int OC = DH / 2;           // gradient columns owned by one softmax thread
-  constexpr uint32_t COL_S = 0, COL_DP = 128, COL_DQ = 256, COL_DK = 256 + 2 * DH, COL_DV = 256 + 3 * DH;
+  constexpr uint32_t COL_S = 0, COL_DP = 128, COL_DK = 256, COL_DV = 256 + NH * DH, COL_DQ = 256 + 2 * NH * DH;
+  static_assert(COL_DQ + 2 * DH <= 512, "TMEM budget");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const int NT = p.NT;
-  const int tile_bytes = NT * 16384;
-  uint8_t* sQ = smem;
-  uint8_t* sK = sQ + tile_bytes;
-  uint8_t* sV = sK + tile_bytes;
-  uint8_t* sdO = sV + tile_bytes;
-  uint8_t* sP = sdO + tile_bytes;      // [2 slabs of 64 keys][128 query rows][128 B]
+  uint8_t* sKV = smem;                 // [2 stages][K 16 KB | V 16 KB]
+  uint8_t* sQO = smem + 65536;         // [2 stages][Q 16 KB | dO 16 KB]
+  uint8_t* sP = smem + 131072;         // [2 slabs of 64 keys][128 query rows][128 B]
   uint8_t* sdS = sP + 32768;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sdS + 32768);
-  uint64_t* ld_full = bars;
-  uint64_t* ld_empty = bars + 1;
-  uint64_t* sdp_full = bars + 2;
-  uint64_t* pds_full = bars + 3;
-  uint64_t* pds_free = bars + 4;
-  uint64_t* dkv_full = bars + 5;
-  uint64_t* dkv_free = bars + 6;
-  uint64_t* dq_full = bars + 7;
-  uint64_t* dq_free = bars + 8;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+  uint64_t* kv_full = bars;            // [2]
+  uint64_t* kv_empty = bars + 2;       // [2]
+  uint64_t* q_full = bars + 4;         // [2]
+  uint64_t* q_empty = bars + 6;        // [2]
+  uint64_t* sdp_full = bars + 8;       // S / dP products complete
+  uint64_t* sdp_free = bars + 9;       // S / dP tiles are in registers
+  uint64_t* pds_full = bars + 10;      // P / dS tiles written
+  uint64_t* grads_done = bars + 11;    // dV / dK / dQ products of a sub-block complete
+  uint64_t* dq_free = bars + 12;       // [2] dQ partial buffer read out
+  uint64_t* dkv_free = bars + 14;      // dK / dV of an item read out
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -554,15 +676,18 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmap_qkv);
     tma_prefetch_desc(&tmap_do);
-    mbar_init(ld_full, 1);
-    mbar_init(ld_empty, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&kv_full[i], 1);
+      mbar_init(&kv_empty[i], 1);
+      mbar_init(&q_full[i], 1);
+      mbar_init(&q_empty[i], 1);
+      mbar_init(&dq_free[i], ATB_SM_WARPS);
+    }
     mbar_init(sdp_full, 1);
-    mbar_init(pds_full, AT_SM_WARPS);
-    mbar_init(pds_free, 1);
-    mbar_init(dkv_full, 1);
-    mbar_init(dkv_free, AT_SM_WARPS);
-    mbar_init(dq_full, 1);
-    mbar_init(dq_free, AT_SM_WARPS);
+    mbar_init(sdp_free, ATB_SM_WARPS);
+    mbar_init(pds_full, ATB_SM_WARPS);
+    mbar_init(grads_done, 1);
+    mbar_init(dkv_free, ATB_SM_WARPS);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -575,273 +700,318 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();
   pdl_trigger();
+  const int NT = p.NT;
 
   if (warp < 4) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
     if (warp == 0) {
       // ------------------------------ TMA producer ------------------------------
       if (lane == 0) {
-        uint32_t ic = 0;
+        uint32_t ic = 0, qc = 0;
         for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++ic) {
-          const int hg = item % p.HG;
-          const int bi = item / p.HG;
-          mbar_wait_wd(ld_empty, (ic & 1) ^ 1);
-          mbar_expect_tx(ld_full, 4u * tile_bytes);
-          const int nbox = p.pack ? 2 : NT;
-          for (int t = 0; t < nbox; ++t) {
-            const int row = p.pack ? (2 * bi + t) * p.S : bi * p.S + t * 128;
-            const int off = p.pack ? t * 8192 : t * 16384;
-            tma_load_2d(sQ + off, &tmap_qkv, ld_full, hg * 64, row);
-            tma_load_2d(sK + off, &tmap_qkv, ld_full, p.Dm + hg * 64, row);
-            tma_load_2d(sV + off, &tmap_qkv, ld_full, 2 * p.Dm + hg * 64, row);
-            tma_load_2d(sdO + off, &tmap_do, ld_full, hg * 64, row);
+          const int kb = item % NT;
+          const int r = item / NT;
+          const int hg = r % p.HG;
+          const int bi = r / p.HG;
+          const int nbox = p.pack ? 2 : 1;
+          {
+            const uint32_t ks = ic & 1;
+            mbar_wait_wd(&kv_empty[ks], ((ic >> 1) & 1) ^ 1);
+            mbar_expect_tx(&kv_full[ks], 32768);
+            uint8_t* k = sKV + ks * 32768;
+            for (int t = 0; t < nbox; ++t) {
+              const int row = p.pack ? (2 * bi + t) * p.S : bi * p.S + kb * 128;
+              tma_load_2d(k + t * 8192, &tmap_qkv, &kv_full[ks], p.Dm + hg * 64, row);
+              tma_load_2d(k + 16384 + t * 8192, &tmap_qkv, &kv_full[ks], 2 * p.Dm + hg * 64, row);
+            }
+          }
+          for (int i = 0; i < NT; ++i, ++qc) {
+            const uint32_t qs = qc & 1;
+            mbar_wait_wd(&q_empty[qs], ((qc >> 1) & 1) ^ 1);
+            mbar_expect_tx(&q_full[qs], 32768);
+            uint8_t* q = sQO + qs * 32768;
+            for (int t = 0; t < nbox; ++t) {
+              const int row = p.pack ? (2 * bi + t) * p.S : bi * p.S + i * 128;
+              tma_load_2d(q + t * 8192, &tmap_qkv, &q_full[qs], hg * 64, row);
+              tma_load_2d(q + 16384 + t * 8192, &tmap_do, &q_full[qs], hg * 64, row);
+            }
           }
         }
       }
     } else if (warp == 1) {
       // ------------------------------ MMA issuer (one thread) ------------------------------
       if (lane == 0) {
-        const uint32_t idesc_g = umma_idesc_bf16(128, DH, 1, 1);     // dV / dK: A and B MN-major
-        const uint32_t idesc_q = umma_idesc_bf16(128, DH, 0, 1);     // dQ: A K-major, B MN-major
-        const uint32_t q_addr = smem_u32(sQ), k_addr = smem_u32(sK), v_addr = smem_u32(sV), do_addr = smem_u32(sdO);
+        constexpr uint32_t idesc_g = umma_idesc_bf16(128, DH, 1, 1);     // dV / dK: A and B MN-major
+        constexpr uint32_t idesc_q = umma_idesc_bf16(128, DH, 0, 1);     // dQ: A K-major, B MN-major
         const uint32_t p_addr = smem_u32(sP), ds_addr = smem_u32(sdS);
-        uint32_t n = 0, g = 0, hc = 0, ic = 0;
-        // pending sub-block whose gradient products are issued after the NEXT sub-block's S / dP products
+        uint32_t n = 0, ic = 0, qc = 0;
+        // pending sub-block: its gradient products are issued after the NEXT sub-block's S / dP products
         bool pend = false;
-        uint32_t pd_n = 0, pd_g = 0, pd_hc = 0;
-        int pd_hh = 0, pd_kb = 0, pd_i = 0, pd_bn = 0;
-        bool pd_last_group = false, pd_last_head = false, pd_last_item = false;
+        uint32_t pd_n = 0, pd_ic = 0, pd_k = 0, pd_q = 0, pd_qs = 0;
+        int pd_hh = 0, pd_i = 0, pd_bn = 0;
+        bool pd_last_tile = false, pd_last_item = false;
         auto grads = [&]() {
-          if (pd_i == 0) mbar_wait_wd(dkv_free, (pd_g & 1) ^ 1);               // dK / dV of the previous group read out
-          if (pd_i == 0 && pd_kb == 0) mbar_wait_wd(dq_free, (pd_hc & 1) ^ 1);  // dQ of the previous head read out
+          mbar_wait_wd(pds_full, pd_n & 1);                                   // P / dS tiles are in shared memory
+          if (pd_i == 0 && pd_hh == 0 && pd_ic > 0) mbar_wait_wd(dkv_free, (pd_ic - 1) & 1);   // previous item's dK / dV read
+          if (pd_n >= 2) mbar_wait_wd(&dq_free[pd_n & 1], ((pd_n >> 1) - 1) & 1);              // dQ buffer read out
           tc_fence_after();
           const uint32_t hoff = DH == 32 ? pd_hh * 64 : 0;
 #pragma unroll
-          for (int kk = 0; kk < 8; ++kk) {           // dV_kb += P^T dO_i   (reduction over the 128 query rows)
+          for (int kk = 0; kk < 8; ++kk) {           // dV += P^T dO_i   (reduction over the 128 query rows)
             const uint64_t da = umma_smem_desc_sw128(p_addr + kk * 2048, 16384, 1024);
-            const uint64_t db = umma_smem_desc_sw128(do_addr + pd_i * 16384 + kk * 2048 + hoff, 8192, 1024);
-            umma_f16(tmem_base + COL_DV, da, db, idesc_g, (pd_i > 0 || kk > 0) ? 1u : 0u);
+            const uint64_t db = umma_smem_desc_sw128(pd_q + 16384 + kk * 2048 + hoff, 8192, 1024);
+            umma_f16(tmem_base + COL_DV + pd_hh * DH, da, db, idesc_g, (pd_i > 0 || kk > 0) ? 1u : 0u);
           }
 #pragma unroll
-          for (int kk = 0; kk < 8; ++kk) {           // dK_kb += dS^T Q_i
+          for (int kk = 0; kk < 8; ++kk) {           // dK += dS^T Q_i
             const uint64_t da = umma_smem_desc_sw128(ds_addr + kk * 2048, 16384, 1024);
-            const uint64_t db = umma_smem_desc_sw128(q_addr + pd_i * 16384 + kk * 2048 + hoff, 8192, 1024);
-            umma_f16(tmem_base + COL_DK, da, db, idesc_g, (pd_i > 0 || kk > 0) ? 1u : 0u);
+            const uint64_t db = umma_smem_desc_sw128(pd_q + kk * 2048 + hoff, 8192, 1024);
+            umma_f16(tmem_base + COL_DK + pd_hh * DH, da, db, idesc_g, (pd_i > 0 || kk > 0) ? 1u : 0u);
           }
           const int ksteps = pd_bn >> 4;
-          for (int ks = 0; ks < ksteps; ++ks) {      // dQ_i += dS K_kb     (reduction over the keys of the block)
+          for (int ks = 0; ks < ksteps; ++ks) {      // dQ_i (partial) = dS K   (reduction over the keys of the block)
             const uint64_t da = umma_smem_desc_sw128(ds_addr + (ks >> 2) * 16384 + (ks & 3) * 32, 16, 1024);
-            const uint64_t db = umma_smem_desc_sw128(k_addr + pd_kb * 16384 + ks * 2048 + hoff, 8192, 1024);
-            umma_f16(tmem_base + COL_DQ + pd_i * DH, da, db, idesc_q, (pd_kb > 0 || ks > 0) ? 1u : 0u);
+            const uint64_t db = umma_smem_desc_sw128(pd_k + ks * 2048 + hoff, 8192, 1024);
+            umma_f16(tmem_base + COL_DQ + (pd_n & 1) * DH, da, db, idesc_q, ks > 0 ? 1u : 0u);
           }
-          umma_commit(pds_free);
-          if (pd_last_group) umma_commit(dkv_full);
-          if (pd_last_head) umma_commit(dq_full);
-          if (pd_last_item) umma_commit(ld_empty);
+          umma_commit(grads_done);
+          if (pd_last_tile) umma_commit(&q_empty[pd_qs]);
+          if (pd_last_item) umma_commit(&kv_empty[pd_ic & 1]);
         };
         for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++ic) {
-          const int hg = item % p.HG;
+          const int kb = item % NT;
+          const int hg = (item / NT) % p.HG;
           const int nh = min(NH, p.H - hg * NH);
-          mbar_wait_wd(ld_full, ic & 1);
-          tc_fence_after();
-          for (int hh = 0; hh < nh; ++hh, ++hc) {
-            for (int kb = 0; kb < NT; ++kb, ++g) {
-              const int bn = (kb == NT - 1) ? p.bn_last : 128;
-              const uint32_t idesc_s = umma_idesc_bf16(128, bn, 0, 0);
-              for (int i = 0; i < NT; ++i, ++n) {
-                if (pend) {
-                  mbar_wait_wd(pds_full, pd_n & 1);       // the S / dP tiles have been read, P / dS are in smem
-                  tc_fence_after();
-                }
+          const int bn = (kb == NT - 1) ? p.bn_last : 128;
+          const uint32_t idesc_s = umma_idesc_bf16(128, bn, 0, 0);
+          const uint32_t ks = ic & 1;
+          mbar_wait_wd(&kv_full[ks], (ic >> 1) & 1);
+          const uint32_t k_addr = smem_u32(sKV + ks * 32768), v_addr = k_addr + 16384;
+          for (int i = 0; i < NT; ++i, ++qc) {
+            const uint32_t qs = qc & 1;
+            mbar_wait_wd(&q_full[qs], (qc >> 1) & 1);
+            const uint32_t q_addr = smem_u32(sQO + qs * 32768), do_addr = q_addr + 16384;
+            for (int hh = 0; hh < nh; ++hh, ++n) {
+              if (n > 0) mbar_wait_wd(sdp_free, (n - 1) & 1);      // the previous S / dP tiles are in registers
+              tc_fence_after();
 #pragma unroll
-                for (int kk = 0; kk < KS; ++kk) {
-                  const uint32_t ko = (hh * KS + kk) * 32;
-                  umma_f16(tmem_base + COL_S, umma_smem_desc_sw128(q_addr + i * 16384 + ko, 16, 1024),
-                           umma_smem_desc_sw128(k_addr + kb * 16384 + ko, 16, 1024), idesc_s, kk > 0 ? 1u : 0u);
-                }
-#pragma unroll
-                for (int kk = 0; kk < KS; ++kk) {
-                  const uint32_t ko = (hh * KS + kk) * 32;
-                  umma_f16(tmem_base + COL_DP, umma_smem_desc_sw128(do_addr + i * 16384 + ko, 16, 1024),
-                           umma_smem_desc_sw128(v_addr + kb * 16384 + ko, 16, 1024), idesc_s, kk > 0 ? 1u : 0u);
-                }
-                umma_commit(sdp_full);
-                if (pend) grads();
-                pend = true;
-                pd_n = n; pd_g = g; pd_hc = hc; pd_hh = hh; pd_kb = kb; pd_i = i; pd_bn = bn;
-                pd_last_group = (i == NT - 1);
-                pd_last_head = pd_last_group && (kb == NT - 1);
-                pd_last_item = pd_last_head && (hh == nh - 1);
+              for (int kk = 0; kk < KS; ++kk) {
+                const uint32_t ko = (hh * KS + kk) * 32;
+                umma_f16(tmem_base + COL_S, umma_smem_desc_sw128(q_addr + ko, 16, 1024),
+                         umma_smem_desc_sw128(k_addr + ko, 16, 1024), idesc_s, kk > 0 ? 1u : 0u);
               }
+#pragma unroll
+              for (int kk = 0; kk < KS; ++kk) {
+                const uint32_t ko = (hh * KS + kk) * 32;
+                umma_f16(tmem_base + COL_DP, umma_smem_desc_sw128(do_addr + ko, 16, 1024),
+                         umma_smem_desc_sw128(v_addr + ko, 16, 1024), idesc_s, kk > 0 ? 1u : 0u);
+              }
+              umma_commit(sdp_full);
+              if (pend) grads();
+              pend = true;
+              pd_n = n; pd_ic = ic; pd_k = k_addr; pd_q = q_addr; pd_qs = qs; pd_hh = hh; pd_i = i; pd_bn = bn;
+              pd_last_tile = (hh == nh - 1);
+              pd_last_item = pd_last_tile && (i == NT - 1);
             }
           }
-          // the operand tiles are single-buffered: finish this item's products before the next item's loads
-          mbar_wait_wd(pds_full, pd_n & 1);
-          tc_fence_after();
-          grads();
-          pend = false;
         }
+        if (pend) grads();
       }
     }
   } else {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
     // ------------------------------ softmax / gradient warps ------------------------------
-    const int half = (warp - 4) >> 2;
-    const int quarter = warp & 3;
+    // 16 warps: thread = (query row, quarter of the key block) -- no reduction runs along a row in the backward, so
+    // the split is free and four warps per scheduler hide each other's latencies
+    const int cq = (warp - 4) >> 2;           // column quarter
+    const int quarter = warp & 3;             // TMEM lane quarter
     const int row = quarter * 32 + lane;
     const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
     const float c = p.c;
     const uint32_t p_row = smem_u32(sP) + row * 128;
     const uint32_t ds_row = smem_u32(sdS) + row * 128;
     const uint32_t sw7 = static_cast<uint32_t>(row & 7);
-    const size_t ld3 = static_cast<size_t>(3) * p.Dm;
-    uint32_t n = 0, g = 0, hc = 0;
+    const uint32_t ld3 = 3u * p.Dm;
+    const bool reduce_dq = NT > 1;
+    constexpr int OQ = DH / 4;                // gradient columns read back by one thread (8 or 16)
 
-    auto store16 = [&](const uint32_t* v, float mul, __nv_bfloat16* dst) {   // OC f32 values -> bf16
-#pragma unroll
-      for (int q8 = 0; q8 < OC / 8; ++q8) {
-        uint4 pk;
-        pk.x = pack_bf16x2(__uint_as_float(v[q8 * 8 + 0]) * mul, __uint_as_float(v[q8 * 8 + 1]) * mul);
-        pk.y = pack_bf16x2(__uint_as_float(v[q8 * 8 + 2]) * mul, __uint_as_float(v[q8 * 8 + 3]) * mul);
-        pk.z = pack_bf16x2(__uint_as_float(v[q8 * 8 + 4]) * mul, __uint_as_float(v[q8 * 8 + 5]) * mul);
-        pk.w = pack_bf16x2(__uint_as_float(v[q8 * 8 + 6]) * mul, __uint_as_float(v[q8 * 8 + 7]) * mul);
-        *reinterpret_cast<uint4*>(dst + q8 * 8) = pk;
+    auto pack8 = [&](const uint32_t* v, float mul) -> uint4 {
+      uint4 o;
+      o.x = pack_bf16x2(__uint_as_float(v[0]) * mul, __uint_as_float(v[1]) * mul);
+      o.y = pack_bf16x2(__uint_as_float(v[2]) * mul, __uint_as_float(v[3]) * mul);
+      o.z = pack_bf16x2(__uint_as_float(v[4]) * mul, __uint_as_float(v[5]) * mul);
+      o.w = pack_bf16x2(__uint_as_float(v[6]) * mul, __uint_as_float(v[7]) * mul);
+      return o;
+    };
+    auto tmem_ld_oq = [&](uint32_t addr, uint32_t* v) {
+      if (OQ == 16) tmem_ld_32x16(addr, v);
+      else tmem_ld_32x8(addr, v);
+    };
+
+    BwdIter cur, nxt;
+    cur.init(p, NH);
+    nxt = cur;
+    // per-item token bookkeeping of this thread's TMEM lane (32-bit: B * H * S < 2^31)
+    auto img_of = [&](const BwdIter& it) { return p.pack ? 2 * it.bi + (row >> 6) : it.bi; };
+    auto tok_of = [&](int t) { return p.pack ? (row & 63) : t * 128 + row; };
+    auto load_stats = [&](const BwdIter& it, float& L, float& d) {
+      const int b_img = img_of(it), tok = tok_of(it.i);
+      L = INFINITY;      // padded query row: p = exp2(-inf) = 0
+      d = 0.f;
+      if (tok < p.S && b_img < p.B) {
+        const uint32_t o = (static_cast<uint32_t>(b_img) * p.H + it.hg * NH + it.hh) * p.S + tok;
+        L = __ldg(p.lse + o);
+        d = __ldg(p.delta + o);
       }
     };
-    auto tmem_ld_oc = [&](uint32_t addr, uint32_t* v) {
-      tmem_ld_32x16(addr, v);
-      if (OC == 32) tmem_ld_32x16(addr + 16, v + (OC == 32 ? 16 : 0));
-    };
+    float Lc = INFINITY, dc = 0.f;
+    if (cur.valid(p)) {
+      load_stats(cur, Lc, dc);
+      nxt.next(p, NH);
+    }
+    uint32_t n = 0;
+    // deferred read-backs of the previous sub-block
+    uint32_t have_prev;
+    asm volatile("mov.u32 %0, 0;" : "=r"(have_prev));
+    bool prev_last_item = false;
+    int prev_qrow = -1, prev_krow = -1;       // global token rows (or -1: padded)
+    int prev_col = 0, prev_col0 = 0, prev_nh = 0;
 
-    for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
-      const int hg = item % p.HG;
-      const int bi = item / p.HG;
-      const int nh = min(NH, p.H - hg * NH);
-      // token (query or key) handled by this thread's TMEM lane in tile t
-      const int b_img = p.pack ? 2 * bi + (row >> 6) : bi;
-      const int tok0 = p.pack ? (row & 63) : row;
-      for (int hh = 0; hh < nh; ++hh, ++hc) {
-        const int h = hg * NH + hh;
-        float Lr[2] = {INFINITY, INFINITY}, dl[2] = {0.f, 0.f};
-        for (int kb = 0; kb < NT; ++kb, ++g) {
-          const int bn = (kb == NT - 1) ? p.bn_last : 128;
-          const int bnh = bn >> 1;
-          const int nch = bnh >> 3;
-          const int colbase = half * bnh;
-          const int kvalid = p.pack ? (((row >> 6) == half) ? p.S : 0) : (p.S - kb * 128 - colbase);
+    // dQ partial of sub-block n - 1 and, after the last sub-block of an item, its dK / dV
+    auto read_back = [&]() {
+      uint32_t vq[OQ];
+      tmem_ld_oq(tmem_base + lane_off + COL_DQ + ((n - 1) & 1) * DH + cq * OQ, vq);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&dq_free[(n - 1) & 1]);
+      if (prev_qrow >= 0) {
+        __nv_bfloat16* dst = p.dqkv + static_cast<size_t>(prev_qrow) * ld3 + prev_col + cq * OQ;
 #pragma unroll
-          for (int i = 0; i < 2; ++i) {
-            if (i < NT) {
-              if (kb == 0) {
-                // softmax statistic and delta = rowsum(dO * O) of this thread's query row
-                const int tok = tok0 + i * 128;
-                if (tok < p.S && b_img < p.B) {
-                  const size_t grow = static_cast<size_t>(b_img) * p.S + tok;
-                  Lr[i] = p.lse[(static_cast<size_t>(b_img) * p.H + h) * p.S + tok];
-                  const uint4* dop = reinterpret_cast<const uint4*>(p.d_out + grow * p.Dm + h * DH);
-                  const uint4* op = reinterpret_cast<const uint4*>(p.o_fwd + grow * p.Dm + h * DH);
-                  float acc = 0.f;
-#pragma unroll
-                  for (int c8 = 0; c8 < DH / 8; ++c8) {
-                    const uint4 a = __ldg(dop + c8), bb = __ldg(op + c8);
-                    const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {bb.x, bb.y, bb.z, bb.w};
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                      const float2 x = unpack_bf16x2(aw[e]), y = unpack_bf16x2(bw[e]);
-                      acc = fmaf(x.x, y.x, acc);
-                      acc = fmaf(x.y, y.y, acc);
-                    }
-                  }
-                  dl[i] = acc;
-                } else {
-                  Lr[i] = INFINITY;      // padded query row: p = exp2(-inf) = 0
-                  dl[i] = 0.f;
-                }
-              }
-              mbar_wait_wd(sdp_full, n & 1);
-              tc_fence_after();
-              uint32_t su[64], du[64];
-              const uint32_t ts = tmem_base + lane_off + COL_S + colbase;
-              const uint32_t td = tmem_base + lane_off + COL_DP + colbase;
-#pragma unroll
-              for (int q8 = 0; q8 < 8; ++q8) {
-                if (q8 < nch) {
-                  tmem_ld_32x8(ts + q8 * 8, su + q8 * 8);
-                  tmem_ld_32x8(td + q8 * 8, du + q8 * 8);
-                }
-              }
-              tmem_ld_wait();
-              if (kvalid < bnh) {
-#pragma unroll
-                for (int e = 0; e < 64; ++e)
-                  if (e >= kvalid) su[e] = 0xff800000u;            // masked key: p = 0, dS = 0
-              }
-              if (n > 0) mbar_wait_wd(pds_free, (n - 1) & 1);       // the previous P / dS tiles have been consumed
-              const float Li = Lr[i], di = dl[i];
-#pragma unroll
-              for (int q8 = 0; q8 < 8; ++q8) {
-                if (q8 < nch) {
-                  float pe[8], de[8];
-#pragma unroll
-                  for (int e = 0; e < 8; ++e) {
-                    pe[e] = ex2f(fmaf(__uint_as_float(su[q8 * 8 + e]), c, -Li));
-                    de[e] = pe[e] * (__uint_as_float(du[q8 * 8 + e]) - di);
-                  }
-                  uint4 pk, dk;
-                  pk.x = pack_bf16x2(pe[0], pe[1]); pk.y = pack_bf16x2(pe[2], pe[3]);
-                  pk.z = pack_bf16x2(pe[4], pe[5]); pk.w = pack_bf16x2(pe[6], pe[7]);
-                  dk.x = pack_bf16x2(de[0], de[1]); dk.y = pack_bf16x2(de[2], de[3]);
-                  dk.z = pack_bf16x2(de[4], de[5]); dk.w = pack_bf16x2(de[6], de[7]);
-                  const uint32_t gc = static_cast<uint32_t>((colbase >> 3) + q8);
-                  const uint32_t off = (gc >> 3) * 16384 + (((gc & 7) ^ sw7) << 4);
-                  sts_v4(p_row + off, pk);
-                  sts_v4(ds_row + off, dk);
-                }
-              }
-              fence_proxy_async();
-              tc_fence_before();
-              __syncwarp();
-              if (lane == 0) mbar_arrive(pds_full);
-              ++n;
-            }
-          }
-          // ---- dK / dV of this key block are complete after its last query tile ----
-          mbar_wait_wd(dkv_full, g & 1);
-          tc_fence_after();
-          {
-            uint32_t vk[OC], vv[OC];
-            tmem_ld_oc(tmem_base + lane_off + COL_DK + half * OC, vk);
-            tmem_ld_oc(tmem_base + lane_off + COL_DV + half * OC, vv);
-            tmem_ld_wait();
-            const int tok = tok0 + kb * 128;
-            if (tok < p.S && b_img < p.B) {
-              __nv_bfloat16* base = p.dqkv + (static_cast<size_t>(b_img) * p.S + tok) * ld3 + h * DH + half * OC;
-              store16(vk, p.scale, base + p.Dm);
-              store16(vv, 1.0f, base + 2 * p.Dm);
-            }
-          }
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(dkv_free);
+        for (int q8 = 0; q8 < OQ / 8; ++q8) {
+          const uint4 pk = pack8(vq + q8 * 8, p.scale);
+          if (reduce_dq) red_add_bf16x2_v4(dst + q8 * 8, pk);
+          else *reinterpret_cast<uint4*>(dst + q8 * 8) = pk;
         }
-        // ---- dQ of this head is complete after the last key block ----
-        mbar_wait_wd(dq_full, hc & 1);
-        tc_fence_after();
+      }
+      if (prev_last_item) {
+#pragma unroll 1
+        for (int hh = 0; hh < prev_nh; ++hh) {
+          uint32_t vk[OQ], vv[OQ];
+          tmem_ld_oq(tmem_base + lane_off + COL_DK + hh * DH + cq * OQ, vk);
+          tmem_ld_oq(tmem_base + lane_off + COL_DV + hh * DH + cq * OQ, vv);
+          tmem_ld_wait();
+          if (prev_krow >= 0) {
+            __nv_bfloat16* dst = p.dqkv + static_cast<size_t>(prev_krow) * ld3 + prev_col0 + hh * DH + cq * OQ;
 #pragma unroll
-        for (int i = 0; i < 2; ++i) {
-          if (i < NT) {
-            uint32_t vq[OC];
-            tmem_ld_oc(tmem_base + lane_off + COL_DQ + i * DH + half * OC, vq);
-            tmem_ld_wait();
-            const int tok = tok0 + i * 128;
-            if (tok < p.S && b_img < p.B)
-              store16(vq, p.scale, p.dqkv + (static_cast<size_t>(b_img) * p.S + tok) * ld3 + h * DH + half * OC);
+            for (int q8 = 0; q8 < OQ / 8; ++q8) {
+              *reinterpret_cast<uint4*>(dst + p.Dm + q8 * 8) = pack8(vk + q8 * 8, p.scale);
+              *reinterpret_cast<uint4*>(dst + 2 * p.Dm + q8 * 8) = pack8(vv + q8 * 8, 1.0f);
+            }
           }
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(dq_free);
+        if (lane == 0) mbar_arrive(dkv_free);
       }
+    };
+
+#pragma unroll 1
+    while (cur.valid(p)) {
+      const int bn = (cur.kb == NT - 1) ? p.bn_last : 128;
+      const int bnq = bn >> 2;                  // keys of this thread's quarter: one or two 16-key groups
+      const int colbase = cq * bnq;
+      int kvalid = p.pack ? (((row >> 6) == (cq >> 1)) ? p.S - (cq & 1) * 32 : 0) : (p.S - cur.kb * 128 - colbase);
+      kvalid = max(0, min(kvalid, bnq));
+      // statistics of the next sub-block's row: in flight during this sub-block
+      float Ln = INFINITY, dn = 0.f;
+      if (nxt.valid(p)) load_stats(nxt, Ln, dn);
+
+      mbar_wait_wd(sdp_full, n & 1);
+      tc_fence_after();
+      uint32_t su[32], du[32];
+      const uint32_t ts = tmem_base + lane_off + COL_S + colbase;
+      const uint32_t td = tmem_base + lane_off + COL_DP + colbase;
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        if (q * 16 < kvalid) {
+          tmem_ld_32x16(ts + q * 16, su + q * 16);
+          tmem_ld_32x16(td + q * 16, du + q * 16);
+        }
+      }
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(sdp_free);       // the next sub-block's S / dP products may overwrite the tiles
+
+      // P and dS of this thread's keys, packed to bf16 pairs (in place over the scores)
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const int lim = kvalid - q * 16;          // valid keys of the group (warp-uniform)
+        if (lim > 0) {
+          if (lim < 16) {
+#pragma unroll
+            for (int e = 1; e < 16; ++e)
+              if (e >= lim) su[q * 16 + e] = 0xff800000u;          // masked key: p = 0, dS = 0
+          }
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const float p0 = ex2f(fmaf(__uint_as_float(su[q * 16 + 2 * e]), c, -Lc));
+            const float p1 = ex2f(fmaf(__uint_as_float(su[q * 16 + 2 * e + 1]), c, -Lc));
+            su[q * 16 + e] = pack_bf16x2(p0, p1);
+            du[q * 16 + e] = pack_bf16x2(p0 * (__uint_as_float(du[q * 16 + 2 * e]) - dc),
+                                         p1 * (__uint_as_float(du[q * 16 + 2 * e + 1]) - dc));
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) su[q * 16 + e] = du[q * 16 + e] = 0u;
+        }
+      }
+      // the previous sub-block's gradient products are done: the P / dS tiles may be rewritten and its dQ partial
+      // (and dK / dV) read.  The stores go first so that they drain under the read-back, before the proxy fence.
+      if (have_prev) {
+        mbar_wait_wd(grads_done, (n - 1) & 1);
+        tc_fence_after();
+      }
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        if (q * 16 < bnq) {
+          const uint32_t gc = static_cast<uint32_t>((colbase >> 3) + 2 * q);
+          const uint32_t o0 = (gc >> 3) * 16384 + (((gc & 7) ^ sw7) << 4);
+          const uint32_t o1 = ((gc + 1) >> 3) * 16384 + ((((gc + 1) & 7) ^ sw7) << 4);
+          sts_v4(p_row + o0, make_uint4(su[q * 16 + 0], su[q * 16 + 1], su[q * 16 + 2], su[q * 16 + 3]));
+          sts_v4(p_row + o1, make_uint4(su[q * 16 + 4], su[q * 16 + 5], su[q * 16 + 6], su[q * 16 + 7]));
+          sts_v4(ds_row + o0, make_uint4(du[q * 16 + 0], du[q * 16 + 1], du[q * 16 + 2], du[q * 16 + 3]));
+          sts_v4(ds_row + o1, make_uint4(du[q * 16 + 4], du[q * 16 + 5], du[q * 16 + 6], du[q * 16 + 7]));
+        }
+      }
+      if (have_prev) read_back();
+      fence_proxy_async();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(pds_full);
+
+      have_prev = 1;
+      {
+        const int b_img = img_of(cur);
+        const int tq = tok_of(cur.i), tk = tok_of(cur.kb);
+        prev_qrow = (tq < p.S && b_img < p.B) ? b_img * p.S + tq : -1;
+        prev_col0 = cur.hg * NH * DH;
+        prev_col = prev_col0 + cur.hh * DH;
+        prev_nh = cur.nh;
+        prev_last_item = cur.last_of_item(p);
+        if (prev_last_item) prev_krow = (tk < p.S && b_img < p.B) ? b_img * p.S + tk : -1;
+      }
+      cur = nxt;
+      Lc = Ln;
+      dc = dn;
+      if (nxt.valid(p)) nxt.next(p, NH);
+      ++n;
+    }
+    if (have_prev) {
+      mbar_wait_wd(grads_done, (n - 1) & 1);
+      tc_fence_after();
+      read_back();
     }
   }
 
@@ -855,8 +1025,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
 }
 
 template <int DH>
-int attn_bwd_tc_launch(const void* qkv, const void* o, const void* d_out, const float* lse, void* dqkv, int B, int S,
-                       int H, cudaStream_t stream) {
+int attn_bwd_tc_launch(const void* qkv, const void* o, const void* d_out, const float* lse, float* delta, void* dqkv,
+                       int B, int S, int H, cudaStream_t stream) {
   const int Dm = H * DH;
   BwdParams p{};
   p.B = B; p.S = S; p.H = H; p.Dm = Dm;
@@ -867,25 +1037,44 @@ int attn_bwd_tc_launch(const void* qkv, const void* o, const void* d_out, const 
     p.items = ((B + 1) / 2) * p.HG;
   } else {
     p.NT = (S + 127) / 128;
-    p.bn_last = ((S - (p.NT - 1) * 128) + 15) & ~15;
-    p.items = B * p.HG;
+    p.bn_last = ((S - (p.NT - 1) * 128) + 63) & ~63;
+    p.items = B * p.HG * p.NT;
   }
   p.scale = 1.0f / sqrtf(static_cast<float>(DH));
   p.c = 1.4426950408889634f * p.scale;
-  p.o_fwd = reinterpret_cast<const __nv_bfloat16*>(o);
-  p.d_out = reinterpret_cast<const __nv_bfloat16*>(d_out);
   p.lse = lse;
+  p.delta = delta;
   p.dqkv = reinterpret_cast<__nv_bfloat16*>(dqkv);
-  const size_t smem = 1024 + 4 * static_cast<size_t>(p.NT) * 16384 + 65536 + 128;
+  {
+    const long long total = static_cast<long long>(B) * S * H;
+    const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, 8LL * device_sms()));
+    cudaError_t de = csm_launch_pdl(attn_delta_kernel<DH>, dim3(blocks), dim3(256), 0, stream,
+                                    reinterpret_cast<const __nv_bfloat16*>(o),
+                                    reinterpret_cast<const __nv_bfloat16*>(d_out), delta, B, S, H);
+    if (de != cudaSuccess) {
+      csm_set_error("attention_bwd: delta launch failed: %s", cudaGetErrorString(de));
+      return CSM_ERR_CUDA;
+    }
+  }
+  if (p.NT > 1) {
+    // several key blocks reduce their dQ partials into the dQ columns of dqkv: start from zero
+    cudaError_t me = cudaMemset2DAsync(dqkv, static_cast<size_t>(3) * Dm * 2, 0, static_cast<size_t>(Dm) * 2,
+                                       static_cast<size_t>(B) * S, stream);
+    if (me != cudaSuccess) {
+      csm_set_error("attention_bwd: memset failed: %s", cudaGetErrorString(me));
+      return CSM_ERR_CUDA;
+    }
+  }
+  const size_t smem = 1024 + 4 * 32768 + 65536 + 256;
   auto kern = attn_bwd_tc_kernel<DH>;
-  static size_t configured = 0;
-  if (smem > configured) {
+  static bool configured = false;
+  if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) {
       csm_set_error("attention_bwd: cudaFuncSetAttribute(%zu) failed: %s", smem, cudaGetErrorString(e));
       return CSM_ERR_CUDA;
     }
-    configured = smem;
+    configured = true;
   }
   CUtensorMap tq, tdo;
   const uint32_t box_rows = p.pack ? 64 : 128;
@@ -894,7 +1083,7 @@ int attn_bwd_tc_launch(const void* qkv, const void* o, const void* d_out, const 
   rc = csm_tensor_map_2d(&tdo, d_out, Dm, static_cast<uint64_t>(B) * S, Dm, 64, box_rows, 2, 128);
   if (rc) return rc;
   const int grid = p.items < device_sms() ? p.items : device_sms();
-  cudaError_t le = csm_launch_pdl(kern, dim3(grid), dim3(AT_THREADS), smem, stream, tq, tdo, p);
+  cudaError_t le = csm_launch_pdl(kern, dim3(grid), dim3(ATB_THREADS), smem, stream, tq, tdo, p);
   if (le != cudaSuccess) {
     csm_set_error("attention_bwd: launch failed: %s", cudaGetErrorString(le));
     return CSM_ERR_CUDA;
@@ -904,27 +1093,53 @@ int attn_bwd_tc_launch(const void* qkv, const void* o, const void* d_out, const 
 
 }  // namespace
 
-// variant: 0 = narrow P.V (N = d), 1 = d = 32 heads computed as N = 64 pairs (diagnostic fallback)
+extern "C" int csm_colsum_bf16(const void* dy_bf16, float* db, int rows, int N, int skip_period, int num_sms,
+                               cudaStream_t stream);
+
+// variant: 0 = probabilities through TMEM (A operand of P.V from TMEM), 1 = through shared memory (diagnostic)
 extern "C" int csm_attention_fwd_tc(const void* qkv_bf16, void* out_bf16, float* lse, int B, int S, int H, int head_dim,
                                     int variant, cudaStream_t stream) {
   CSM_CHECK_ARG(B > 0 && S > 0 && H > 0, "csm_attention_fwd: bad sizes B=%d S=%d H=%d", B, S, H);
   CSM_CHECK_ARG((H * head_dim) % 8 == 0, "csm_attention_fwd: H * head_dim must be a multiple of 8");
+  const bool tm = variant == 0;
   if (head_dim == 32) {
-    if (variant == 1) return attn_fwd_tc_launch<32, 64>(qkv_bf16, out_bf16, lse, B, S, H, stream);
-    return attn_fwd_tc_launch<32, 32>(qkv_bf16, out_bf16, lse, B, S, H, stream);
+    if (S <= 128) {
+      return tm ? attn_fwd_tc_launch<32, 4, 4, true>(qkv_bf16, out_bf16, lse, B, S, H, stream)
+                : attn_fwd_tc_launch<32, 4, 4, false>(qkv_bf16, out_bf16, lse, B, S, H, stream);
+    }
+    return tm ? attn_fwd_tc_launch<32, 6, 7, true>(qkv_bf16, out_bf16, lse, B, S, H, stream)
+              : attn_fwd_tc_launch<32, 6, 7, false>(qkv_bf16, out_bf16, lse, B, S, H, stream);
   }
-  if (head_dim == 64) return attn_fwd_tc_launch<64, 64>(qkv_bf16, out_bf16, lse, B, S, H, stream);
+  if (head_dim == 64) {
+    return tm ? attn_fwd_tc_launch<64, 4, 4, true>(qkv_bf16, out_bf16, lse, B, S, H, stream)
+              : attn_fwd_tc_launch<64, 4, 4, false>(qkv_bf16, out_bf16, lse, B, S, H, stream);
+  }
   csm_set_error("csm_attention_fwd: head_dim must be 32 or 64 (got %d)", head_dim);
   return CSM_ERR_ARG;
 }
 
-extern "C" int csm_attention_bwd_tc(const void* qkv_bf16, const void* out_bf16, const void* d_out_bf16, const float* lse,
-                                    void* dqkv_bf16, int B, int S, int H, int head_dim, cudaStream_t stream) {
+extern "C" int csm_attention_fwd(const void* qkv_bf16, void* out_bf16, float* lse, int B, int S, int H, int head_dim,
+                                 cudaStream_t stream) {
+  return csm_attention_fwd_tc(qkv_bf16, out_bf16, lse, B, S, H, head_dim, 0, stream);
+}
+
+extern "C" int csm_attention_bwd(const void* qkv_bf16, const void* out_bf16, const void* d_out_bf16, const float* lse,
+                                 float* delta_scratch, void* dqkv_bf16, float* dbias, int B, int S, int H,
+                                 int head_dim, cudaStream_t stream) {
   CSM_CHECK_ARG(B > 0 && S > 0 && H > 0, "csm_attention_bwd: bad sizes B=%d S=%d H=%d", B, S, H);
-  CSM_CHECK_ARG(S <= 256, "csm_attention_bwd_tc: S=%d > 256 is served by the two-pass kernels", S);
   CSM_CHECK_ARG((H * head_dim) % 8 == 0, "csm_attention_bwd: H * head_dim must be a multiple of 8");
-  if (head_dim == 32) return attn_bwd_tc_launch<32>(qkv_bf16, out_bf16, d_out_bf16, lse, dqkv_bf16, B, S, H, stream);
-  if (head_dim == 64) return attn_bwd_tc_launch<64>(qkv_bf16, out_bf16, d_out_bf16, lse, dqkv_bf16, B, S, H, stream);
-  csm_set_error("csm_attention_bwd: head_dim must be 32 or 64 (got %d)", head_dim);
-  return CSM_ERR_ARG;
+  CSM_CHECK_ARG(delta_scratch != nullptr, "csm_attention_bwd: needs the delta scratch buffer [B * H * S] f32");
+  int rc;
+  if (head_dim == 32)
+    rc = attn_bwd_tc_launch<32>(qkv_bf16, out_bf16, d_out_bf16, lse, delta_scratch, dqkv_bf16, B, S, H, stream);
+  else if (head_dim == 64)
+    rc = attn_bwd_tc_launch<64>(qkv_bf16, out_bf16, d_out_bf16, lse, delta_scratch, dqkv_bf16, B, S, H, stream);
+  else {
+    csm_set_error("csm_attention_bwd: head_dim must be 32 or 64 (got %d)", head_dim);
+    return CSM_ERR_ARG;
+  }
+  if (rc) return rc;
+  // attn.qkv.bias gradient = column sums of dqkv over the tokens
+  if (dbias != nullptr) return csm_colsum_bf16(dqkv_bf16, dbias, B * S, 3 * H * head_dim, 0, 0, stream);
+  return CSM_OK;
 }

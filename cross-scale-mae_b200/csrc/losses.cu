@@ -215,9 +215,14 @@ __global__ void bn_patch_fwd_kernel(const __nv_bfloat16* __restrict__ h, const f
       running_var[l] = (1.f - momentum) * running_var[l] + momentum * var * (cnt / (cnt - 1.f));
     }
   }
-  } else {  // eval mode: normalise with the running statistics
+  } else {  // eval mode: normalise with the running statistics (kept for the backward, which then uses
+            // dh = gamma * rstd * dy: the statistics are constants)
     mean = running_mean[l];
     rstd = rsqrtf(running_var[l] + eps);
+    if (threadIdx.x == 0) {
+      mean_out[l] = mean;
+      rstd_out[l] = rstd;
+    }
   }
   const float a = rstd * gamma[l], b = beta[l] - mean * rstd * gamma[l];
 #pragma unroll 4
@@ -248,7 +253,7 @@ __global__ void bn_patch_bwd_kernel(const __nv_bfloat16* __restrict__ h, const _
                                     const __nv_bfloat16* __restrict__ d_out, const float* __restrict__ gamma,
                                     const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
                                     __nv_bfloat16* __restrict__ dh, float* __restrict__ dgamma,
-                                    float* __restrict__ dbeta, int N, int Sd, int Hp) {
+                                    float* __restrict__ dbeta, int N, int Sd, int Hp, int training) {
   __shared__ float s_buf[32];
   const int l = blockIdx.x;
   const int per_row = Hp / 8;
@@ -278,7 +283,8 @@ __global__ void bn_patch_bwd_kernel(const __nv_bfloat16* __restrict__ h, const _
     dbeta[l] = s1;
   }
   const float cnt = static_cast<float>(N) * Hp;
-  const float m1 = s1 / cnt, m2 = s2 / cnt, gr = gamma[l] * rstd;
+  // eval mode (running statistics are constants): dh = gamma * rstd * dy, no batch-statistic terms
+  const float m1 = training ? s1 / cnt : 0.f, m2 = training ? s2 / cnt : 0.f, gr = gamma[l] * rstd;
 #pragma unroll 2
   for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
     const int n = idx / per_row, c = (idx % per_row) * 8;
@@ -751,10 +757,10 @@ extern "C" int csm_bn_patch_fwd(const void* h_bf16, const float* gamma, const fl
 
 extern "C" int csm_bn_patch_bwd(const void* h_bf16, const void* out_bf16, const void* d_out_bf16, const float* gamma,
                                 const float* mean, const float* rstd, void* dh_bf16, float* dgamma, float* dbeta,
-                                int N, int L, int Hp, cudaStream_t stream) {
+                                int N, int L, int Hp, int training, cudaStream_t stream) {
   CSM_CHECK_ARG(N > 0 && L > 0 && Hp % 8 == 0, "csm_bn_patch_bwd: bad sizes N=%d L=%d Hp=%d", N, L, Hp);
   const size_t cl_smem = static_cast<size_t>((N + BN_CL - 1) / BN_CL) * Hp * 2 * 2;
-  if (N >= BN_CL && cl_smem <= 96 * 1024) {
+  if (training && N >= BN_CL && cl_smem <= 96 * 1024) {
     static size_t configured = 0;
     if (cl_smem > configured) {
       cudaFuncSetAttribute(bn_patch_bwd_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cl_smem);
@@ -770,7 +776,7 @@ extern "C" int csm_bn_patch_bwd(const void* h_bf16, const void* out_bf16, const 
   bn_patch_bwd_kernel<<<L, 1024, 0, stream>>>(
       reinterpret_cast<const __nv_bfloat16*>(h_bf16), reinterpret_cast<const __nv_bfloat16*>(out_bf16),
       reinterpret_cast<const __nv_bfloat16*>(d_out_bf16), gamma, mean, rstd, reinterpret_cast<__nv_bfloat16*>(dh_bf16),
-      dgamma, dbeta, N, L + 1, Hp);
+      dgamma, dbeta, N, L + 1, Hp, training);
   CSM_CHECK_LAUNCH("bn_patch_bwd");
   return CSM_OK;
 }

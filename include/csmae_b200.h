@@ -122,13 +122,15 @@ int csm_cross_mse_fwd(const void* cp_bf16, const float* tgt, float* loss_sum, in
                       csm_stream_t stream);
 int csm_cross_mse_bwd(const void* cp_bf16, const float* tgt, void* d_cp_bf16, float* d_tgt, const float* grad_scalar,
                       float coef, int rows, int Sd, int Dd, csm_stream_t stream);
-/* BatchNorm1d(num_patches) over [N, L, Hp] + ReLU, train mode (MLP.py:7-8) */
+/* BatchNorm1d(num_patches) over [N, L, Hp] + ReLU (MLP.py:7-8).  training = 1: batch statistics (+ running-stat update);
+ * training = 0: running statistics (mean / rstd still written for the backward, which then treats them as constants:
+ * dh = gamma * rstd * dy, as nn.BatchNorm1d in eval mode) */
 int csm_bn_patch_fwd(const void* h_bf16, const float* gamma, const float* beta, void* out_bf16, float* mean,
                      float* rstd, float* running_mean, float* running_var, int N, int L, int Hp, float eps,
                      float momentum, int training, csm_stream_t stream);
 int csm_bn_patch_bwd(const void* h_bf16, const void* out_bf16, const void* d_out_bf16, const float* gamma,
                      const float* mean, const float* rstd, void* dh_bf16, float* dgamma, float* dbeta, int N, int L,
-                     int Hp, csm_stream_t stream);
+                     int Hp, int training, csm_stream_t stream);
 /* NT-Xent on the token-mean encoder features (util/contrast_loss.py:71-101; MAE_ViT_MsLdCeCd.py:62-69) */
 int csm_ntxent_fwd(const float* enc_out, float* zhat, float* fnorm, float* neg, float* loss_sum, int B, int Se, int D,
                    float tau, float eps, csm_stream_t stream);
@@ -139,7 +141,20 @@ int csm_ntxent_bwd(const float* zhat, const float* fnorm, const float* neg, cons
  * table_dev: device array of 80-byte entries {float* p; const float* g; float* m; float* v; bf16* shadow_or_null;
  * int64 n; float lr, wd, beta1, beta2, eps, bias_correction1, sqrt(bias_correction2), grad_scale};
  * chunks_dev: device array of {int tensor_index, int chunk_index} work items of 8192 elements */
-int csm_adamw_multi(const void* table_dev, const void* chunks_dev, int num_chunks, int num_sms, csm_stream_t stream);
+int csm_adamw_multi(const void* table_dev, const void* chunks_dev, int num_chunks, const float* ctl_dev, int num_sms,
+                    csm_stream_t stream);
+/* ctl_dev (nullable, device f32[2]): {gradient multiplier (GradScaler's 1/scale x clip coefficient), found_inf}: the
+ * multiplier is applied to every gradient on the fly and a nonzero found_inf skips the whole update -- the AMP step of
+ * util/misc.py:314-326 with no host synchronisation between backward and step.
+ * csm_grad_stats_f32: the matching single pass over the flat gradient buffer: stats[0] += sum((x * *mul_dev)^2)
+ * (global gradient norm of the UNSCALED gradients), stats[1] = 1 when any element is not finite. */
+int csm_grad_stats_f32(const float* x, long long n, const float* mul_dev, float* stats, int num_sms,
+                       csm_stream_t stream);
+/* scalar part of the AMP step (GradScaler.unscale_/step/update, util/misc.py:314-326) on the device: stats = the pair
+ * csm_grad_stats_f32 wrote, state = {scale, growth_tracker, 1 / scale} (updated in place), ctl = the pair
+ * csm_adamw_multi reads, norm_out[0] = global gradient norm; clip <= 0 disables clipping */
+int csm_amp_update(const float* stats, float* state, float* ctl, float* norm_out, float clip, float growth,
+                   float backoff, int interval, csm_stream_t stream);
 /* out[0] += sum of squares of x[0..n)  (global gradient norm of the flat gradient buffer in one pass) */
 int csm_sumsq_f32(const float* x, long long n, float* out, int num_sms, csm_stream_t stream);
 

@@ -1,10 +1,10 @@
-"""Import the REAL reference classes from /root/reference (build container only).
+"""Import the REAL reference classes: from /root/reference in the build container, from the verbatim copy in
+oracle/_ref (tools/vendor_ref.py; git-ignored, travels to the GPU box) elsewhere.
 
-TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).  Used by
-tests/golden/make_golden.py to produce the committed fixtures and, when
-/root/reference is present, by tests that check the restatement against the
-live reference.  /root/reference does not exist on the GPU box: nothing marked
-`gpu`, `smoke()` or `bench.py` may call this module.
+TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).  Used by tests/golden/make_golden.py to produce the committed
+fixtures, by tests that check the restatement against the live reference, by the GPU test that runs the unmodified
+engine_pretrain.train_one_epoch, and by bench.py's `--impl reference` arm.  Nothing may read /root/reference at run
+time on the GPU box.
 
 Why shims are needed: `import models_mae` fails as
 shipped -- models_mae/__init__.py:16-19 star-imports four modules that are not
@@ -23,7 +23,12 @@ import os
 import sys
 import types
 
+# /root/reference in the build container; on the GPU box the verbatim copy tools/vendor_ref.py placed in oracle/_ref
+# (git-ignored, travels with the snapshot)
+_VENDORED = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
 REFERENCE_ROOT = os.environ.get("CSM_REFERENCE_ROOT", "/root/reference")
+if not os.path.isdir(os.path.join(REFERENCE_ROOT, "models_mae")) and os.path.isdir(os.path.join(_VENDORED, "models_mae")):
+    REFERENCE_ROOT = _VENDORED
 
 # size dicts restated from /root/reference/models_mae/__init__.py:42-58
 ARGS_VIT_BASE = dict(dim_model=768, encoder_num_layers=12, encoder_num_heads=12,

@@ -242,7 +242,8 @@ def _native_ddp_worker(rank, world, port, q):
     w0 = m.decoder_pred.weight.detach().clone()
     loss, _, _ = ddp(torch.randn(2, 3, 64, 64), torch.randn(2, 3, 64, 64), 0.75)
     (loss * 2.0).backward()
-    ok = fired == list(range(len(fired))) and len(fired) == 1 + min(3, 4)   # decoder tail + 2 encoder groups + head
+    # decoder tail + (encoder layer groups - 1) + head: one group per encoder layer by default
+    ok = fired == list(range(len(fired))) and len(fired) == 1 + eng._sync_groups and eng._sync_groups == 4
     for n, p in m.named_parameters():
         if n.startswith("encoder_norm.") or not p.requires_grad:
             ok &= p.grad is None

@@ -20,5 +20,5 @@ delta = torch.empty(B * H * S, device="cuda")
 for _ in range(3):
     nat.call("csm_attention_fwd_tc", qkv, out, lse, B, S, H, d, 0)
     if mode == "bwd":
-        nat.call("csm_attention_bwd_tc", qkv, out, d_out, lse, dqkv, B, S, H, d)
+        nat.call("csm_attention_bwd", qkv, out, d_out, lse, delta, dqkv, None, B, S, H, d)
 torch.cuda.synchronize()
