@@ -3,15 +3,20 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--arch base|large] [--batch B] [--input-size S]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
-    python bench.py --impl reference ...      # the reference algorithm on the host CPU cores
+    python bench.py --impl reference ...      # the VERBATIM reference classes (oracle/_ref) on the host CPU cores
 
 A step = one full training step of MAE_ViT_MsLdCeCd on one synthetic two-scale batch:
 zero_grad -> forward(imgs1, imgs2, 0.75) -> backward -> AdamW.step (betas 0.9/0.95, wd 0.05, as
 main_pretrain.py:426-427).  `value` times it with the batch already resident in HBM; `e2e` times the
-same step through the public nn.Module call with the batch in pinned HOST memory (H2D copy and the
-loss read-back inside the timed region).  One JSON line on stdout (rank 0).
+same step through the public nn.Module call with the batch in pinned HOST memory (H2D copy and an immediate
+loss.item() read-back inside the timed region, as engine_pretrain.py:49-55 does); `e2e.stock_engine` is the
+UNMODIFIED reference loop engine_pretrain.train_one_epoch driving this module.  One JSON line on stdout (rank 0);
+the default run appends `extra_configs` (ViT-L/224 bs 32 and ViT-L/448 bs 16, BASELINE.json configs[2] and [4]).
 """
 import argparse
+import contextlib
+import hashlib
+import io
 import json
 import os
 import subprocess
@@ -35,6 +40,7 @@ ARCH = {
     "large": dict(dim_model=1024, encoder_num_layers=24, encoder_num_heads=16, decoder_embed_dim=512,
                   decoder_num_layers=8, decoder_num_heads=16),
 }
+GEMM_SOURCE = os.path.join(ROOT, "cross-scale-mae_b200", "csrc", "gemm_tcgen05.cu")
 
 
 # ------------------------------------------------------------------------------------------------
@@ -68,6 +74,24 @@ def measured_peaks():
     return dict(tflops_burst=1590.0, tflops_sustained=1400.0, hbm_gbs=6650.0, source="fallback (B200_PROFILING.md)")
 
 
+def gemm_traffic(launches_per_step):
+    """DRAM bytes per GEMM launch from the committed `ncu --set full` capture of THIS build's GEMM (tools/ncu_traffic.py
+    writes the file with the sha256 of gemm_tcgen05.cu and the launch count it saw): anything else is not a
+    measurement of the benched binary and is reported as null with the reason."""
+    path = os.path.join(ROOT, "profiles", "r2_gemm_dram_traffic.json")
+    if not os.path.exists(path):
+        return None, "no ncu --set full capture committed for this build"
+    with open(path) as f:
+        t = json.load(f)
+    with open(GEMM_SOURCE, "rb") as f:
+        sha = hashlib.sha256(f.read()).hexdigest()
+    if t.get("gemm_source_sha256") != sha:
+        return None, "profiles/r2_gemm_dram_traffic.json was captured on another build of gemm_tcgen05.cu"
+    if t.get("launches_per_step") != launches_per_step:
+        return None, (f"capture saw {t.get('launches_per_step')} GEMM launches per step, this run {launches_per_step}")
+    return t["avg_bytes_per_launch"], f"ncu --set full, {t['launches']} launches ({t.get('source', '')})"
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled while the timed region runs: ONE long-running `nvidia-smi -lms 200`
     (the recipe's clocks line, B200_PROFILING.md) started before and killed after.  (Spawning nvidia-smi per sample
@@ -77,7 +101,6 @@ class ClockSampler:
     def __init__(self, index):
         self.index = index
         self.rows = []
-        self.stop_flag = threading.Event()
         self.proc = None
         self.reader = None
 
@@ -101,7 +124,6 @@ class ClockSampler:
                 self.rows.append(parts)
 
     def stop(self):
-        self.stop_flag.set()
         if self.proc is not None:
             self.proc.terminate()            # the exact process started above
             try:
@@ -123,18 +145,43 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
-# CPU arm: the reference's algorithm (oracle/restatement.py, pinned against the real reference by
-# tests/test_oracle_golden.py) on the host cores.  /root/reference itself does not exist on the GPU box.
+# CPU arm.  kind "reference": the VERBATIM reference classes (oracle/_ref: models_mae/MAE_ViT_MsLdCeCd.py and its
+# bases, copied by tools/vendor_ref.py; timm 0.4.12's Block / PatchEmbed -- a pip dependency absent from this image --
+# come from oracle/timm_shim.py) through the reference's own forward (single input, scale 2 = its in-model
+# RandomResizedCrop), loss.backward() and torch.optim.AdamW, fp32, all host threads.  kind "port": oracle/restatement.py
+# when oracle/_ref did not travel.  /root/reference itself does not exist on the GPU box.
 # ------------------------------------------------------------------------------------------------
 def cpu_reference_step_time(arch, size, batch, steps, warmup):
-    from oracle import restatement as R
     torch.set_num_threads(os.cpu_count() or 1)
     a = ARCH[arch]
+    g = torch.Generator().manual_seed(1000)
+    from oracle import ref_loader
+    if ref_loader.reference_available():
+        _, _, RefCeCd = ref_loader.reference_classes()
+        with contextlib.redirect_stdout(io.StringIO()):       # the reference constructors print
+            torch.manual_seed(0)
+            model = RefCeCd(**a, input_size=size, patch_size=16, input_channels=3, device="cpu").train()
+        decay = [p for n, p in model.named_parameters() if p.requires_grad and not (p.ndim == 1 or n.endswith(".bias"))]
+        no_decay = [p for n, p in model.named_parameters() if p.requires_grad and (p.ndim == 1 or n.endswith(".bias"))]
+        opt = torch.optim.AdamW([{"params": no_decay, "weight_decay": 0.0}, {"params": decay, "weight_decay": 0.05}],
+                                lr=1.5e-4, betas=(0.9, 0.95))
+        x = torch.randn(batch, 3, size, size, generator=g)
+        times = []
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            opt.zero_grad()
+            loss, _, _ = model(x, mask_ratio=MASK_RATIO)
+            loss.backward()
+            opt.step()
+            loss.item()
+            if i >= warmup:
+                times.append(time.perf_counter() - t0)
+        return sum(times) / len(times), "reference"
+    from oracle import restatement as R
     sd = R.make_state_dict(**a, input_size=size, patch_size=16, seed=0)
     leaves = {k: v.clone().requires_grad_(k not in R.FROZEN_KEYS) for k, v in sd.items()}
     opt = torch.optim.AdamW([v for v in leaves.values() if v.requires_grad], lr=1e-4, betas=(0.9, 0.95),
                             weight_decay=0.05)
-    g = torch.Generator().manual_seed(1000)
     L = (size // 16) ** 2
     x1, x2 = torch.randn(batch, 3, size, size, generator=g), torch.randn(batch, 3, size, size, generator=g)
     rm, rv = torch.zeros(L), torch.ones(L)
@@ -150,7 +197,15 @@ def cpu_reference_step_time(arch, size, batch, steps, warmup):
         out["loss"].item()
         if i >= warmup:
             times.append(time.perf_counter() - t0)
-    return sum(times) / len(times)
+    return sum(times) / len(times), "port"
+
+
+def cpu_sample_text(kind, steps, cpu_batch):
+    what = ("the verbatim reference MAE_ViT_MsLdCeCd (oracle/_ref, timm Block from oracle/timm_shim.py): "
+            "zero_grad, forward(imgs, mask_ratio=0.75) with its in-model crop, backward, torch.optim.AdamW.step"
+            if kind == "reference" else "oracle/restatement.py (reference algorithm): fwd+bwd+AdamW")
+    return (f"{steps} timed steps of {what}, each on a {cpu_batch}-image sample of the workload's batch "
+            f"(images/s is batch-insensitive on the CPU), fp32, all host threads")
 
 
 def run_reference(args):
@@ -158,24 +213,32 @@ def run_reference(args):
     if rank != 0:
         return
     cpu_batch = args.cpu_batch
-    sec = cpu_reference_step_time(args.arch, args.input_size, cpu_batch, args.steps, max(1, min(args.warmup, 1)))
+    sec, kind = cpu_reference_step_time(args.arch, args.input_size, cpu_batch, args.steps, 1)
     ips = cpu_batch / sec
     cores = torch.get_num_threads()
-    sample = (f"{args.steps} timed steps of fwd+bwd+AdamW, each on a {cpu_batch}-image sample of the workload's batch "
-              f"(images/s is batch-insensitive on CPU), fp32, all host threads, oracle/restatement.py")
+    # `config` names the workload this arm SAMPLES (the driver matches it against the GPU arm's line); what the arm
+    # actually ran -- its own batch, optimizer, precision, device -- is spelled out in `reference_arm` and in
+    # `cpu_baseline.sample`
+    cfg = workload_config(args, args.batch, max(1, args.gpus))
+    ref_arm = {"device": "cpu", "batch_per_step": cpu_batch, "dtype": "f32", "threads": cores,
+               "optimizer": "torch.optim.AdamW (betas 0.9/0.95, wd 0.05)", "processes": 1,
+               "form": "single-input forward, scale 2 by the model's own RandomResizedCrop"
+               if kind == "reference" else "paired inputs (oracle/restatement.py)"}
     line = {"impl": "reference", "metric": METRIC, "value": ips, "unit": "images/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(args, args.batch, max(1, args.gpus)),
-            "cpu_baseline": {"value": ips, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
+            "steps": args.steps, "warmup": 1, "ms_per_step": sec * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg, "reference_arm": ref_arm,
+            "cpu_baseline": {"value": ips, "unit": "images/s", "cores": cores, "kind": kind,
+                             "sample": cpu_sample_text(kind, args.steps, cpu_batch)},
             "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
 
-def workload_config(args, batch, world):
-    return {"workload": f"MAE_ViT_MsLdCeCd vit_{args.arch}_patch16 two-scale ({args.input_size}+{args.input_size}) "
+def workload_config(args, batch, world, arch=None, size=None):
+    arch = arch or args.arch
+    size = size or args.input_size
+    return {"workload": f"MAE_ViT_MsLdCeCd vit_{arch}_patch16 two-scale ({size}+{size}) "
                         f"bs={batch}/GPU mask_ratio=0.75, fwd+bwd+AdamW",
-            "global_batch": batch * world, "input_size": args.input_size,
+            "global_batch": batch * world, "input_size": size,
             "parallelism": (f"dp{world} ({'torch DDP' if getattr(args, 'torch_ddp', False) else 'engine-overlapped NCCL all-reduce'})"
                             if world > 1 else "single"),
             "optimizer": "torch.optim.AdamW(fused=True)" if getattr(args, "torch_adamw", False) else "csmae_b200.FusedAdamW",
@@ -183,49 +246,57 @@ def workload_config(args, batch, world):
 
 
 # ------------------------------------------------------------------------------------------------
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--impl", default="csmae_b200", choices=["csmae_b200", "reference"])
-    ap.add_argument("--arch", default="base", choices=["base", "large"])
-    ap.add_argument("--batch", type=int, default=None, help="images per GPU (default 64 base / 32 large)")
-    ap.add_argument("--input-size", type=int, default=224)
-    ap.add_argument("--cpu-batch", type=int, default=8)
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--torch-ddp", action="store_true", help="N>1: wrap with torch's DistributedDataParallel")
-    ap.add_argument("--torch-adamw", action="store_true", help="torch.optim.AdamW(fused=True) instead of FusedAdamW")
-    ap.add_argument("--profile-kernels", action="store_true", help="print the per-kernel CUDA-event breakdown")
-    args = ap.parse_args()
-    if args.batch is None:
-        args.batch = 64 if args.arch == "base" else 32
-    if args.impl == "reference":
-        run_reference(args)
-        return
+class Env:
+    def __init__(self, args):
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(self.local_rank)
+        self.dev = torch.device("cuda", self.local_rank)
+        if self.world > 1:
+            os.environ.setdefault("NCCL_IB_DISABLE", "1")
+            dist.init_process_group("nccl", device_id=self.dev)
+        assert self.world == args.gpus or self.world == 1, f"--gpus {args.gpus} but WORLD_SIZE={self.world}"
 
+    def barrier(self):
+        if self.world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(self, ms):
+        if self.world > 1:
+            t = torch.tensor([ms], device=self.dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = t.item()
+        return ms
+
+    def timed(self, fn, k):
+        self.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(k):
+            fn()
+        e1.record()
+        self.barrier()
+        return self.max_over_ranks(e0.elapsed_time(e1)) / k
+
+
+def measure(env, args, arch, B, S, steps, warmup, full):
+    """One workload: device-resident `value`, host-fed `e2e`; with full=True also the clock samples, the stock-engine
+    loop, the per-kernel breakdown and the roofline of the GEMM family."""
     import csmae_b200
     from csmae_b200 import _native
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        os.environ.setdefault("NCCL_IB_DISABLE", "1")
-        dist.init_process_group("nccl", device_id=dev)
-    assert world == args.gpus or world == 1, f"--gpus {args.gpus} but WORLD_SIZE={world}"
+    world, rank, dev = env.world, env.rank, env.dev
 
     torch.manual_seed(0)
-    ctor = csmae_b200.mae_vit_base_patch16 if args.arch == "base" else csmae_b200.mae_vit_large_patch16
-    model = ctor(input_size=args.input_size, device=str(dev)).to(dev).train()
+    ctor = csmae_b200.mae_vit_base_patch16 if arch == "base" else csmae_b200.mae_vit_large_patch16
+    model = ctor(input_size=S, device=str(dev)).to(dev).train()
     step_model = model
     if world > 1:
         # same constructor call as main_pretrain.py:417-421; csmae_b200's wrapper lets the engine all-reduce the
         # flat gradient buffer in segments overlapped with the backward (--torch-ddp: torch's own wrapper)
         wrapper = torch.nn.parallel.DistributedDataParallel if args.torch_ddp else csmae_b200.DistributedDataParallel
-        step_model = wrapper(model, device_ids=[local_rank], find_unused_parameters=True)
+        step_model = wrapper(model, device_ids=[env.local_rank], find_unused_parameters=True)
     decay = [p for n, p in model.named_parameters() if p.requires_grad and not (p.ndim == 1 or n.endswith(".bias"))]
     no_decay = [p for n, p in model.named_parameters() if p.requires_grad and (p.ndim == 1 or n.endswith(".bias"))]
     groups = [{"params": no_decay, "weight_decay": 0.0}, {"params": decay, "weight_decay": 0.05}]
@@ -235,7 +306,6 @@ def main():
         # row f1: one kernel for the whole AdamW step, which also rewrites the bf16 shadow weights
         opt = csmae_b200.FusedAdamW(groups, lr=1.5e-4, betas=(0.9, 0.95), model=model)
 
-    B, S = args.batch, args.input_size
     g = torch.Generator(device=dev).manual_seed(1000 + rank)
     imgs1 = torch.randn(B, 3, S, S, device=dev, generator=g)
     imgs2 = torch.randn(B, 3, S, S, device=dev, generator=g)
@@ -250,52 +320,16 @@ def main():
         opt.step()
         return loss
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def timed(fn, k):
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(k):
-            fn()
-        e1.record()
-        barrier()
-        ms = e0.elapsed_time(e1)
-        if world > 1:
-            t = torch.tensor([ms], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = t.item()
-        return ms / k
-
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(max(warmup, 3)):
         loss = step(imgs1, imgs2)
     assert torch.isfinite(loss).item(), "non-finite loss"
 
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
+    sampler = ClockSampler(env.local_rank)
+    if rank == 0 and full:
         sampler.start()
     launches0 = _native.launch_count
-    ms_step = timed(lambda: step(imgs1, imgs2), args.steps)
+    ms_step = env.timed(lambda: step(imgs1, imgs2), steps)
     launches = _native.launch_count - launches0
-
-    # fwd+bwd only (the BASELINE metric's second figure)
-    def fwd_bwd():
-        opt.zero_grad(set_to_none=True)
-        l_, _, _ = step_model(imgs1, imgs2, MASK_RATIO)
-        l_.backward()
-    ms_fwd_bwd = timed(fwd_bwd, max(3, args.steps // 2))
-
-    # host-side cost of enqueueing one step (no synchronisation inside): if this approaches ms_per_step the
-    # path is launch-bound on the CPU
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for _ in range(5):
-        step(imgs1, imgs2)
-    host_ms = (time.perf_counter() - t0) / 5 * 1e3
-    torch.cuda.synchronize()
 
     # end to end through the public API: every step's batch starts in pinned HOST memory, is copied to the
     # device (csmae_b200.DevicePrefetcher: the copy of step i+1 runs on a side stream while step i trains),
@@ -329,70 +363,192 @@ def main():
 
     def e2e_timed(lag):
         e2e_run(3, lag)
-        barrier()
+        env.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        e2e_run(args.steps, lag)
+        e2e_run(steps, lag)
         e1.record()
-        barrier()
-        ms = e0.elapsed_time(e1) / args.steps
-        if world > 1:
-            t = torch.tensor([ms], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = t.item()
-        return ms
+        env.barrier()
+        return env.max_over_ranks(e0.elapsed_time(e1) / steps)
     ms_e2e_sync = e2e_timed(0)       # loss.item() right after every step, as engine_pretrain.py:55 does
-    ms_e2e = e2e_timed(1)            # same reads, one step late
+    out = {"arch": arch, "batch": B, "size": S, "ms_step": ms_step, "launches": launches, "ms_e2e_sync": ms_e2e_sync,
+           "h2d": int(host1.numel() * 4 * 2)}
+    if not full:
+        del prefetcher, opt, step_model, model
+        torch.cuda.empty_cache()
+        return out
+    out["ms_e2e_lag"] = e2e_timed(1)            # same reads, one step late
+
+    # fwd+bwd only (the BASELINE metric's second figure)
+    def fwd_bwd():
+        opt.zero_grad(set_to_none=True)
+        l_, _, _ = step_model(imgs1, imgs2, MASK_RATIO)
+        l_.backward()
+    out["ms_fwd_bwd"] = env.timed(fwd_bwd, max(3, steps // 2))
+
+    # host-side cost of enqueueing one step (no synchronisation inside): if this approaches ms_per_step the
+    # path is launch-bound on the CPU
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(5):
+        step(imgs1, imgs2)
+    out["host_ms"] = (time.perf_counter() - t0) / 5 * 1e3
+    torch.cuda.synchronize()
+
+    # the UNMODIFIED reference loop (engine_pretrain.py:18-101, verbatim copy in oracle/_ref) driving this module:
+    # loader of pinned host batches -> .to(device) -> fp16-autocast context -> model(samples, mask_ratio) (single
+    # input: scale 2 is the in-model crop kernel) -> loss.item() -> loss_scaler(...) -> zero_grad -> synchronize.
+    # The loop is the reference's CALLER (not a checker): only its file is loaded from oracle/_ref.
+    out["stock_engine"] = stock_engine_e2e(env, args, model, step_model, opt, host1, steps)
     sampler.stop()
+    out["clocks"] = sampler.summary()
 
-    # per-kernel breakdown of one step with CUDA events on the launching stream (outside the timed region)
-    model._engine.use_graphs = False          # the breakdown times each C-ABI call eagerly
-    breakdown = kernel_breakdown(_native, lambda: step(imgs1, imgs2))     # every rank: the step all-reduces
+    # per-kernel breakdown of one step with CUDA events on the launching stream (outside the timed region):
+    # graphs off and the wgrad side stream off, so every C-ABI call is timed back to back on ONE stream and the
+    # families add up to a serial step (the graphed step overlaps wgrads with the dgrad chain and is shorter)
+    model._engine.use_graphs = False
+    model._engine.use_side_stream = False
+    step(imgs1, imgs2)
+    out["breakdown"] = kernel_breakdown(_native, lambda: step(imgs1, imgs2))     # every rank: the step all-reduces
+    del prefetcher, opt, step_model, model
+    torch.cuda.empty_cache()
+    return out
 
+
+def stock_engine_e2e(env, args, model, step_model, opt, host_batch, steps):
+    try:
+        from oracle import ref_loader
+        if not ref_loader.reference_available():
+            return {"unavailable": "oracle/_ref did not travel (tools/vendor_ref.py needs /root/reference)"}
+        engine = ref_loader.reference_module("engine_pretrain")
+    except Exception as e:      # noqa: BLE001
+        return {"unavailable": f"{type(e).__name__}: {e}"}
+    import csmae_b200
+    scaler = csmae_b200.NativeScalerWithGradNormCount()
+    if not isinstance(opt, csmae_b200.FusedAdamW):
+        return {"unavailable": "stock-engine loop is measured with FusedAdamW only"}
+    ns = argparse.Namespace(accum_iter=1, mask_ratio=MASK_RATIO, lr=1.5e-4, min_lr=0.0, warmup_epochs=40, epochs=800,
+                            local_rank=env.local_rank, wandb_project=None)
+
+    class Loader:
+        def __init__(self, k):
+            self.k = k
+
+        def __len__(self):
+            return self.k
+
+        def __iter__(self):
+            return ((host_batch, None) for _ in range(self.k))
+
+    def epoch(k):
+        with contextlib.redirect_stdout(io.StringIO()):           # the loop prints its meters; stdout carries the JSON line
+            return engine.train_one_epoch(step_model, Loader(k), opt, env.dev, 0, scaler, log_writer=None, args=ns)
+    epoch(4)
+    env.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    stats = epoch(steps)
+    e1.record()
+    env.barrier()
+    ms = env.max_over_ranks(e0.elapsed_time(e1) / steps)
+    B = host_batch.shape[0]
+    return {"value": B * env.world / (ms * 1e-3), "unit": "images/s", "ms_per_step": ms,
+            "h2d_bytes_per_step": int(host_batch.numel() * 4), "d2h_bytes_per_step": 4,
+            "loop": "unmodified engine_pretrain.train_one_epoch (oracle/_ref), single-input forward with the in-model "
+                    "crop kernel, csmae_b200.NativeScalerWithGradNormCount + FusedAdamW, loss.item() and "
+                    "torch.cuda.synchronize() every step",
+            "loss": stats.get("loss")}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="csmae_b200", choices=["csmae_b200", "reference"])
+    ap.add_argument("--arch", default="base", choices=["base", "large"])
+    ap.add_argument("--batch", type=int, default=None, help="images per GPU (default 64 base / 32 large)")
+    ap.add_argument("--input-size", type=int, default=224)
+    ap.add_argument("--cpu-batch", type=int, default=8)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the ViT-L/224 and ViT-L/448 extra_configs")
+    ap.add_argument("--torch-ddp", action="store_true", help="N>1: wrap with torch's DistributedDataParallel")
+    ap.add_argument("--torch-adamw", action="store_true", help="torch.optim.AdamW(fused=True) instead of FusedAdamW")
+    ap.add_argument("--profile-kernels", action="store_true", help="print the per-kernel CUDA-event breakdown")
+    args = ap.parse_args()
+    default_workload = args.arch == "base" and args.batch is None and args.input_size == 224
+    if args.batch is None:
+        args.batch = 64 if args.arch == "base" else 32
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    env = Env(args)
+    world, rank = env.world, env.rank
+    B, S = args.batch, args.input_size
+    m = measure(env, args, args.arch, B, S, args.steps, args.warmup, full=True)
+    extras = []
+    if default_workload and not args.no_extra:
+        # BASELINE.json configs[2] (ViT-L/16 224, bs 32/GPU) and configs[4] (ViT-L/16 448, bs 16/GPU): short runs of
+        # the same step, device-resident and host-fed
+        for arch, b, s in (("large", 32, 224), ("large", 16, 448)):
+            k = max(5, min(args.steps, 15))
+            x = measure(env, args, arch, b, s, k, 3, full=False)
+            fl = flops_per_image(arch, s)
+            ips = b * world / (x["ms_step"] * 1e-3)
+            extras.append({"config": workload_config(args, b, world, arch, s), "steps": k, "warmup": 3,
+                           "ms_per_step": x["ms_step"], "value": ips, "unit": "images/s",
+                           "e2e": {"value": b * world / (x["ms_e2e_sync"] * 1e-3), "unit": "images/s",
+                                   "ms_per_step": x["ms_e2e_sync"], "h2d_bytes_per_step": x["h2d"],
+                                   "d2h_bytes_per_step": 4},
+                           "gpu_launches": x["launches"],
+                           "step_frac_of_flop_roofline": ips / world * fl["fwd_bwd"] / (measured_peaks()["tflops_sustained"] * 1e12)})
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
+    breakdown = m["breakdown"]
     fl = flops_per_image(args.arch, S)
     peaks = measured_peaks()
-    ips = B * world / (ms_step * 1e-3)
-    ips_e2e = B * world / (ms_e2e * 1e-3)
-    # DRAM bytes per GEMM launch from the committed ncu --set full capture of the same shapes (ViT-B only)
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r1e_gemm_dram_traffic.json")
-    if args.arch == "base" and args.input_size == 224 and B == 64 and os.path.exists(tpath):
-        with open(tpath) as f:
-            traffic = json.load(f)["avg_bytes_per_launch"]
+    ips = B * world / (m["ms_step"] * 1e-3)
     gemm_ms = sum(v["ms"] for k, v in breakdown.items() if k.startswith("csm_linear"))
     gemm_n = sum(v["n"] for k, v in breakdown.items() if k.startswith("csm_linear"))
     step_ms_prof = sum(v["ms"] for v in breakdown.values())
+    traffic, traffic_note = gemm_traffic(gemm_n) if default_workload else (None, "captured for the default workload only")
     gemm_tflops = 3 * fl["gemm_fwd"] * B / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
     roofline = {"bound": "tensor", "kernel": "gemm_kernel (tcgen05; csm_linear_fwd/dgrad/wgrad, all launches of one step)",
                 "achieved": gemm_tflops, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
-                "frac": gemm_tflops / peaks["tflops_sustained"], "traffic": traffic,
+                "frac": gemm_tflops / peaks["tflops_sustained"], "traffic": traffic, "traffic_source": traffic_note,
                 "launches_per_step": gemm_n, "avg_launch_us": gemm_ms * 1e3 / gemm_n if gemm_n else None,
                 "flops_per_launch_avg": 3 * fl["gemm_fwd"] * B / gemm_n if gemm_n else None,
+                "timing": "CUDA events around every launch of one un-graphed step on one stream (launches back to back, "
+                          "caches as in the step)",
                 "peak_source": peaks["source"] + " (sustained: kernel timed inside a long step)",
                 "share_of_step": gemm_ms / step_ms_prof if step_ms_prof else None,
                 "step_frac_of_flop_roofline": ips / world * fl["fwd_bwd"] / (peaks["tflops_sustained"] * 1e12)}
     line = {"metric": METRIC, "value": ips, "unit": "images/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "warmup": max(args.warmup, 3), "ms_per_step": m["ms_step"], "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": workload_config(args, B, world),
-            "fwd_bwd_ms": ms_fwd_bwd, "host_enqueue_ms_per_step": host_ms, "gpu_launches": launches,
-            "e2e": {"value": ips_e2e, "unit": "images/s", "ms_per_step": ms_e2e,
-                    "h2d_bytes_per_step": int(host1.numel() * 4 * 2), "d2h_bytes_per_step": 4,
-                    "loss_read": "every step, issued after the next step is enqueued (1-step lag)",
-                    "immediate_read_ms_per_step": ms_e2e_sync,
-                    "immediate_read_value": B * world / (ms_e2e_sync * 1e-3)},
-            "clocks": sampler.summary(), "roofline": roofline,
+            "fwd_bwd_ms": m["ms_fwd_bwd"], "host_enqueue_ms_per_step": m["host_ms"], "gpu_launches": m["launches"],
+            "e2e": {"value": B * world / (m["ms_e2e_sync"] * 1e-3), "unit": "images/s", "ms_per_step": m["ms_e2e_sync"],
+                    "h2d_bytes_per_step": m["h2d"], "d2h_bytes_per_step": 4,
+                    "loss_read": "loss.item() right after every step (engine_pretrain.py:55)",
+                    "lagged_read_ms_per_step": m["ms_e2e_lag"],
+                    "lagged_read_value": B * world / (m["ms_e2e_lag"] * 1e-3),
+                    "stock_engine": m["stock_engine"]},
+            "clocks": m["clocks"], "roofline": roofline,
             "flops_per_image": fl, "kernel_ms": {k: round(v["ms"], 4) for k, v in sorted(
-                breakdown.items(), key=lambda kv: -kv[1]["ms"])}}
+                breakdown.items(), key=lambda kv: -kv[1]["ms"])},
+            "kernel_ms_note": "graphs off, single stream: families add up to a serial step; the graphed step overlaps "
+                              "the wgrad side stream with the dgrad chain"}
+    if extras:
+        line["extra_configs"] = extras
     if world == 1 and not args.no_cpu_baseline:
-        sec = cpu_reference_step_time(args.arch, S, args.cpu_batch, 2, 1)
+        k = 4
+        sec, kind = cpu_reference_step_time(args.arch, S, args.cpu_batch, k, 1)
         line["cpu_baseline"] = {"value": args.cpu_batch / sec, "unit": "images/s", "cores": torch.get_num_threads(),
-                                "kind": "port", "sample": f"2 timed steps of fwd+bwd+AdamW at batch {args.cpu_batch}, "
-                                                          f"fp32, oracle/restatement.py (reference algorithm)"}
+                                "kind": kind, "sample": cpu_sample_text(kind, k, args.cpu_batch)}
     if args.profile_kernels:
         for k, v in sorted(breakdown.items(), key=lambda kv: -kv[1]["ms"]):
             print(f"# {k:28s} {v['ms']:9.3f} ms  {v['n']:5d} launches", file=sys.stderr)

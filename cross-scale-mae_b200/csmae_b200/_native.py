@@ -55,6 +55,7 @@ SIGNATURES = {
     "csm_ntxent_bwd": [_P, _P, _P, _P, _P, _I, _I, _F, _F, _P],
     "csm_adamw_multi": [_P, _P, _I, _P, _I, _P],
     "csm_grad_stats_f32": [_P, _L, _P, _P, _I, _P],
+    "csm_sincos_pos_embed": [_P, _I, _I, _I, _P],
     "csm_amp_update": [_P, _P, _P, _P, _F, _F, _F, _I, _P],
     "csm_sumsq_f32": [_P, _L, _P, _I, _P],
 }

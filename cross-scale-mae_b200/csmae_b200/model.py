@@ -17,7 +17,7 @@ import torch
 import torch.nn as nn
 
 from .engine import CrossScaleStep, HotPathEngine
-from .pos_embed import get_2d_sincos_pos_embed
+from .pos_embed import get_2d_sincos_pos_embed, sincos_pos_embed_  # noqa: F401
 
 
 # ------------------------------------------------------------------------------------------------
@@ -160,10 +160,8 @@ class MAE_ViT_Baseline(nn.Module):
     # ---- init (MAE_ViT_Baseline.py:201-241) -------------------------------------------------------
     def initialize_weights(self):
         grid = int(self.patch_embed.num_patches ** 0.5)
-        self.encoder_pos_embed.data.copy_(torch.from_numpy(
-            get_2d_sincos_pos_embed(self.encoder_pos_embed.shape[-1], grid, cls_token=True)).float().unsqueeze(0))
-        self.decoder_pos_embed.data.copy_(torch.from_numpy(
-            get_2d_sincos_pos_embed(self.decoder_pos_embed.shape[-1], grid, cls_token=True)).float().unsqueeze(0))
+        sincos_pos_embed_(self.encoder_pos_embed.data, grid, cls_token=True)
+        sincos_pos_embed_(self.decoder_pos_embed.data, grid, cls_token=True)
         w = self.patch_embed.proj.weight.data
         torch.nn.init.xavier_uniform_(w.view([w.shape[0], -1]))
         torch.nn.init.normal_(self.cls_token, std=0.02)

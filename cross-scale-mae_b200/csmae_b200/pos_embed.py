@@ -4,8 +4,28 @@ Follows util/pos_embed.py:16-63 of the reference: row h*G + w is
 [sin(w*omega) | cos(w*omega) | sin(h*omega) | cos(h*omega)] with omega_k = 10000^(-k / (D/4)); the
 w-coordinate comes first because the reference builds its meshgrid w-first (pos_embed.py:24).
 Row 0 (cls token) is all zeros.
+
+`sincos_pos_embed_` fills a parameter in place: on a CUDA tensor through the C-ABI op `csm_sincos_pos_embed`
+(SURVEY.md 8b's operator list), on a CPU tensor (a module built on the host and moved later) through the numpy
+restatement below -- the two agree to the last fp32 bit except where fp64 libm differences straddle a rounding
+boundary (tests/test_kernels_gpu.py).
 """
 import numpy as np
+import torch
+
+
+def sincos_pos_embed_(param, grid_size, cls_token=True):
+    """param: [1, cls + G*G, D] fp32 tensor, filled in place (MAE_ViT_Baseline.py:203-218)."""
+    D = param.shape[-1]
+    if param.is_cuda:
+        from . import _native as nat
+        if not param.is_contiguous() or param.dtype != torch.float32:
+            raise nat.NativeError("sincos_pos_embed_: needs a contiguous fp32 tensor")
+        with torch.cuda.device(param.device):
+            nat.call("csm_sincos_pos_embed", param, D, grid_size, 1 if cls_token else 0)
+    else:
+        param.copy_(torch.from_numpy(get_2d_sincos_pos_embed(D, grid_size, cls_token)).float().unsqueeze(0))
+    return param
 
 
 def get_2d_sincos_pos_embed(embed_dim, grid_size, cls_token=False):

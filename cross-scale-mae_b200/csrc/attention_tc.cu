@@ -41,7 +41,7 @@ struct FwdParams {
   int B, S, H, Dm, HG;
   int pack;          // two images per 128-row tile (S <= 64)
   int QT, nb, BN;    // query tiles per image, key blocks, keys per block (multiple of 16)
-  int items;
+  int items, pairs;
   float c;           // d^-1/2 * log2(e)
   __nv_bfloat16* out;
   float* lse;
@@ -94,6 +94,14 @@ __device__ __forceinline__ void tmem_st_32x8(uint32_t taddr, const uint32_t* r) 
                "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
                : "memory");
 }
+__device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 // D[tmem] (+)= A[tmem, bf16 pairs packed along K] * B[smem desc]
 __device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
@@ -108,39 +116,61 @@ __device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, ui
       : "memory");
 }
 
-// DH: head dim (32: two heads per 64-column group, 64: one).  NG0 / NG1: 16-key groups of the two softmax threads of a
-// query row; the key block is BN = 16 * (NG0 + NG1) keys (208 = 96 + 112, so that the 197 keys of the decoder split
-// 96 / 101, or 128 = 64 + 64).  PTMEM: the probabilities go back to TMEM (over the score columns they came from) and
-// feed the P.V product as its TMEM A operand; otherwise they go through a 128-byte-swizzled shared-memory tile.
-template <int DH, int NG0, int NG1, bool PTMEM>
+// Work of one CTA = "pairs" (stride gridDim.x); a pair is two UNITS that run concurrently on the two softmax warp
+// groups: the two d = 32 heads of one (image, 64-column head group, query tile) item, which share the item's Q and
+// K / V tiles, or -- for d = 64, one head per 64-column group -- two consecutive items.
+struct FwdUnit {
+  int valid, item, hg, b, row_q0, row_q1, row_k0, row_k1;
+};
+template <int NH>
+__device__ __forceinline__ FwdUnit fwd_unit(const FwdParams& p, int pair, int w) {
+  FwdUnit u;
+  u.item = NH == 2 ? pair : 2 * pair + w;
+  u.valid = u.item < p.items && (NH == 1 || w < min(NH, p.H - ((p.pack ? u.item % p.HG : (u.item / p.QT) % p.HG)) * NH));
+  if (!p.pack) {
+    const int qt = u.item % p.QT;
+    const int r = u.item / p.QT;
+    u.hg = r % p.HG;
+    u.b = r / p.HG;
+    u.row_q0 = u.b * p.S + qt * 128;
+    u.row_k0 = u.b * p.S;
+    u.row_q1 = u.row_k1 = 0;
+  } else {
+    u.hg = u.item % p.HG;
+    u.b = 2 * (u.item / p.HG);
+    u.row_q0 = u.row_k0 = u.b * p.S;
+    u.row_q1 = u.row_k1 = (u.b + 1) * p.S;
+  }
+  return u;
+}
+
+// DH: head dim (32: two heads per 64-column group, 64: one).  BN: keys per block (multiple of 16; 208 covers the 197
+// keys of the decoder in one block).  The probabilities go back to TMEM over the score columns they came from (bf16
+// pairs) and feed the P.V product as its TMEM A operand.
+template <int DH, int BN>
 __global__ void __launch_bounds__(AT_THREADS, 1)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv,
                    const FwdParams p) {
   constexpr int NH = 64 / DH;          // heads per 64-column group
   constexpr int KS = DH / 16;          // 16-wide k-steps of one head in the Q / K rows
-  constexpr int OC = DH / 2;           // output columns owned by one softmax thread
-  constexpr int NG = NG0 > NG1 ? NG0 : NG1;
-  constexpr int BN = 16 * (NG0 + NG1); // keys per block
-  constexpr int BNH0 = 16 * NG0;       // keys of the first half
+  constexpr int NST = 4 / NH;          // shared-memory stages of the Q and of the K/V tiles
   constexpr int KV_BYTES = BN * 128;   // one K (or V) block
-  constexpr int PSLABS = PTMEM ? 0 : (BN + 63) / 64;
-  constexpr uint32_t COL_O = 2 * BN;   // O of key half h at COL_O + h * DH
+  constexpr uint32_t COL_O = 2 * BN;   // O of warp group g at COL_O + g * DH
   static_assert(2 * BN + 2 * DH <= 512, "TMEM budget");
+  static_assert(BN % 16 == 0, "key block");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sQ = smem;                                  // [2][16 KB]
-  uint8_t* sKV = smem + 2 * AT_QBYTES;                 // [2][K | V]
-  uint8_t* sP = sKV + 4 * KV_BYTES;                    // [PSLABS][128 rows][128 B]
-  float* xch = reinterpret_cast<float*>(sP + PSLABS * 16384);   // {max, sum} x parity x half x row
-  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(xch) + AT_XCH_BYTES);
-  uint64_t* q_full = bars;            // [2]
-  uint64_t* q_empty = bars + 2;       // [2]
-  uint64_t* kv_full = bars + 4;       // [2]
-  uint64_t* kv_empty = bars + 6;      // [2]
-  uint64_t* s_full = bars + 8;        // [2]
-  uint64_t* p_full = bars + 10;
-  uint64_t* o_full = bars + 11;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+  uint8_t* sQ = smem;                                  // [NST][16 KB]
+  uint8_t* sKV = smem + NST * AT_QBYTES;               // [NST][K | V]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sKV + NST * 2 * KV_BYTES);
+  uint64_t* q_full = bars;                 // [NST]
+  uint64_t* q_empty = bars + NST;          // [NST]
+  uint64_t* kv_full = bars + 2 * NST;      // [NST]
+  uint64_t* kv_empty = bars + 3 * NST;     // [NST]
+  uint64_t* s_full = bars + 4 * NST;       // [2]  per warp group
+  uint64_t* p_full = s_full + 2;           // [2]
+  uint64_t* o_full = s_full + 4;           // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_full + 6);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -148,15 +178,17 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmap_q);
     tma_prefetch_desc(&tmap_kv);
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < NST; ++i) {
       mbar_init(&q_full[i], 1);
-      mbar_init(&q_empty[i], 1);
+      mbar_init(&q_empty[i], NH);        // released by the last P.V of every unit that reads the tile
       mbar_init(&kv_full[i], 1);
-      mbar_init(&kv_empty[i], 1);
-      mbar_init(&s_full[i], 1);
+      mbar_init(&kv_empty[i], NH);
     }
-    mbar_init(p_full, AT_SM_WARPS);
-    mbar_init(o_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_full[i], 4);
+      mbar_init(&o_full[i], 1);
+    }
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -169,52 +201,48 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();
   pdl_trigger();
+  const int nb = p.nb;
 
-  // Iteration order inside a work item: heads of the group outermost, key blocks innermost.  With a single key block
-  // both heads share one K/V load; with several blocks the blocks are re-fetched per head (L2 hits).
-  const bool shared_kv = (p.nb == 1);
   if (warp < 4) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
     if (warp == 0) {
       // ------------------------------ TMA producer ------------------------------
       if (lane == 0) {
-        uint32_t ic = 0, kvc = 0;
-        for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++ic) {
-          int hg, row_q0, row_q1, row_k0, row_k1;
-          if (!p.pack) {
-            const int qt = item % p.QT;
-            const int r = item / p.QT;
-            hg = r % p.HG;
-            const int b = r / p.HG;
-            row_q0 = b * p.S + qt * 128;
-            row_k0 = b * p.S;
-            row_q1 = row_k1 = 0;
-          } else {
-            hg = item % p.HG;
-            const int pair = item / p.HG;
-            row_q0 = row_k0 = (2 * pair) * p.S;
-            row_q1 = row_k1 = (2 * pair + 1) * p.S;
-          }
-          const int nh = min(NH, p.H - hg * NH);
-          const uint32_t qs = ic & 1;
-          mbar_wait_wd(&q_empty[qs], ((ic >> 1) & 1) ^ 1);
+        uint32_t qc = 0, kvc = 0;
+        auto load_q = [&](const FwdUnit& u) {
+          const uint32_t qs = qc % NST;
+          mbar_wait_wd(&q_empty[qs], ((qc / NST) & 1) ^ 1);
           mbar_expect_tx(&q_full[qs], AT_QBYTES);
           uint8_t* q = sQ + qs * AT_QBYTES;
-          tma_load_2d(q, &tmap_q, &q_full[qs], hg * 64, row_q0);
-          if (p.pack) tma_load_2d(q + 8192, &tmap_q, &q_full[qs], hg * 64, row_q1);
-          const int nloads = shared_kv ? 1 : nh * p.nb;
-          for (int l = 0; l < nloads; ++l, ++kvc) {
-            const int j = shared_kv ? 0 : l % p.nb;
-            const uint32_t ks = kvc & 1;
-            mbar_wait_wd(&kv_empty[ks], ((kvc >> 1) & 1) ^ 1);
-            mbar_expect_tx(&kv_full[ks], 2u * KV_BYTES);
-            uint8_t* k = sKV + ks * 2 * KV_BYTES;
-            uint8_t* v = k + KV_BYTES;
-            tma_load_2d(k, &tmap_kv, &kv_full[ks], p.Dm + hg * 64, row_k0 + j * BN);
-            tma_load_2d(v, &tmap_kv, &kv_full[ks], 2 * p.Dm + hg * 64, row_k0 + j * BN);
-            if (p.pack) {
-              tma_load_2d(k + 8192, &tmap_kv, &kv_full[ks], p.Dm + hg * 64, row_k1);
-              tma_load_2d(v + 8192, &tmap_kv, &kv_full[ks], 2 * p.Dm + hg * 64, row_k1);
+          tma_load_2d(q, &tmap_q, &q_full[qs], u.hg * 64, u.row_q0);
+          if (p.pack) tma_load_2d(q + 8192, &tmap_q, &q_full[qs], u.hg * 64, u.row_q1);
+          ++qc;
+        };
+        auto load_kv = [&](const FwdUnit& u, int j) {
+          const uint32_t ks = kvc % NST;
+          mbar_wait_wd(&kv_empty[ks], ((kvc / NST) & 1) ^ 1);
+          mbar_expect_tx(&kv_full[ks], 2u * KV_BYTES);
+          uint8_t* k = sKV + ks * 2 * KV_BYTES;
+          uint8_t* v = k + KV_BYTES;
+          tma_load_2d(k, &tmap_kv, &kv_full[ks], p.Dm + u.hg * 64, u.row_k0 + j * BN);
+          tma_load_2d(v, &tmap_kv, &kv_full[ks], 2 * p.Dm + u.hg * 64, u.row_k0 + j * BN);
+          if (p.pack) {
+            tma_load_2d(k + 8192, &tmap_kv, &kv_full[ks], p.Dm + u.hg * 64, u.row_k1);
+            tma_load_2d(v + 8192, &tmap_kv, &kv_full[ks], 2 * p.Dm + u.hg * 64, u.row_k1);
+          }
+          ++kvc;
+        };
+        for (int pair = blockIdx.x; pair < p.pairs; pair += gridDim.x) {
+          const FwdUnit u0 = fwd_unit<NH>(p, pair, 0), u1 = fwd_unit<NH>(p, pair, 1);
+          if (NH == 2) {
+            load_q(u0);
+            for (int j = 0; j < nb; ++j) load_kv(u0, j);
+          } else {
+            load_q(u0);
+            if (u1.valid) load_q(u1);
+            for (int j = 0; j < nb; ++j) {
+              load_kv(u0, j);
+              if (u1.valid) load_kv(u1, j);
             }
           }
         }
@@ -222,263 +250,285 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
     } else if (warp == 1) {
       // ------------------------------ MMA issuer (one thread) ------------------------------
       if (lane == 0) {
-        constexpr uint32_t idesc_s = umma_idesc_bf16(128, BN, 0, 0);
         constexpr uint32_t idesc_o = umma_idesc_bf16(128, DH, 0, 1);
-        const uint32_t p_addr = smem_u32(sP);
-        uint32_t it = 0, ic = 0, kvc = 0;
-        // the P.V product of an iteration is issued after the NEXT S = Q K^T, so the softmax warps always find their
-        // next score tile ready
-        bool have_prev = false;
-        uint32_t pv_it = 0, pv_ks = 0, pv_qs = 0;
-        int pv_hh = 0;
-        bool pv_last_kv = false, pv_last_item = false;
-        auto issue_pv = [&]() {
-          mbar_wait_wd(p_full, pv_it & 1);
-          tc_fence_after();
-          const uint32_t v_addr = smem_u32(sKV + pv_ks * 2 * KV_BYTES + KV_BYTES) + (DH == 32 ? pv_hh * 64 : 0);
-          const uint32_t tmem_p = tmem_base + (pv_it & 1) * BN;
-#pragma unroll
-          for (int k = 0; k < NG0 + NG1; ++k) {        // each key half accumulates into its own O
-            const int hf = k >= NG0 ? 1 : 0, kh = k - hf * NG0;
-            const uint64_t db = umma_smem_desc_sw128(v_addr + k * 2048, 8192, 1024);
-            const uint32_t tmem_o = tmem_base + COL_O + hf * DH;
-            if (PTMEM) {
-              umma_f16_ts(tmem_o, tmem_p + hf * BNH0 + kh * 8, db, idesc_o, kh > 0 ? 1u : 0u);
-            } else {
-              const uint64_t da = umma_smem_desc_sw128(p_addr + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024);
-              umma_f16(tmem_o, da, db, idesc_o, kh > 0 ? 1u : 0u);
-            }
-          }
-          umma_commit(o_full);
-          if (pv_last_kv) umma_commit(&kv_empty[pv_ks]);
-          if (pv_last_item) umma_commit(&q_empty[pv_qs]);
+        // Sequence of (pair, key block, unit-of-pair) steps; unit w always runs on warp group w with score buffer w.
+        // Per step: S = Q K^T is issued two steps ahead of the P.V that consumes the same TMEM buffer, so a warp
+        // group finds its next score tile ready when it comes back from draining O.
+        struct Ent {
+          uint32_t q_addr, k_addr, v_addr, q_stage, kv_stage;
+          int hh, bn, last_j, valid, releases;
         };
-        for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++ic) {
-          const int hg = p.pack ? item % p.HG : (item / p.QT) % p.HG;
-          const int nh = min(NH, p.H - hg * NH);
-          const uint32_t qs = ic & 1;
-          mbar_wait_wd(&q_full[qs], (ic >> 1) & 1);
-          const uint32_t q_addr = smem_u32(sQ + qs * AT_QBYTES);
-          uint32_t ks = 0;
-          for (int hh = 0; hh < nh; ++hh) {
-            for (int j = 0; j < p.nb; ++j, ++it) {
-              if (!(shared_kv && hh > 0)) {
-                ks = kvc & 1;
-                mbar_wait_wd(&kv_full[ks], (kvc >> 1) & 1);
-                ++kvc;
-              }
-              tc_fence_after();
-              const uint32_t k_addr = smem_u32(sKV + ks * 2 * KV_BYTES);
-              const uint32_t tmem_s = tmem_base + (it & 1) * BN;
+        Ent ent[2];
+        ent[0].valid = ent[1].valid = 0;
+        uint32_t qc = 0, kvc = 0, cnt[2] = {0, 0};
+        uint32_t cur_q[2] = {0, 0}, cur_kv = 0;
+        // iteration state of the "S issue" cursor
+        int a_pair = blockIdx.x, a_j = 0, a_w = 0;
+        auto issue_s = [&]() -> bool {           // issues S for the next step of the sequence into buffer a_w
+          if (a_pair >= p.pairs) return false;
+          const int w = a_w;
+          const FwdUnit u = fwd_unit<NH>(p, a_pair, w);
+          Ent& e = ent[w];
+          e.valid = u.valid;
+          if (u.valid) {
+            if (a_j == 0 && (NH == 1 || w == 0)) {       // a new Q tile
+              const uint32_t qs = qc % NST;
+              mbar_wait_wd(&q_full[qs], (qc / NST) & 1);
+              ++qc;
+              cur_q[NH == 1 ? w : 0] = qs;
+            }
+            if (NH == 1 || w == 0) {                     // a new K / V block
+              const uint32_t ks = kvc % NST;
+              mbar_wait_wd(&kv_full[ks], (kvc / NST) & 1);
+              ++kvc;
+              cur_kv = ks;
+            }
+            e.q_stage = cur_q[NH == 1 ? w : 0];
+            e.kv_stage = cur_kv;
+            e.hh = NH == 2 ? w : 0;
+            e.q_addr = smem_u32(sQ + e.q_stage * AT_QBYTES);
+            e.k_addr = smem_u32(sKV + e.kv_stage * 2 * KV_BYTES);
+            e.v_addr = e.k_addr + KV_BYTES;
+            e.bn = p.pack ? 128 : min(BN, ((p.S - a_j * BN) + 15) & ~15);
+            e.last_j = (a_j == nb - 1);
+            // tiles shared by the two heads of a group are released by both units; a group with a single head
+            // (odd H) releases twice from its only unit
+            e.releases = (NH == 2 && w == 0 && !fwd_unit<NH>(p, a_pair, 1).valid) ? 2 : 1;
+            tc_fence_after();
+            const uint32_t idesc_s = umma_idesc_bf16(128, e.bn, 0, 0);
+            const uint32_t tmem_s = tmem_base + w * BN;
 #pragma unroll
-              for (int kk = 0; kk < KS; ++kk) {
-                const uint64_t da = umma_smem_desc_sw128(q_addr + (hh * KS + kk) * 32, 16, 1024);
-                const uint64_t db = umma_smem_desc_sw128(k_addr + (hh * KS + kk) * 32, 16, 1024);
-                umma_f16(tmem_s, da, db, idesc_s, kk > 0 ? 1u : 0u);
-              }
-              umma_commit(&s_full[it & 1]);
-              if (have_prev) issue_pv();
-              have_prev = true;
-              pv_it = it; pv_ks = ks; pv_qs = qs; pv_hh = hh;
-              pv_last_kv = shared_kv ? (hh == nh - 1) : true;
-              pv_last_item = (hh == nh - 1) && (j == p.nb - 1);
+            for (int kk = 0; kk < KS; ++kk) {
+              const uint64_t da = umma_smem_desc_sw128(e.q_addr + (e.hh * KS + kk) * 32, 16, 1024);
+              const uint64_t db = umma_smem_desc_sw128(e.k_addr + (e.hh * KS + kk) * 32, 16, 1024);
+              umma_f16(tmem_s, da, db, idesc_s, kk > 0 ? 1u : 0u);
+            }
+            umma_commit(&s_full[w]);
+          }
+          if (++a_w == 2) {
+            a_w = 0;
+            if (++a_j == nb) {
+              a_j = 0;
+              a_pair += gridDim.x;
             }
           }
+          return true;
+        };
+        auto issue_pv = [&](int w) {
+          Ent& e = ent[w];
+          if (!e.valid) return;
+          mbar_wait_wd(&p_full[w], cnt[w] & 1);
+          ++cnt[w];
+          tc_fence_after();
+          const uint32_t v_addr = e.v_addr + (DH == 32 ? e.hh * 64 : 0);
+          const uint32_t tmem_p = tmem_base + w * BN;
+          const uint32_t tmem_o = tmem_base + COL_O + w * DH;
+          const int ksteps = e.bn >> 4;
+          for (int k = 0; k < ksteps; ++k) {
+            const uint64_t db = umma_smem_desc_sw128(v_addr + k * 2048, 8192, 1024);
+            umma_f16_ts(tmem_o, tmem_p + k * 8, db, idesc_o, k > 0 ? 1u : 0u);
+          }
+          umma_commit(&o_full[w]);
+          for (int r = 0; r < e.releases; ++r) {
+            umma_commit(&kv_empty[e.kv_stage]);
+            if (e.last_j) umma_commit(&q_empty[e.q_stage]);
+          }
+        };
+        // prologue: the first step of both warp groups; then P.V of a step followed by S of the step after next
+        bool more = issue_s();
+        if (more) more = issue_s();
+        int w = 0;
+        // every issue_s() call fills ent[a_w] of the step it issued; P.V of that entry must be issued before the
+        // entry is overwritten by the S two steps later -- the loop below keeps exactly that order
+        while (ent[0].valid || ent[1].valid) {
+          issue_pv(w);
+          ent[w].valid = 0;
+          if (more) more = issue_s();      // refills ent[w] (the cursor's a_w == w here by construction)
+          w ^= 1;
         }
-        if (have_prev) issue_pv();
       }
     }
   } else {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
-    // ------------------------------ softmax warps ------------------------------
-    const int half = (warp - 4) >> 2;         // which half of the key block
+    // ------------------------------ softmax warp groups ------------------------------
+    const int g = (warp - 4) >> 2;            // warp group = unit of the pair = score buffer
     const int quarter = warp & 3;             // TMEM lane quarter this warp may access
     const int row = quarter * 32 + lane;
     const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
-    const int colbase = half * BNH0;
-    const int bnh = half ? 16 * NG1 : 16 * NG0;   // keys of this thread's half
     const float c = p.c;
-    float* xm = xch;                          // [parity][half][row]
-    float* xl = xch + 512;
-    const uint32_t p_row = smem_u32(sP) + row * 128;
-    const uint32_t sw7 = static_cast<uint32_t>(row & 7);
+    const uint32_t tmem_s = tmem_base + lane_off + g * BN;
+    const uint32_t tmem_o = tmem_base + lane_off + COL_O + g * DH;
+    uint32_t cnt = 0;
 
-    // online-softmax state of the head in flight; owned by drain()
-    float m_run = -INFINITY, l_run = 0.f;
-    float o_acc[OC];
-#pragma unroll
-    for (int i = 0; i < OC; ++i) o_acc[i] = 0.f;
-    uint32_t it = 0;
-    uint32_t have_prev;      // opaque to the compiler: keeps it from peeling the first iteration of the item loops
-    asm volatile("mov.u32 %0, 0;" : "=r"(have_prev));
-    bool prev_first = false, prev_last = false, prev_valid = false;
-    uint32_t prev_it = 0;
-    __nv_bfloat16* prev_out = nullptr;
-    float* prev_lse = nullptr;
-
-    // Fold the P.V result of iteration prev_it into the running output.  The two key halves were exponentiated
-    // against their OWN row maximum (no exchange before the exp): their partial outputs O_h and partial sums l_h are
-    // combined here with the factors exp2((m_h - m) * c).
-    auto drain = [&]() {
-      mbar_wait_wd(o_full, prev_it & 1);
-      tc_fence_after();
-      uint32_t o0[OC], o1[OC];
-      const uint32_t oaddr = tmem_base + lane_off + COL_O + half * OC;
-      tmem_ld_32x16(oaddr, o0);
-      tmem_ld_32x16(oaddr + DH, o1);
-      if (OC == 32) {
-        tmem_ld_32x16(oaddr + 16, o0 + (OC == 32 ? 16 : 0));
-        tmem_ld_32x16(oaddr + DH + 16, o1 + (OC == 32 ? 16 : 0));
-      }
-      const uint32_t xo = (prev_it & 1) * 256 + row;
-      const float m0 = xm[xo], m1 = xm[xo + 128], l0 = xl[xo], l1 = xl[xo + 128];
-      if (prev_first) {
-        m_run = -INFINITY;
-        l_run = 0.f;
-#pragma unroll
-        for (int i = 0; i < OC; ++i) o_acc[i] = 0.f;
-      }
-      const float m_new = fmaxf(m_run, fmaxf(m0, m1));
-      const float a = ex2f((m_run - m_new) * c), b0 = ex2f((m0 - m_new) * c), b1 = ex2f((m1 - m_new) * c);
-      l_run = fmaf(l_run, a, fmaf(l0, b0, l1 * b1));
-      m_run = m_new;
-      tmem_ld_wait();
-#pragma unroll
-      for (int i = 0; i < OC; ++i)
-        o_acc[i] = fmaf(o_acc[i], a, fmaf(__uint_as_float(o0[i]), b0, __uint_as_float(o1[i]) * b1));
-      if (prev_last && prev_valid) {
-        const float inv = 1.0f / l_run;
-#pragma unroll
-        for (int g = 0; g < OC / 8; ++g) {
-          uint4 pk;
-          pk.x = pack_bf16x2(o_acc[g * 8 + 0] * inv, o_acc[g * 8 + 1] * inv);
-          pk.y = pack_bf16x2(o_acc[g * 8 + 2] * inv, o_acc[g * 8 + 3] * inv);
-          pk.z = pack_bf16x2(o_acc[g * 8 + 4] * inv, o_acc[g * 8 + 5] * inv);
-          pk.w = pack_bf16x2(o_acc[g * 8 + 6] * inv, o_acc[g * 8 + 7] * inv);
-          *reinterpret_cast<uint4*>(prev_out + g * 8) = pk;
-        }
-        if (half == 0) *prev_lse = m_run * c + log2f(l_run);
-      }
-    };
-
-    for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
-      int hg, b, srow;
+#pragma unroll 1
+    for (int pair = blockIdx.x; pair < p.pairs; pair += gridDim.x) {
+      const FwdUnit u = fwd_unit<NH>(p, pair, g);
+      if (!u.valid) continue;
+      const int h = u.hg * NH + (NH == 2 ? g : 0);
+      int b, srow;
       if (!p.pack) {
-        const int qt = item % p.QT;
-        const int r = item / p.QT;
-        hg = r % p.HG;
-        b = r / p.HG;
-        srow = qt * 128 + row;
+        b = u.b;
+        srow = (u.item % p.QT) * 128 + row;
       } else {
-        hg = item % p.HG;
-        b = 2 * (item / p.HG) + (row >> 6);
+        b = u.b + (row >> 6);
         srow = row & 63;
       }
-      const int nh = min(NH, p.H - hg * NH);
       const bool row_valid = (srow < p.S) && (b < p.B);
-#pragma unroll 1
-      for (int hh = 0; hh < nh; ++hh) {
-        const int h = hg * NH + hh;
-#pragma unroll 1
-        for (int j = 0; j < p.nb; ++j, ++it) {
-          // valid keys of this thread's half (warp-uniform): nfull whole 16-key groups, then one partial group of
-          // rem keys (handled by its own 16 registers so that the unrolled loops carry no per-element masking), then
-          // groups that only receive zero probabilities
-          int kvalid = p.pack ? (((row >> 6) == half) ? p.S : 0) : (p.S - j * BN - colbase);
-          kvalid = max(0, min(kvalid, bnh));
-          const int nfull = kvalid >> 4;
-          const int rem = kvalid & 15;
-          const uint32_t buf = it & 1;
-          mbar_wait_wd(&s_full[buf], (it >> 1) & 1);
-          tc_fence_after();
-          uint32_t su[NG * 16], tu[16];
-          const uint32_t taddr = tmem_base + lane_off + buf * BN + colbase;
+      // warps whose 32 rows are all padding skip the arithmetic (their P / O rows are garbage nobody reads)
+      const bool warp_active = p.pack ? ((u.b + (quarter >> 1)) < p.B && (quarter & 1) * 32 < p.S)
+                                      : ((u.item % p.QT) * 128 + quarter * 32 < p.S);
+      float m_run = -INFINITY, l_run = 0.f;
+      float o_acc[DH];
 #pragma unroll
-          for (int g = 0; g < NG; ++g)
-            if (g < nfull) tmem_ld_32x16(taddr + g * 16, su + g * 16);
-          if (rem) tmem_ld_32x16(taddr + nfull * 16, tu);
-          tmem_ld_wait();
-          float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-          if (rem) {
+      for (int i = 0; i < DH; ++i) o_acc[i] = 0.f;
+#pragma unroll 1
+      for (int j = 0; j < nb; ++j, ++cnt) {
+        // this row's keys inside the block: columns [c0, c0 + kvalid); everything else of the block's bn columns
+        // receives zero probabilities
+        const int bn = p.pack ? 128 : min(BN, ((p.S - j * BN) + 15) & ~15);
+        const int c0 = p.pack ? (row >> 6) * 64 : 0;
+        const int kvalid = p.pack ? p.S : min(BN, p.S - j * BN);
+        mbar_wait_wd(&s_full[g], cnt & 1);
+        tc_fence_after();
+        float alpha = 1.f;
+        if (warp_active) {
+          // ---- pass 1: row maximum (the next chunk's TMEM load is in flight while a chunk is reduced)
+          float mx0 = -INFINITY, mx1 = -INFINITY;
+          {
+            uint32_t a[32], bq[32];
+            const int nch = (kvalid + 31) >> 5;
+            tmem_ld_32x32(tmem_s + c0, a);
+#pragma unroll 1
+            for (int ch = 0; ch < nch; ch += 2) {
+              tmem_ld_wait();
+              if (ch + 1 < nch) tmem_ld_32x32(tmem_s + c0 + (ch + 1) * 32, bq);
+              {
+                const int lim = kvalid - ch * 32;
+                if (lim >= 32) {
 #pragma unroll
-            for (int e = 0; e < 16; ++e) {
-              if (e >= rem) tu[e] = 0xff800000u;                   // -inf: p = 0
-              mx[e & 3] = fmaxf(mx[e & 3], __uint_as_float(tu[e]));
+                  for (int e = 0; e < 32; e += 2) {
+                    mx0 = fmaxf(mx0, __uint_as_float(a[e]));
+                    mx1 = fmaxf(mx1, __uint_as_float(a[e + 1]));
+                  }
+                } else {
+#pragma unroll
+                  for (int e = 0; e < 32; ++e)
+                    if (e < lim) mx0 = fmaxf(mx0, __uint_as_float(a[e]));
+                }
+              }
+              if (ch + 1 < nch) {
+                tmem_ld_wait();
+                if (ch + 2 < nch) tmem_ld_32x32(tmem_s + c0 + (ch + 2) * 32, a);
+                const int lim = kvalid - (ch + 1) * 32;
+                if (lim >= 32) {
+#pragma unroll
+                  for (int e = 0; e < 32; e += 2) {
+                    mx0 = fmaxf(mx0, __uint_as_float(bq[e]));
+                    mx1 = fmaxf(mx1, __uint_as_float(bq[e + 1]));
+                  }
+                } else {
+#pragma unroll
+                  for (int e = 0; e < 32; ++e)
+                    if (e < lim) mx0 = fmaxf(mx0, __uint_as_float(bq[e]));
+                }
+              }
             }
           }
+          const float m_new = fmaxf(m_run, fmaxf(mx0, mx1));
+          alpha = ex2f((m_run - m_new) * c);
+          m_run = m_new;
+          const float mc = m_new * c;
+          // ---- pass 2: p = exp2(s*c - m*c) -> bf16 pairs, written over the score columns the P.V product reads as
+          // its A operand (16-key groups, two per chunk); the next chunk's TMEM load is in flight meanwhile
+          float ls0 = 0.f, ls1 = 0.f;
+          const int ngroups = bn >> 4;                 // 16-key groups the P.V product reads
+          const int g0 = c0 >> 4;                      // first group of this row's keys
+          const int nch2 = (ngroups + 1) >> 1;
+          auto chunk = [&](const uint32_t* s, int ch) {
+            uint32_t pk[16];
+            const int gi = 2 * ch;
+            const int k0 = (gi - g0) * 16;             // key index (within this row's keys) of s[0]
+            const bool two = gi + 1 < ngroups;
+            const int lim = kvalid - k0;               // valid keys from s[0] on (may be <= 0 or >= 32)
+            if (k0 >= 0 && (lim >= 32 || (!two && lim >= 16))) {
 #pragma unroll
-          for (int g = 0; g < NG; ++g) {
-            if (g < nfull) {
-#pragma unroll
-              for (int e = 0; e < 16; ++e) mx[e & 3] = fmaxf(mx[e & 3], __uint_as_float(su[g * 16 + e]));
-            }
-          }
-          const float m_h = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
-          const float mc = m_h * c;
-          if (!PTMEM && have_prev) drain();              // also: the P tile in shared memory is free again
-          float ls[4] = {0.f, 0.f, 0.f, 0.f};
-          auto store_p = [&](int g, const uint32_t* pk) {
-            if (PTMEM) {
-              tmem_st_32x8(taddr + g * 8, pk);
-            } else {
-              const uint32_t gc = static_cast<uint32_t>((colbase >> 3) + 2 * g);
-              sts_v4(p_row + (gc >> 3) * 16384 + (((gc & 7) ^ sw7) << 4), make_uint4(pk[0], pk[1], pk[2], pk[3]));
-              sts_v4(p_row + ((gc + 1) >> 3) * 16384 + ((((gc + 1) & 7) ^ sw7) << 4),
-                     make_uint4(pk[4], pk[5], pk[6], pk[7]));
-            }
-          };
-#pragma unroll
-          for (int g = 0; g < NG; ++g) {
-            uint32_t pk[8];
-            if (g < nfull) {
-#pragma unroll
-              for (int e = 0; e < 8; ++e) {
-                const float e0 = ex2f(fmaf(__uint_as_float(su[g * 16 + 2 * e]), c, -mc));
-                const float e1 = ex2f(fmaf(__uint_as_float(su[g * 16 + 2 * e + 1]), c, -mc));
-                ls[e & 3] += e0 + e1;
+              for (int e = 0; e < 16; ++e) {
+                const float e0 = ex2f(fmaf(__uint_as_float(s[2 * e]), c, -mc));
+                const float e1 = ex2f(fmaf(__uint_as_float(s[2 * e + 1]), c, -mc));
+                ls0 += e0;
+                ls1 += e1;
                 pk[e] = pack_bf16x2(e0, e1);
               }
-              store_p(g, pk);
-            } else if (g * 16 < bnh && (g > nfull || rem == 0)) {
+            } else if (k0 >= 0 && lim > 0) {
 #pragma unroll
-              for (int e = 0; e < 8; ++e) pk[e] = 0u;
-              store_p(g, pk);
+              for (int e = 0; e < 16; ++e) {
+                const float e0 = (2 * e < lim) ? ex2f(fmaf(__uint_as_float(s[2 * e]), c, -mc)) : 0.f;
+                const float e1 = (2 * e + 1 < lim) ? ex2f(fmaf(__uint_as_float(s[2 * e + 1]), c, -mc)) : 0.f;
+                ls0 += e0;
+                ls1 += e1;
+                pk[e] = pack_bf16x2(e0, e1);
+              }
+            } else {                                   // the other image's keys (packed tiles): zero probabilities
+#pragma unroll
+              for (int e = 0; e < 16; ++e) pk[e] = 0u;
+            }
+            if (two) tmem_st_32x16(tmem_s + gi * 8, pk);
+            else tmem_st_32x8(tmem_s + gi * 8, pk);
+          };
+          {
+            uint32_t sa[32], sb[32];
+            tmem_ld_32x32(tmem_s, sa);
+#pragma unroll 1
+            for (int ch = 0; ch < nch2; ch += 2) {
+              tmem_ld_wait();
+              if (ch + 1 < nch2) tmem_ld_32x32(tmem_s + (ch + 1) * 32, sb);
+              chunk(sa, ch);
+              if (ch + 1 < nch2) {
+                tmem_ld_wait();
+                if (ch + 2 < nch2) tmem_ld_32x32(tmem_s + (ch + 2) * 32, sa);
+                chunk(sb, ch + 1);
+              }
             }
           }
-          if (rem) {
-            uint32_t pk[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              const float e0 = ex2f(fmaf(__uint_as_float(tu[2 * e]), c, -mc));
-              const float e1 = ex2f(fmaf(__uint_as_float(tu[2 * e + 1]), c, -mc));
-              ls[e & 3] += e0 + e1;
-              pk[e] = pack_bf16x2(e0, e1);
-            }
-            store_p(nfull, pk);
-          }
-          const uint32_t xo = buf * 256 + half * 128 + row;
-          xm[xo] = m_h;
-          xl[xo] = (ls[0] + ls[1]) + (ls[2] + ls[3]);
-          if (PTMEM) {
-            if (have_prev) drain();
-            tmem_st_wait();
-          } else {
-            fence_proxy_async();
-          }
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(p_full);
-          have_prev = 1;
-          prev_it = it;
-          prev_first = (j == 0);
-          prev_last = (j == p.nb - 1);
-          prev_valid = row_valid;
-          prev_out = p.out + (static_cast<size_t>(b) * p.S + srow) * p.Dm + h * DH + half * OC;
-          prev_lse = p.lse + (static_cast<size_t>(b) * p.H + h) * p.S + srow;
+          l_run = fmaf(l_run, alpha, ls0 + ls1);
+          tmem_st_wait();
         }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[g]);
+        // ---- O of this block
+        mbar_wait_wd(&o_full[g], cnt & 1);
+        tc_fence_after();
+        if (warp_active) {
+          uint32_t o[DH];
+#pragma unroll
+          for (int q = 0; q < DH / 16; ++q) tmem_ld_32x16(tmem_o + q * 16, o + q * 16);
+          tmem_ld_wait();
+          if (nb == 1) {
+#pragma unroll
+            for (int i = 0; i < DH; ++i) o_acc[i] = __uint_as_float(o[i]);
+          } else {
+#pragma unroll
+            for (int i = 0; i < DH; ++i) o_acc[i] = fmaf(o_acc[i], alpha, __uint_as_float(o[i]));
+          }
+        }
+        tc_fence_before();
+      }
+      if (row_valid) {
+        const float inv = 1.0f / l_run;
+        __nv_bfloat16* dst = p.out + (static_cast<size_t>(b) * p.S + srow) * p.Dm + h * DH;
+#pragma unroll
+        for (int q8 = 0; q8 < DH / 8; ++q8) {
+          uint4 pk;
+          pk.x = pack_bf16x2(o_acc[q8 * 8 + 0] * inv, o_acc[q8 * 8 + 1] * inv);
+          pk.y = pack_bf16x2(o_acc[q8 * 8 + 2] * inv, o_acc[q8 * 8 + 3] * inv);
+          pk.z = pack_bf16x2(o_acc[q8 * 8 + 4] * inv, o_acc[q8 * 8 + 5] * inv);
+          pk.w = pack_bf16x2(o_acc[q8 * 8 + 6] * inv, o_acc[q8 * 8 + 7] * inv);
+          *reinterpret_cast<uint4*>(dst + q8 * 8) = pk;
+        }
+        p.lse[(static_cast<size_t>(b) * p.H + h) * p.S + srow] = m_run * c + log2f(l_run);
       }
     }
-    if (have_prev) drain();
   }
 
   __syncwarp();
@@ -500,9 +550,10 @@ int device_sms() {
   return sms;
 }
 
-template <int DH, int NG0, int NG1, bool PTMEM>
+template <int DH, int BN>
 int attn_fwd_tc_launch(const void* qkv, void* out, float* lse, int B, int S, int H, cudaStream_t stream) {
-  constexpr int BN = 16 * (NG0 + NG1);
+  constexpr int NH = 64 / DH;
+  constexpr int NST = 4 / NH;
   const int Dm = H * DH;
   FwdParams p{};
   p.B = B; p.S = S; p.H = H; p.Dm = Dm;
@@ -517,12 +568,12 @@ int attn_fwd_tc_launch(const void* qkv, void* out, float* lse, int B, int S, int
     p.QT = (S + 127) / 128;
     p.items = B * p.HG * p.QT;
   }
+  p.pairs = NH == 2 ? p.items : (p.items + 1) / 2;
   p.c = 1.4426950408889634f / sqrtf(static_cast<float>(DH));
   p.out = reinterpret_cast<__nv_bfloat16*>(out);
   p.lse = lse;
-  constexpr int PSLABS = PTMEM ? 0 : (BN + 63) / 64;
-  const size_t smem = 1024 + 2 * AT_QBYTES + 4 * static_cast<size_t>(BN) * 128 + PSLABS * 16384 + AT_XCH_BYTES + 128;
-  auto kern = attn_fwd_tc_kernel<DH, NG0, NG1, PTMEM>;
+  const size_t smem = 1024 + NST * (AT_QBYTES + 2 * static_cast<size_t>(BN) * 128) + 256;
+  auto kern = attn_fwd_tc_kernel<DH, BN>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
@@ -537,7 +588,7 @@ int attn_fwd_tc_launch(const void* qkv, void* out, float* lse, int B, int S, int
   if (rc) return rc;
   rc = csm_tensor_map_2d(&tkv, qkv, 3ull * Dm, static_cast<uint64_t>(B) * S, 3ull * Dm, 64, p.pack ? 64 : BN, 2, 128);
   if (rc) return rc;
-  const int grid = p.items < device_sms() ? p.items : device_sms();
+  const int grid = p.pairs < device_sms() ? p.pairs : device_sms();
   cudaError_t le = csm_launch_pdl(kern, dim3(grid), dim3(AT_THREADS), smem, stream, tq, tkv, p);
   if (le != cudaSuccess) {
     csm_set_error("attention_fwd: launch failed: %s", cudaGetErrorString(le));
@@ -1096,24 +1147,17 @@ int attn_bwd_tc_launch(const void* qkv, const void* o, const void* d_out, const 
 extern "C" int csm_colsum_bf16(const void* dy_bf16, float* db, int rows, int N, int skip_period, int num_sms,
                                cudaStream_t stream);
 
-// variant: 0 = probabilities through TMEM (A operand of P.V from TMEM), 1 = through shared memory (diagnostic)
+// (variant is ignored: the shared-memory P path of the first version is gone; kept for tools/attn_tc_check.py)
 extern "C" int csm_attention_fwd_tc(const void* qkv_bf16, void* out_bf16, float* lse, int B, int S, int H, int head_dim,
                                     int variant, cudaStream_t stream) {
+  (void)variant;
   CSM_CHECK_ARG(B > 0 && S > 0 && H > 0, "csm_attention_fwd: bad sizes B=%d S=%d H=%d", B, S, H);
   CSM_CHECK_ARG((H * head_dim) % 8 == 0, "csm_attention_fwd: H * head_dim must be a multiple of 8");
-  const bool tm = variant == 0;
   if (head_dim == 32) {
-    if (S <= 128) {
-      return tm ? attn_fwd_tc_launch<32, 4, 4, true>(qkv_bf16, out_bf16, lse, B, S, H, stream)
-                : attn_fwd_tc_launch<32, 4, 4, false>(qkv_bf16, out_bf16, lse, B, S, H, stream);
-    }
-    return tm ? attn_fwd_tc_launch<32, 6, 7, true>(qkv_bf16, out_bf16, lse, B, S, H, stream)
-              : attn_fwd_tc_launch<32, 6, 7, false>(qkv_bf16, out_bf16, lse, B, S, H, stream);
+    if (S <= 128) return attn_fwd_tc_launch<32, 128>(qkv_bf16, out_bf16, lse, B, S, H, stream);
+    return attn_fwd_tc_launch<32, 208>(qkv_bf16, out_bf16, lse, B, S, H, stream);
   }
-  if (head_dim == 64) {
-    return tm ? attn_fwd_tc_launch<64, 4, 4, true>(qkv_bf16, out_bf16, lse, B, S, H, stream)
-              : attn_fwd_tc_launch<64, 4, 4, false>(qkv_bf16, out_bf16, lse, B, S, H, stream);
-  }
+  if (head_dim == 64) return attn_fwd_tc_launch<64, 128>(qkv_bf16, out_bf16, lse, B, S, H, stream);
   csm_set_error("csm_attention_fwd: head_dim must be 32 or 64 (got %d)", head_dim);
   return CSM_ERR_ARG;
 }

@@ -9,6 +9,8 @@
 // no tensor cores.  Index outputs are bit-exact against a stable argsort.
 #include "common.cuh"
 
+#include <algorithm>
+
 namespace {
 using namespace csm;
 
@@ -286,6 +288,41 @@ __global__ void resized_crop_kernel(const float* __restrict__ imgs, float* __res
 }
 
 }  // namespace
+
+// Fixed 2-D sin-cos position table (util/pos_embed.py:16-63), init-time: out[row, :] for row = cls + h*G + w is
+// [sin(w*om) | cos(w*om) | sin(h*om) | cos(h*om)], om_k = 10000^(-k / (D/4)) -- the reference's meshgrid is w-first
+// (pos_embed.py:24).  Evaluated in fp64 like numpy and rounded once to fp32; the cls row is zero.
+namespace {
+__global__ void sincos_pos_embed_kernel(float* __restrict__ out, int D, int G, int cls) {
+  const int quarter = D / 4;
+  const long long total = static_cast<long long>(G) * G * quarter;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int k = static_cast<int>(idx % quarter);
+    const int pos = static_cast<int>(idx / quarter);
+    const double om = 1.0 / pow(10000.0, static_cast<double>(k) / static_cast<double>(quarter));
+    const double aw = static_cast<double>(pos % G) * om, ah = static_cast<double>(pos / G) * om;
+    float* row = out + static_cast<size_t>(pos + cls) * D;
+    row[k] = static_cast<float>(sin(aw));
+    row[quarter + k] = static_cast<float>(cos(aw));
+    row[2 * quarter + k] = static_cast<float>(sin(ah));
+    row[3 * quarter + k] = static_cast<float>(cos(ah));
+  }
+  if (cls && blockIdx.x == 0)
+    for (int c = threadIdx.x; c < D; c += blockDim.x) out[c] = 0.f;
+}
+}  // namespace
+
+extern "C" int csm_sincos_pos_embed(float* out, int embed_dim, int grid_size, int cls_token, cudaStream_t stream) {
+  CSM_CHECK_ARG(out != nullptr && grid_size > 0, "csm_sincos_pos_embed: bad arguments");
+  CSM_CHECK_ARG(embed_dim > 0 && embed_dim % 4 == 0, "csm_sincos_pos_embed: embed_dim must be divisible by 4 (got %d)",
+                embed_dim);
+  const long long total = static_cast<long long>(grid_size) * grid_size * (embed_dim / 4);
+  const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, 148 * 8));
+  sincos_pos_embed_kernel<<<blocks, 256, 0, stream>>>(out, embed_dim, grid_size, cls_token ? 1 : 0);
+  CSM_CHECK_LAUNCH("sincos_pos_embed");
+  return CSM_OK;
+}
 
 extern "C" int csm_resized_crop(const float* imgs, float* out, int planes, int H, int W, int top, int left, int h,
                                 int w, int S, cudaStream_t stream) {

@@ -74,6 +74,9 @@ int csm_random_masking(const float* noise, int nimg, int L, int keep, long long*
  * imgs [planes = N*C, H, W] resized to [planes, S, S] with torchvision's bilinear + antialias filter */
 int csm_resized_crop(const float* imgs, float* out, int planes, int H, int W, int top, int left, int h, int w, int S,
                      csm_stream_t stream);
+/* fixed 2-D sin-cos position table [cls_token + G*G, embed_dim] f32 (util/pos_embed.py:16-63; w-coordinate first, cls
+ * row zero), evaluated in fp64 and rounded once -- init-time (MAE_ViT_Baseline.py:203-218) */
+int csm_sincos_pos_embed(float* out, int embed_dim, int grid_size, int cls_token, csm_stream_t stream);
 /* kept patches -> GEMM operand rows [(nimg*(keep+1)), C*p*p] in Conv2d (c,py,px) order; cls slot rows zero
  * (timm PatchEmbed conv, MAE_ViT_Baseline.py:75-77,245, fused with the masking gather :251) */
 int csm_patch_gather(const float* imgs, const int* ids_shuffle, void* out_bf16, int nimg, int C, int H, int p, int L,

@@ -655,3 +655,22 @@ def test_grad_stats_and_amp_update(nat):
     assert ctl[1].item() == 1.0 and state.tolist()[:3] == [1024.0, 0.0, 1.0 / 1024.0]
     # csm_adamw_multi leaves everything untouched when found_inf is set (covered end to end in
     # test_native_scaler_matches_reference_scaler)
+
+
+@pytest.mark.parametrize("D,G,cls", [(768, 14, 1), (512, 14, 1), (1024, 28, 1), (64, 6, 0)])
+def test_sincos_pos_embed(nat, D, G, cls):
+    """csm_sincos_pos_embed against the numpy restatement of util/pos_embed.py:16-63 (itself pinned bit-for-bit to the
+    live reference by tests/test_host_cpu.py): both evaluate in fp64 and round once, so the fp32 tables agree except
+    where the two libms' last-bit differences straddle an fp32 rounding boundary (at most 1 ulp, a handful of
+    entries)."""
+    from csmae_b200.pos_embed import get_2d_sincos_pos_embed, sincos_pos_embed_
+    want = torch.from_numpy(get_2d_sincos_pos_embed(D, G, cls_token=bool(cls))).float()
+    out = torch.full((1, cls + G * G, D), float("nan"), device="cuda")
+    sincos_pos_embed_(out, G, cls_token=bool(cls))
+    got = out[0].cpu()
+    diff = (got - want).abs()
+    exact = (got == want).float().mean().item()
+    print(f"D={D} G={G}: {exact * 100:.4f} % of entries bit-identical, max diff {diff.max().item():.3e}")
+    assert diff.max().item() <= 1.2e-7 and exact >= 0.999
+    if cls:
+        assert torch.equal(got[0], torch.zeros(D))
