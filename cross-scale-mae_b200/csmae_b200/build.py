@@ -20,6 +20,8 @@ STAMP = os.path.join(LIB_DIR, "build.stamp")
 SOURCES = ["runtime.cu", "gemm_tcgen05.cu", "attention.cu", "attention_tc.cu", "layernorm.cu", "masking.cu", "losses.cu", "optim.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC"]
+# development switches, e.g. CSM_NVCC_EXTRA="-DCSM_ATTN_TIMING" (per-phase cycle counters, tools/attn_phase.py)
+NVCC_FLAGS += os.environ.get("CSM_NVCC_EXTRA", "").split()
 
 
 def _nvcc():
