@@ -606,11 +606,12 @@ def test_native_scaler_matches_reference_scaler():
     # the moments see every unscaled (and, at the clipped step, clipped: coefficient ~0.03) gradient: a wrong
     # multiplier, a missed clip or a step that should have been skipped shows up here at O(1)
     assert rel_l2(ours["m1"], ref["m1"]) < 2e-2 and rel_l2(ours["m2"], ref["m2"]) < 2e-2
-    # zero-initialised biases consist of the six Adam updates only (each ~lr in size whatever the gradient's
-    # magnitude): bf16-level gradient differences move them by a few 1e-3 relative; a missed or extra update would
-    # be 1/6 of their norm
+    # weight matrices only: Adam normalises every element's gradient, so elements whose true gradient is zero (the
+    # key part of attn.qkv.bias -- softmax is invariant to a key bias -- or zero-initialised biases behind it) move
+    # by +-lr with the sign of the ROUNDING noise, which legitimately differs between the two arms
     for n, w in ref["w"].items():
-        assert rel_l2(ours["w"][n], w) < 2e-2, n
+        if w.ndim >= 2 and w.shape[0] > 1:
+            assert rel_l2(ours["w"][n], w) < 1e-3, (n, rel_l2(ours["w"][n], w))
     # resume: the state dict loads into either scaler
     s2 = csmae_b200.NativeScalerWithGradNormCount()
     s2.load_state_dict(ref["sd"])

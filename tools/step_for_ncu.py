@@ -9,7 +9,8 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "cross-scale-mae_b200"))
-os.environ["CSMAE_CUDA_GRAPHS"] = "0"
+GRAPHS = os.environ.get("CSM_NCU_GRAPHS", "0") == "1"      # 1: profile one step replayed from CUDA graphs instead
+os.environ["CSMAE_CUDA_GRAPHS"] = "1" if GRAPHS else "0"
 import torch  # noqa: E402
 import csmae_b200  # noqa: E402
 
@@ -33,7 +34,7 @@ def step():
     return loss
 
 
-for _ in range(3):
+for _ in range(8 if GRAPHS else 3):
     step()
 torch.cuda.synchronize()
 torch.cuda.cudart().cudaProfilerStart()
