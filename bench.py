@@ -330,6 +330,9 @@ def measure(env, args, arch, B, S, steps, warmup, full):
     launches0 = _native.launch_count
     ms_step = env.timed(lambda: step(imgs1, imgs2), steps)
     launches = _native.launch_count - launches0
+    if getattr(args, "quick", False):
+        sampler.stop()
+        return {"arch": arch, "batch": B, "size": S, "ms_step": ms_step, "launches": launches, "clocks": sampler.summary()}
 
     # end to end through the public API: every step's batch starts in pinned HOST memory, is copied to the
     # device (csmae_b200.DevicePrefetcher: the copy of step i+1 runs on a side stream while step i trains),
@@ -474,6 +477,7 @@ def main():
     ap.add_argument("--no-extra", action="store_true", help="skip the ViT-L/224 and ViT-L/448 extra_configs")
     ap.add_argument("--torch-ddp", action="store_true", help="N>1: wrap with torch's DistributedDataParallel")
     ap.add_argument("--torch-adamw", action="store_true", help="torch.optim.AdamW(fused=True) instead of FusedAdamW")
+    ap.add_argument("--quick", action="store_true", help="development: device-resident ms/step only, one short line")
     ap.add_argument("--profile-kernels", action="store_true", help="print the per-kernel CUDA-event breakdown")
     args = ap.parse_args()
     default_workload = args.arch == "base" and args.batch is None and args.input_size == 224
@@ -487,6 +491,14 @@ def main():
     world, rank = env.world, env.rank
     B, S = args.batch, args.input_size
     m = measure(env, args, args.arch, B, S, args.steps, args.warmup, full=True)
+    if args.quick:
+        if rank == 0:
+            m["images_per_s"] = B * world / (m["ms_step"] * 1e-3)
+            m["env"] = {k: v for k, v in os.environ.items() if k.startswith("CSMAE_")}
+            print(json.dumps(m), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
+        return
     extras = []
     if default_workload and not args.no_extra:
         # BASELINE.json configs[2] (ViT-L/16 224, bs 32/GPU) and configs[4] (ViT-L/16 448, bs 16/GPU): short runs of

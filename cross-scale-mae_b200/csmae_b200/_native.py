@@ -80,7 +80,8 @@ class NativeError(RuntimeError):
 
 
 def library_path():
-    return _build.LIB_PATH
+    # CSMAE_LIB: a development build of the same library (e.g. the -DCSM_ATTN_TIMING variant of tools/attn_phase.py)
+    return os.environ.get("CSMAE_LIB") or _build.LIB_PATH
 
 
 def load():

@@ -129,6 +129,16 @@ class HotPathEngine:
         self.stream_k_mode = os.environ.get("CSMAE_STREAM_K", "0")        # "0" | "1" (fwd + bwd) | "fwd"
         self._side = {}
         self._side_dirty = False
+        # Row chains (see _parts; opt-in, CSMAE_CHAINS=2): the images of a step are split into two halves whose
+        # encoder / decoder block chains run on two streams -- nothing in a Block mixes samples, so the halves are
+        # independent until the losses, and while one half drains the tail of a kernel the other half's next kernel
+        # could take the idle SMs.  Measured on B200 (profiles/r2e_chains_ab.jsonl): slower on every workload
+        # (ViT-B 13.94 -> 14.46 ms, ViT-L 14.67 -> 16.53 ms): the half-size GEMMs lose more to tile quantisation and
+        # fixed cost per launch than the overlap returns, so the default stays one chain.
+        self.num_chains = max(1, min(2, int(os.environ.get("CSMAE_CHAINS", "1"))))
+        self.chain_min_images = 8            # below this a step is launch-bound, not tail-bound: one chain
+        self._chain = {}
+        self._chain_forked = False
         self._sync_enabled = False  # overlapped gradient all-reduce (parallel.py)
         self._sync_group = None     # its process group (None = the default group)
         self._sync_world = 1
@@ -153,18 +163,56 @@ class HotPathEngine:
             self._side[dev] = s
         return s
 
-    def _on_side(self, dev, fn):
+    def _on_side(self, dev, fn, after=None):
+        """Runs fn on the side stream once everything issued so far on the current stream (and on the streams in
+        `after`: the row chains that produced what fn reads) has completed."""
         if not self.use_side_stream:
+            for s in after or ():
+                self._wait(torch.cuda.current_stream(dev), s)
             fn()
             return
-        main = torch.cuda.current_stream(dev)
         side = self._side_stream(dev)
-        ev = torch.cuda.Event()
-        ev.record(main)
-        side.wait_event(ev)
+        self._wait(side, torch.cuda.current_stream(dev))
+        for s in after or ():
+            self._wait(side, s)
         with torch.cuda.stream(side):
             fn()
         self._side_dirty = True
+
+    @staticmethod
+    def _wait(waiter, producer):
+        if waiter is producer or waiter == producer:
+            return
+        ev = torch.cuda.Event()
+        ev.record(producer)
+        waiter.wait_event(ev)
+
+    # ------------------------------------------------------------------ row chains
+    def _chain_stream(self, dev):
+        s = self._chain.get(dev)
+        if s is None:
+            s = torch.cuda.Stream(device=dev)
+            self._chain[dev] = s
+        return s
+
+    def _parts(self, NB, dev):
+        """[(stream, first image, images)] of the row chains: chain 0 runs on the caller's stream, chain 1 on a second
+        stream (forked / joined by events, captured into the same CUDA graphs)."""
+        main = torch.cuda.current_stream(dev)
+        if self.num_chains < 2 or NB < 2 * self.chain_min_images:
+            return [(main, 0, NB)]
+        h = NB // 2
+        return [(main, 0, h), (self._chain_stream(dev), h, NB - h)]
+
+    def _fork(self, parts):
+        """Chain streams start after everything issued so far on the caller's stream."""
+        for s, *_ in parts[1:]:
+            self._wait(s, parts[0][0])
+
+    def _join(self, parts):
+        """The caller's stream continues after every chain."""
+        for s, *_ in parts[1:]:
+            self._wait(parts[0][0], s)
 
     def _join_side(self, dev):
         if self.use_side_stream and self._side_dirty:
@@ -379,27 +427,40 @@ class HotPathEngine:
              NB, L, keep, D)
 
         # ---- encoder blocks; encoder_norm is computed-and-discarded upstream: skipped (Baseline.py:264)
-        x = self._blocks_fwd("enc", "encoder", len(m.encoder), x, NB, Se, D, m.encoder_num_heads, params, w16, dev)
+        # From here to the decoder's prediction the images are independent: the row chains (see _parts) run
+        # concurrently, each on its own stream over its own rows of the same buffers.
+        parts = self._parts(NB, dev)
+        self._fork(parts)
+        x = self._blocks_fwd("enc", "encoder", len(m.encoder), x, parts, Se, D, m.encoder_num_heads, params, w16, dev,
+                             NB)
         enc_bf16 = buf("enc_bf16", (NB * Se, D), bf16)
-        call("csm_cast_f32_bf16", x, enc_bf16, NB * Se * D)
 
         # ---- decoder (Baseline.py:268-297) -----------------------------------------------------
         demb = buf("demb", (NB * Se, Dd), bf16)
-        call("csm_linear_fwd", enc_bf16, w16["decoder_embed.weight"], params["decoder_embed.bias"], demb, None,
-             NB * Se, Dd, D, EPI_BF16)
         y = buf("dec.x0", (NB * Sd, Dd), f32)
-        call("csm_decoder_assemble", demb, ids_restore, params["mask_token"], params["decoder_pos_embed"], y,
-             NB, L, keep, Dd)
-        y = self._blocks_fwd("dec", "decoder", len(m.decoder), y, NB, Sd, Dd, m.decoder_num_heads, params, w16, dev)
+        for cs, b0, nb in parts:
+            e0, e1, d0, d1 = b0 * Se, (b0 + nb) * Se, b0 * Sd, (b0 + nb) * Sd
+            with torch.cuda.stream(cs):
+                call("csm_cast_f32_bf16", x[e0:e1], enc_bf16[e0:e1], nb * Se * D)
+                call("csm_linear_fwd", enc_bf16[e0:e1], w16["decoder_embed.weight"], params["decoder_embed.bias"],
+                     demb[e0:e1], None, nb * Se, Dd, D, EPI_BF16)
+                call("csm_decoder_assemble", demb[e0:e1], ids_restore[b0:b0 + nb], params["mask_token"],
+                     params["decoder_pos_embed"], y[d0:d1], nb, L, keep, Dd)
+        y = self._blocks_fwd("dec", "decoder", len(m.decoder), y, parts, Sd, Dd, m.decoder_num_heads, params, w16, dev,
+                             NB)
         dec_f32 = buf("dec_f32", (NB * Sd, Dd), f32)
         dec_bf16 = buf("dec_bf16", (NB * Sd, Dd), bf16)
         dn_mean = buf("dn_mean", (NB * Sd,), f32)
         dn_rstd = buf("dn_rstd", (NB * Sd,), f32)
-        call("csm_layernorm_fwd", y, params["decoder_norm.weight"], params["decoder_norm.bias"], dec_bf16, dec_f32,
-             dn_mean, dn_rstd, NB * Sd, Dd, LN_EPS)
         pred_full = buf("pred_full", (NB * Sd, P), bf16)
-        call("csm_linear_fwd", dec_bf16, w16["decoder_pred.weight"], params["decoder_pred.bias"], pred_full, None,
-             NB * Sd, P, Dd, EPI_BF16)
+        for cs, b0, nb in parts:
+            d0, d1 = b0 * Sd, (b0 + nb) * Sd
+            with torch.cuda.stream(cs):
+                call("csm_layernorm_fwd", y[d0:d1], params["decoder_norm.weight"], params["decoder_norm.bias"],
+                     dec_bf16[d0:d1], dec_f32[d0:d1], dn_mean[d0:d1], dn_rstd[d0:d1], nb * Sd, Dd, LN_EPS)
+                call("csm_linear_fwd", dec_bf16[d0:d1], w16["decoder_pred.weight"], params["decoder_pred.bias"],
+                     pred_full[d0:d1], None, nb * Sd, P, Dd, EPI_BF16)
+        self._join(parts)
 
         # ---- losses ----------------------------------------------------------------------------
         loss_acc = buf("loss_acc", (8,), f32)
@@ -471,7 +532,7 @@ class HotPathEngine:
             t = self._coefs[key] = torch.tensor(coefs, dtype=torch.float32).to(dev)
         return t
 
-    def _blocks_fwd(self, tag, pname, nlayers, x, NB, S, Dm, heads, params, w16, dev):
+    def _blocks_fwd(self, tag, pname, nlayers, x, parts, S, Dm, heads, params, w16, dev, NB):
         bf16, f32 = torch.bfloat16, torch.float32
         rows = NB * S
         d = Dm // heads
@@ -481,29 +542,32 @@ class HotPathEngine:
             hid = params[q + "mlp.fc1.weight"].shape[0]
             ln1 = buf(t + "ln1", (rows, Dm), bf16)
             mean1, rstd1 = buf(t + "mean1", (rows,), f32), buf(t + "rstd1", (rows,), f32)
-            call("csm_layernorm_fwd", x, params[q + "norm1.weight"], params[q + "norm1.bias"], ln1, None, mean1, rstd1,
-                 rows, Dm, LN_EPS)
             qkv = buf(t + "qkv", (rows, 3 * Dm), bf16)
-            call("csm_linear_fwd", ln1, w16[q + "attn.qkv.weight"], params[q + "attn.qkv.bias"], qkv, None,
-                 rows, 3 * Dm, Dm, EPI_BF16)
             ao = buf(t + "ao", (rows, Dm), bf16)
             lse = buf(t + "lse", (NB * heads * S,), f32)
-            call("csm_attention_fwd", qkv, ao, lse, NB, S, heads, d)
             xmid = buf(t + "xmid", (rows, Dm), f32)
-            call("csm_linear_fwd", ao, w16[q + "attn.proj.weight"], params[q + "attn.proj.bias"], xmid, x,
-                 rows, Dm, Dm, EPI_RESID)
             ln2 = buf(t + "ln2", (rows, Dm), bf16)
             mean2, rstd2 = buf(t + "mean2", (rows,), f32), buf(t + "rstd2", (rows,), f32)
-            call("csm_layernorm_fwd", xmid, params[q + "norm2.weight"], params[q + "norm2.bias"], ln2, None, mean2,
-                 rstd2, rows, Dm, LN_EPS)
             # fc1 + GELU in one epilogue; what is kept for the backward is gelu'(h), not h
             gp = buf(t + "gp", (rows, hid), bf16)
             act = buf(t + "act", (rows, hid), bf16)
-            call("csm_linear_fwd", ln2, w16[q + "mlp.fc1.weight"], params[q + "mlp.fc1.bias"], gp, act,
-                 rows, hid, Dm, EPI_GELU)
             xout = buf(t + "xout", (rows, Dm), f32)
-            call("csm_linear_fwd", act, w16[q + "mlp.fc2.weight"], params[q + "mlp.fc2.bias"], xout, xmid,
-                 rows, Dm, hid, EPI_RESID)
+            for cs, b0, nb in parts:
+                r0, r1, n = b0 * S, (b0 + nb) * S, nb * S
+                with torch.cuda.stream(cs):
+                    call("csm_layernorm_fwd", x[r0:r1], params[q + "norm1.weight"], params[q + "norm1.bias"],
+                         ln1[r0:r1], None, mean1[r0:r1], rstd1[r0:r1], n, Dm, LN_EPS)
+                    call("csm_linear_fwd", ln1[r0:r1], w16[q + "attn.qkv.weight"], params[q + "attn.qkv.bias"],
+                         qkv[r0:r1], None, n, 3 * Dm, Dm, EPI_BF16)
+                    call("csm_attention_fwd", qkv[r0:r1], ao[r0:r1], lse[b0 * heads * S:], nb, S, heads, d)
+                    call("csm_linear_fwd", ao[r0:r1], w16[q + "attn.proj.weight"], params[q + "attn.proj.bias"],
+                         xmid[r0:r1], x[r0:r1], n, Dm, Dm, EPI_RESID)
+                    call("csm_layernorm_fwd", xmid[r0:r1], params[q + "norm2.weight"], params[q + "norm2.bias"],
+                         ln2[r0:r1], None, mean2[r0:r1], rstd2[r0:r1], n, Dm, LN_EPS)
+                    call("csm_linear_fwd", ln2[r0:r1], w16[q + "mlp.fc1.weight"], params[q + "mlp.fc1.bias"],
+                         gp[r0:r1], act[r0:r1], n, hid, Dm, EPI_GELU)
+                    call("csm_linear_fwd", act[r0:r1], w16[q + "mlp.fc2.weight"], params[q + "mlp.fc2.bias"],
+                         xout[r0:r1], xmid[r0:r1], n, Dm, hid, EPI_RESID)
             x = xout
         return x
 
@@ -665,39 +729,63 @@ class HotPathEngine:
             call("csm_colsum_bf16", dh1, G["predictor.0.bias"], N * Sd, Hp, 0, nsm)
             call("csm_linear_dgrad", dh1, w16["predictor.0.weight"], dy2[N * Sd:], None, N * Sd, Hp, Dd, EPI_F32)
 
-        # ---- decoder_norm, decoder blocks ---------------------------------------------------------
+        # ---- decoder_norm, decoder blocks (row chains, as in the forward) ---------------------------
+        parts = self._parts(NB, dev)
+        chain_streams = [cs for cs, _, _ in parts[1:]]
         y_final = B[f"dec.{len(m.decoder) - 1}.xout"] if len(m.decoder) else B["dec.x0"]
         dres = buf("b.dec.dres", (rows_d, Dd), f32)
         dres16 = buf("b.dec.dres16", (rows_d, Dd), bf16)
         # the bf16 residual-stream gradient every LayerNorm backward emits is the dY of the Linear feeding
         # that residual add, so its column sums (that Linear's bias gradient) are taken in the same pass
         top_fc2_bias = G[f"decoder.{len(m.decoder) - 1}.mlp.fc2.bias"] if len(m.decoder) else None
-        call("csm_layernorm_bwd", d_dec, dy2, y_final, B["dn_mean"], B["dn_rstd"], params["decoder_norm.weight"], None,
-             dres, dres16, G["decoder_norm.weight"], G["decoder_norm.bias"], top_fc2_bias, rows_d, Dd, nsm)
-        self._blocks_bwd("dec", "decoder", len(m.decoder), dres, dres16, NB, Sd, Dd, m.decoder_num_heads, params, w16,
-                         G, dev, nsm, top_bias_done=True)
+        self._fork(parts)
+        for cs, b0, nb in parts:
+            d0, d1 = b0 * Sd, (b0 + nb) * Sd
+            with torch.cuda.stream(cs):
+                call("csm_layernorm_bwd", d_dec[d0:d1], None if dy2 is None else dy2[d0:d1], y_final[d0:d1],
+                     B["dn_mean"][d0:d1], B["dn_rstd"][d0:d1], params["decoder_norm.weight"], None, dres[d0:d1],
+                     dres16[d0:d1], G["decoder_norm.weight"], G["decoder_norm.bias"], top_fc2_bias, nb * Sd, Dd, nsm)
+        self._blocks_bwd("dec", "decoder", len(m.decoder), dres, dres16, parts, NB, Sd, Dd, m.decoder_num_heads, params,
+                         w16, G, dev, nsm, top_bias_done=True)
         if len(segs) > 1:
+            self._join(parts)
             fire(0)                                  # decoder.*, decoder_pred, decoder_norm, predictor are final
+            self._fork(parts)
 
         # ---- un-shuffle backward, decoder_embed ---------------------------------------------------
         d_demb = buf("b.d_demb", (rows_e, Dd), bf16)
-        call("csm_decoder_assemble_bwd", dres, B["ids_shuffle"], d_demb, G["mask_token"], NB, L, keep, Dd)
-        call("csm_linear_wgrad", d_demb, B["enc_bf16"], G["decoder_embed.weight"], rows_e, Dd, D, nsm)
-        call("csm_colsum_bf16", d_demb, G["decoder_embed.bias"], rows_e, Dd, 0, nsm)
         d_enc = buf("b.enc.dln", (rows_e, D), bf16)
-        call("csm_linear_dgrad", d_demb, w16["decoder_embed.weight"], d_enc, None, rows_e, Dd, D, EPI_BF16)
-
         # ---- NT-Xent feature gradient joins the encoder output gradient ---------------------------
         d_feat = None
         if ns == 2 and self.use_ce:
             d_feat = buf("b.d_feat", (NB, D), f32)
             call("csm_ntxent_bwd", B["ntx.zhat"], B["ntx.fnorm"], B["ntx.neg"], g, d_feat, N, D, NTXENT_TAU, NTXENT_EPS)
+            self._fork(parts)
         eres = buf("b.enc.dres", (rows_e, D), f32)
         eres16 = buf("b.enc.dres16", (rows_e, D), bf16)
-        call("csm_encoder_out_grad", d_enc, d_feat, eres, eres16, NB, Se, D)
-        eres16 = self._blocks_bwd("enc", "encoder", len(m.encoder), eres, eres16, NB, Se, D, m.encoder_num_heads, params, w16,
-                         G, dev, nsm, top_bias_done=False,
-                         after_layer=lambda i: fire(1 + seg_layers.index(i)) if i in seg_layers else None)
+        for cs, b0, nb in parts:
+            e0, e1, d0, d1 = b0 * Se, (b0 + nb) * Se, b0 * Sd, (b0 + nb) * Sd
+            with torch.cuda.stream(cs):
+                call("csm_decoder_assemble_bwd", dres[d0:d1], B["ids_shuffle"][b0:b0 + nb], d_demb[e0:e1],
+                     G["mask_token"], nb, L, keep, Dd)
+                call("csm_linear_dgrad", d_demb[e0:e1], w16["decoder_embed.weight"], d_enc[e0:e1], None, nb * Se, Dd, D,
+                     EPI_BF16)
+                call("csm_encoder_out_grad", d_enc[e0:e1], None if d_feat is None else d_feat[b0:b0 + nb], eres[e0:e1],
+                     eres16[e0:e1], nb, Se, D)
+
+        def side_demb():
+            call("csm_linear_wgrad", d_demb, B["enc_bf16"], G["decoder_embed.weight"], rows_e, Dd, D, nsm)
+            call("csm_colsum_bf16", d_demb, G["decoder_embed.bias"], rows_e, Dd, 0, nsm)
+        self._on_side(dev, side_demb, chain_streams)
+
+        def enc_boundary(i):
+            if i in seg_layers:
+                self._join(parts)
+                fire(1 + seg_layers.index(i))
+                self._fork(parts)
+        eres16 = self._blocks_bwd("enc", "encoder", len(m.encoder), eres, eres16, parts, NB, Se, D, m.encoder_num_heads,
+                                  params, w16, G, dev, nsm, top_bias_done=False, after_layer=enc_boundary)
+        self._join(parts)
 
         # ---- cls token, patch embed (only the kept patches carry gradient; cls-slot rows are zero) -
         call("csm_cls_grad", eres, G["cls_token"], NB, Se, D)
@@ -710,13 +798,26 @@ class HotPathEngine:
             boundary(0)
         return flat, [G[n] for n in names]
 
-    def _blocks_bwd(self, tag, pname, nlayers, dres, dres16, NB, S, Dm, heads, params, w16, G, dev, nsm,
+    def _blocks_bwd(self, tag, pname, nlayers, dres, dres16, parts, NB, S, Dm, heads, params, w16, G, dev, nsm,
                     top_bias_done, after_layer=None):
+        """Backward of a stack of Blocks.  The critical chain (dgrad -> LayerNorm backward -> attention backward) runs
+        per row chain on the chains' streams; the weight-gradient GEMMs and bias column sums, which reduce over ALL
+        rows, are issued once per Linear on the side stream after every chain has produced its rows of dY."""
         bf16, f32 = torch.bfloat16, torch.float32
         rows = NB * S
         d = Dm // heads
         B = self._bufs
         buf = lambda name, shape, dt: self._buf(name, shape, dt, dev)
+        chain_streams = [cs for cs, _, _ in parts[1:]]
+
+        def per_chain(fn):
+            for cs, b0, nb in parts:
+                with torch.cuda.stream(cs):
+                    fn(b0, nb, b0 * S, (b0 + nb) * S, nb * S)
+
+        dln = buf(f"b.{tag}.dln", (rows, Dm), bf16)
+        d_ao = buf(f"b.{tag}.d_ao", (rows, Dm), bf16)
+        delta = buf(f"b.{tag}.delta", (NB * heads * S,), f32)
         for i in reversed(range(nlayers)):
             t, q = f"{tag}.{i}.", f"{pname}.{i}."
             hid = params[q + "mlp.fc1.weight"].shape[0]
@@ -734,39 +835,50 @@ class HotPathEngine:
                 call("csm_linear_wgrad", dres16, B[t + "act"], G[q + "mlp.fc2.weight"], rows, Dm, hid, nsm)
                 if first_bias:
                     call("csm_colsum_bf16", dres16, G[q + "mlp.fc2.bias"], rows, Dm, 0, nsm)
-            self._on_side(dev, side_fc2)
-            call("csm_linear_dgrad", dres16, w16[q + "mlp.fc2.weight"], dh, B[t + "gp"], rows, Dm, hid, EPI_DGELU)
+            self._on_side(dev, side_fc2, chain_streams)
+            per_chain(lambda b0, nb, r0, r1, n: call(
+                "csm_linear_dgrad", dres16[r0:r1], w16[q + "mlp.fc2.weight"], dh[r0:r1], B[t + "gp"][r0:r1], n, Dm, hid,
+                EPI_DGELU))
 
             def side_fc1(dh=dh, t=t, q=q, hid=hid):
                 call("csm_linear_wgrad", dh, B[t + "ln2"], G[q + "mlp.fc1.weight"], rows, hid, Dm, nsm)
                 call("csm_colsum_bf16", dh, G[q + "mlp.fc1.bias"], rows, hid, 0, nsm)
-            self._on_side(dev, side_fc1)
-            dln = buf(f"b.{tag}.dln", (rows, Dm), bf16)
-            call("csm_linear_dgrad", dh, w16[q + "mlp.fc1.weight"], dln, None, rows, hid, Dm, EPI_BF16)
-            call("csm_layernorm_bwd", dln, None, B[t + "xmid"], B[t + "mean2"], B[t + "rstd2"],
-                 params[q + "norm2.weight"], dres, dres, d16a, G[q + "norm2.weight"], G[q + "norm2.bias"],
-                 G[q + "attn.proj.bias"], rows, Dm, nsm)
+            self._on_side(dev, side_fc1, chain_streams)
+
+            def mlp_tail(b0, nb, r0, r1, n):
+                call("csm_linear_dgrad", dh[r0:r1], w16[q + "mlp.fc1.weight"], dln[r0:r1], None, n, hid, Dm, EPI_BF16)
+                call("csm_layernorm_bwd", dln[r0:r1], None, B[t + "xmid"][r0:r1], B[t + "mean2"][r0:r1],
+                     B[t + "rstd2"][r0:r1], params[q + "norm2.weight"], dres[r0:r1], dres[r0:r1], d16a[r0:r1],
+                     G[q + "norm2.weight"], G[q + "norm2.bias"], G[q + "attn.proj.bias"], n, Dm, nsm)
+            per_chain(mlp_tail)
             # attention branch: x_mid = x_in + proj(attn(qkv(norm1(x_in))))
 
             def side_proj(d16a=d16a, t=t, q=q):
                 call("csm_linear_wgrad", d16a, B[t + "ao"], G[q + "attn.proj.weight"], rows, Dm, Dm, nsm)
-            self._on_side(dev, side_proj)
-            d_ao = buf(f"b.{tag}.d_ao", (rows, Dm), bf16)
-            call("csm_linear_dgrad", d16a, w16[q + "attn.proj.weight"], d_ao, None, rows, Dm, Dm, EPI_BF16)
-            delta = buf(f"b.{tag}.delta", (NB * heads * S,), f32)
-            # (the kernel can also emit the qkv.bias column sums itself -- measured slower than the separate
-            #  pass on B200: the extra tail per CTA is not hidden at one CTA per SM)
-            call("csm_attention_bwd", B[t + "qkv"], B[t + "ao"], d_ao, B[t + "lse"], delta, dqkv, None,
-                 NB, S, heads, d)
+            self._on_side(dev, side_proj, chain_streams)
+
+            def attn_branch(b0, nb, r0, r1, n):
+                call("csm_linear_dgrad", d16a[r0:r1], w16[q + "attn.proj.weight"], d_ao[r0:r1], None, n, Dm, Dm,
+                     EPI_BF16)
+                # (the kernel can also emit the qkv.bias column sums itself -- measured slower than the separate
+                #  pass on B200: the extra tail per CTA is not hidden at one CTA per SM)
+                call("csm_attention_bwd", B[t + "qkv"][r0:r1], B[t + "ao"][r0:r1], d_ao[r0:r1],
+                     B[t + "lse"][b0 * heads * S:], delta[b0 * heads * S:], dqkv[r0:r1], None, nb, S, heads, d)
+            per_chain(attn_branch)
 
             def side_qkv(dqkv=dqkv, t=t, q=q):
                 call("csm_linear_wgrad", dqkv, B[t + "ln1"], G[q + "attn.qkv.weight"], rows, 3 * Dm, Dm, nsm)
                 call("csm_colsum_bf16", dqkv, G[q + "attn.qkv.bias"], rows, 3 * Dm, 0, nsm)
-            self._on_side(dev, side_qkv)
-            call("csm_linear_dgrad", dqkv, w16[q + "attn.qkv.weight"], dln, None, rows, 3 * Dm, Dm, EPI_BF16)
+            self._on_side(dev, side_qkv, chain_streams)
             below_fc2_bias = G[f"{pname}.{i - 1}.mlp.fc2.bias"] if i > 0 else None
-            call("csm_layernorm_bwd", dln, None, x_in, B[t + "mean1"], B[t + "rstd1"], params[q + "norm1.weight"],
-                 dres, dres, d16b, G[q + "norm1.weight"], G[q + "norm1.bias"], below_fc2_bias, rows, Dm, nsm)
+
+            def attn_tail(b0, nb, r0, r1, n):
+                call("csm_linear_dgrad", dqkv[r0:r1], w16[q + "attn.qkv.weight"], dln[r0:r1], None, n, 3 * Dm, Dm,
+                     EPI_BF16)
+                call("csm_layernorm_bwd", dln[r0:r1], None, x_in[r0:r1], B[t + "mean1"][r0:r1], B[t + "rstd1"][r0:r1],
+                     params[q + "norm1.weight"], dres[r0:r1], dres[r0:r1], d16b[r0:r1], G[q + "norm1.weight"],
+                     G[q + "norm1.bias"], below_fc2_bias, n, Dm, nsm)
+            per_chain(attn_tail)
             dres16 = d16b
             if after_layer is not None:
                 after_layer(i)

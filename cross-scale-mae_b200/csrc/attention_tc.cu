@@ -50,9 +50,13 @@ struct FwdParams {
 // bounded wait: a protocol error traps (the launch fails with an error) instead of hanging the device
 __device__ __forceinline__ void mbar_wait_wd(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000ll) __trap();
+  long long t0 = 0;
+  for (uint32_t tries = 1; !mbar_try_wait(bar, parity); ++tries) {
+    if ((tries & 1023u) == 0) {            // the clock is read once per 1024 failed tries: the wait loop itself
+      const long long t = clock64();      // stays two instructions long
+      if (t0 == 0) t0 = t;
+      else if (t - t0 > 4000000000ll) __trap();
+    }
   }
 }
 
@@ -86,6 +90,18 @@ struct IC {
   static constexpr int value = N;
 };
 
+// Development builds (CSM_NVCC_EXTRA=-DCSM_ATTN_TIMING, tools/attn_phase.py): cycles spent per phase of the backward
+// kernel's sub-block loop, summed over the sub-blocks of one softmax warp (warp 4, lane 0) and of the MMA thread of
+// every CTA.  Slot 15 counts sub-blocks.
+#ifdef CSM_ATTN_TIMING
+__device__ unsigned long long g_attn_phase[16];
+#define ATT_T(var) const long long var = clock64()
+#define ATT_ACC(slot, t1, t0) acc_t[slot] += (t1) - (t0)
+#else
+#define ATT_T(var)
+#define ATT_ACC(slot, t1, t0)
+#endif
+
 // ---------------------------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------------------------
@@ -105,6 +121,20 @@ __device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, ui
       "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
       "}\n" ::"r"(tmem_d),
       "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+__device__ __forceinline__ void umma_f16_ts_lh(uint32_t tmem_d, uint32_t tmem_a, uint32_t b_lo, uint32_t b_hi,
+                                               uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .b64 db;\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "mov.b64 db, {%2, %3};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
       : "memory");
 }
 
@@ -220,73 +250,80 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
         }
       }
     } else if (warp == 1) {
-      // ------------------------------ MMA issuer (one thread) ------------------------------
-      if (lane == 0) {
-        constexpr uint32_t idesc_s = umma_idesc_bf16(128, BN, 0, 0);
-        constexpr uint32_t idesc_o = umma_idesc_bf16(128, DH, 0, 1);
-        const uint32_t p_addr = smem_u32(sP);
-        uint32_t it = 0, ic = 0, kvc = 0;
-        // the P.V product of an iteration is issued after the NEXT S = Q K^T, so the softmax warps always find their
-        // next score tile ready
-        bool have_prev = false;
-        uint32_t pv_it = 0, pv_ks = 0, pv_qs = 0;
-        int pv_hh = 0;
-        bool pv_last_kv = false, pv_last_item = false;
-        auto issue_pv = [&]() {
-          mbar_wait_wd(p_full, pv_it & 1);
-          tc_fence_after();
-          const uint32_t v_addr = smem_u32(sKV + pv_ks * 2 * KV_BYTES + KV_BYTES) + (DH == 32 ? pv_hh * 64 : 0);
-          const uint32_t tmem_p = tmem_base + (pv_it & 1) * BN;
+      // ------------------------------ MMA issuer ------------------------------
+      // The whole warp walks the schedule (warp-uniform control flow, so descriptors and loop state live in uniform
+      // registers); one elected lane issues.  Every descriptor is base_lo + a constant (see umma_desc_lo).
+      constexpr uint32_t idesc_s = umma_idesc_bf16(128, BN, 0, 0);
+      constexpr uint32_t idesc_o = umma_idesc_bf16(128, DH, 0, 1);
+      constexpr uint32_t HI = umma_desc_hi_sw128(1024);
+      constexpr uint32_t LBO_K = (16u >> 4) << 16, LBO_MN = (8192u >> 4) << 16;
+      constexpr uint32_t OFF_KV = (2u * AT_QBYTES) >> 4, KV16 = KV_BYTES >> 4, OFF_P = OFF_KV + 4 * KV16;
+      const uint32_t base_lo = __shfl_sync(0xffffffffu, (smem_u32(smem) & 0x3FFFFu) >> 4, 0);
+      const uint32_t p_lo = base_lo + OFF_P + LBO_K;
+      uint32_t it = 0, ic = 0, kvc = 0;
+      // the P.V product of an iteration is issued after the NEXT S = Q K^T, so the softmax warps always find their
+      // next score tile ready
+      bool have_prev = false;
+      uint32_t pv_it = 0, pv_ks = 0, pv_qs = 0;
+      int pv_hh = 0;
+      bool pv_last_kv = false, pv_last_item = false;
+      auto issue_pv = [&]() {
+        mbar_wait_wd(p_full, pv_it & 1);
+        tc_fence_after();
+        const uint32_t v_lo = base_lo + OFF_KV + pv_ks * (2 * KV16) + KV16 + (DH == 32 ? pv_hh * 4 : 0) + LBO_MN;
+        const uint32_t tmem_p = tmem_base + (pv_it & 1) * BN;
+        if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < NG0 + NG1; ++k) {        // each key half accumulates into its own O
             const int hf = k >= NG0 ? 1 : 0, kh = k - hf * NG0;
-            const uint64_t db = umma_smem_desc_sw128(v_addr + k * 2048, 8192, 1024);
             const uint32_t tmem_o = tmem_base + COL_O + hf * DH;
             if (PTMEM) {
-              umma_f16_ts(tmem_o, tmem_p + hf * BNH0 + kh * 8, db, idesc_o, kh > 0 ? 1u : 0u);
+              umma_f16_ts_lh(tmem_o, tmem_p + hf * BNH0 + kh * 8, v_lo + k * 128, HI, idesc_o, kh > 0 ? 1u : 0u);
             } else {
-              const uint64_t da = umma_smem_desc_sw128(p_addr + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024);
-              umma_f16(tmem_o, da, db, idesc_o, kh > 0 ? 1u : 0u);
+              umma_f16_lh(tmem_o, p_lo + (k >> 2) * 1024 + (k & 3) * 2, HI, v_lo + k * 128, HI, idesc_o,
+                          kh > 0 ? 1u : 0u);
             }
           }
           umma_commit(o_full);
           if (pv_last_kv) umma_commit(&kv_empty[pv_ks]);
           if (pv_last_item) umma_commit(&q_empty[pv_qs]);
-        };
-        for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++ic) {
-          const int hg = p.pack ? item % p.HG : (item / p.QT) % p.HG;
-          const int nh = min(NH, p.H - hg * NH);
-          const uint32_t qs = ic & 1;
-          mbar_wait_wd(&q_full[qs], (ic >> 1) & 1);
-          const uint32_t q_addr = smem_u32(sQ + qs * AT_QBYTES);
-          uint32_t ks = 0;
-          for (int hh = 0; hh < nh; ++hh) {
-            for (int j = 0; j < p.nb; ++j, ++it) {
-              if (!(shared_kv && hh > 0)) {
-                ks = kvc & 1;
-                mbar_wait_wd(&kv_full[ks], (kvc >> 1) & 1);
-                ++kvc;
-              }
-              tc_fence_after();
-              const uint32_t k_addr = smem_u32(sKV + ks * 2 * KV_BYTES);
-              const uint32_t tmem_s = tmem_base + (it & 1) * BN;
-#pragma unroll
-              for (int kk = 0; kk < KS; ++kk) {
-                const uint64_t da = umma_smem_desc_sw128(q_addr + (hh * KS + kk) * 32, 16, 1024);
-                const uint64_t db = umma_smem_desc_sw128(k_addr + (hh * KS + kk) * 32, 16, 1024);
-                umma_f16(tmem_s, da, db, idesc_s, kk > 0 ? 1u : 0u);
-              }
-              umma_commit(&s_full[it & 1]);
-              if (have_prev) issue_pv();
-              have_prev = true;
-              pv_it = it; pv_ks = ks; pv_qs = qs; pv_hh = hh;
-              pv_last_kv = shared_kv ? (hh == nh - 1) : true;
-              pv_last_item = (hh == nh - 1) && (j == p.nb - 1);
+        }
+        __syncwarp();
+      };
+      for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++ic) {
+        const int hg = p.pack ? item % p.HG : (item / p.QT) % p.HG;
+        const int nh = min(NH, p.H - hg * NH);
+        const uint32_t qs = ic & 1;
+        mbar_wait_wd(&q_full[qs], (ic >> 1) & 1);
+        const uint32_t q_lo = base_lo + qs * (AT_QBYTES >> 4) + LBO_K;
+        uint32_t ks = 0;
+        for (int hh = 0; hh < nh; ++hh) {
+          for (int j = 0; j < p.nb; ++j, ++it) {
+            if (!(shared_kv && hh > 0)) {
+              ks = kvc & 1;
+              mbar_wait_wd(&kv_full[ks], (kvc >> 1) & 1);
+              ++kvc;
             }
+            tc_fence_after();
+            const uint32_t k_lo = base_lo + OFF_KV + ks * (2 * KV16) + LBO_K;
+            const uint32_t tmem_s = tmem_base + (it & 1) * BN;
+            const uint32_t ko = hh * KS * 2;            // 32 bytes per k-step, in 16-byte units
+            if (elect_one()) {
+#pragma unroll
+              for (int kk = 0; kk < KS; ++kk)
+                umma_f16_lh(tmem_s, q_lo + ko + kk * 2, HI, k_lo + ko + kk * 2, HI, idesc_s, kk > 0 ? 1u : 0u);
+              umma_commit(&s_full[it & 1]);
+            }
+            __syncwarp();
+            if (have_prev) issue_pv();
+            have_prev = true;
+            pv_it = it; pv_ks = ks; pv_qs = qs; pv_hh = hh;
+            pv_last_kv = shared_kv ? (hh == nh - 1) : true;
+            pv_last_item = (hh == nh - 1) && (j == p.nb - 1);
           }
         }
-        if (have_prev) issue_pv();
       }
+      if (have_prev) issue_pv();
     }
   } else {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
@@ -739,84 +776,111 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
         }
       }
     } else if (warp == 1) {
-      // ------------------------------ MMA issuer (one thread) ------------------------------
-      if (lane == 0) {
-        constexpr uint32_t idesc_g = umma_idesc_bf16(128, DH, 1, 1);     // dV / dK: A and B MN-major
-        constexpr uint32_t idesc_q = umma_idesc_bf16(128, DH, 0, 1);     // dQ: A K-major, B MN-major
-        const uint32_t p_addr = smem_u32(sP), ds_addr = smem_u32(sdS);
-        uint32_t n = 0, ic = 0, qc = 0;
-        // pending sub-block: its gradient products are issued after the NEXT sub-block's S / dP products
-        bool pend = false;
-        uint32_t pd_n = 0, pd_ic = 0, pd_k = 0, pd_q = 0, pd_qs = 0;
-        int pd_hh = 0, pd_i = 0, pd_bn = 0;
-        bool pd_last_tile = false, pd_last_item = false;
-        auto grads = [&]() {
-          mbar_wait_wd(pds_full, pd_n & 1);                                   // P / dS tiles are in shared memory
-          if (pd_i == 0 && pd_hh == 0 && pd_ic > 0) mbar_wait_wd(dkv_free, (pd_ic - 1) & 1);   // previous item's dK / dV read
-          if (pd_n >= 2) mbar_wait_wd(&dq_free[pd_n & 1], ((pd_n >> 1) - 1) & 1);              // dQ buffer read out
-          tc_fence_after();
-          const uint32_t hoff = DH == 32 ? pd_hh * 64 : 0;
+      // ------------------------------ MMA issuer ------------------------------
+      // The whole warp walks the schedule (warp-uniform control flow: descriptors and loop state live in uniform
+      // registers); one elected lane issues.  Every descriptor is base_lo + a constant: base_lo is the 16-byte-unit
+      // address of the shared-memory window, broadcast so that the compiler knows it is uniform.
+      constexpr uint32_t idesc_g = umma_idesc_bf16(128, DH, 1, 1);     // dV / dK: A and B MN-major
+      constexpr uint32_t idesc_q = umma_idesc_bf16(128, DH, 0, 1);     // dQ: A K-major, B MN-major
+      constexpr uint32_t HI = umma_desc_hi_sw128(1024);
+      constexpr uint32_t LBO_K = (16u >> 4) << 16, LBO_MN = (8192u >> 4) << 16, LBO_PT = (16384u >> 4) << 16;
+      constexpr uint32_t OFF_QO = 65536u >> 4, OFF_P = 131072u >> 4, OFF_DS = (131072u + 32768u) >> 4;
+      const uint32_t base_lo = __shfl_sync(0xffffffffu, (smem_u32(smem) & 0x3FFFFu) >> 4, 0);
+      const uint32_t p_lo_mn = base_lo + OFF_P + LBO_PT, ds_lo_mn = base_lo + OFF_DS + LBO_PT;
+      const uint32_t ds_lo_k = base_lo + OFF_DS + LBO_K;
+      uint32_t n = 0, ic = 0, qc = 0;
+      // pending sub-block: its gradient products are issued after the NEXT sub-block's S / dP products
+      bool pend = false;
+      uint32_t pd_n = 0, pd_ic = 0, pd_ks = 0, pd_qs = 0;
+      int pd_hh = 0, pd_i = 0, pd_bn = 0;
+      bool pd_last_tile = false, pd_last_item = false;
+#ifdef CSM_ATTN_TIMING
+      long long acc_t[16] = {0};
+#endif
+      auto grads = [&]() {
+        ATT_T(g0);
+        mbar_wait_wd(pds_full, pd_n & 1);                                   // P / dS tiles are in shared memory
+        ATT_T(g1);
+        ATT_ACC(8, g1, g0);
+        if (pd_i == 0 && pd_hh == 0 && pd_ic > 0) mbar_wait_wd(dkv_free, (pd_ic - 1) & 1);   // previous item's dK / dV read
+        if (pd_n >= 2) mbar_wait_wd(&dq_free[pd_n & 1], ((pd_n >> 1) - 1) & 1);              // dQ buffer read out
+        tc_fence_after();
+        const uint32_t hoff = DH == 32 ? static_cast<uint32_t>(pd_hh) * 4u : 0u;            // 64 bytes per head
+        const uint32_t q_lo = base_lo + OFF_QO + pd_qs * 2048u + hoff + LBO_MN;
+        const uint32_t do_lo = q_lo + 1024u;                                                // dO tile: + 16 KB
+        const uint32_t k_lo = base_lo + pd_ks * 2048u + hoff + LBO_MN;
+        const uint32_t tm_dv = tmem_base + COL_DV + pd_hh * DH, tm_dk = tmem_base + COL_DK + pd_hh * DH;
+        const uint32_t tm_dq = tmem_base + COL_DQ + (pd_n & 1) * DH;
+        const uint32_t acc0 = pd_i > 0 ? 1u : 0u;
+        const int ksteps = pd_bn >> 4;             // 4 or 8
+        if (elect_one()) {
 #pragma unroll
-          for (int kk = 0; kk < 8; ++kk) {           // dV += P^T dO_i   (reduction over the 128 query rows)
-            const uint64_t da = umma_smem_desc_sw128(p_addr + kk * 2048, 16384, 1024);
-            const uint64_t db = umma_smem_desc_sw128(pd_q + 16384 + kk * 2048 + hoff, 8192, 1024);
-            umma_f16(tmem_base + COL_DV + pd_hh * DH, da, db, idesc_g, (pd_i > 0 || kk > 0) ? 1u : 0u);
-          }
+          for (int kk = 0; kk < 8; ++kk)           // dV += P^T dO_i   (reduction over the 128 query rows)
+            umma_f16_lh(tm_dv, p_lo_mn + kk * 128, HI, do_lo + kk * 128, HI, idesc_g, kk > 0 ? 1u : acc0);
 #pragma unroll
-          for (int kk = 0; kk < 8; ++kk) {           // dK += dS^T Q_i
-            const uint64_t da = umma_smem_desc_sw128(ds_addr + kk * 2048, 16384, 1024);
-            const uint64_t db = umma_smem_desc_sw128(pd_q + kk * 2048 + hoff, 8192, 1024);
-            umma_f16(tmem_base + COL_DK + pd_hh * DH, da, db, idesc_g, (pd_i > 0 || kk > 0) ? 1u : 0u);
-          }
-          const int ksteps = pd_bn >> 4;
-          for (int ks = 0; ks < ksteps; ++ks) {      // dQ_i (partial) = dS K   (reduction over the keys of the block)
-            const uint64_t da = umma_smem_desc_sw128(ds_addr + (ks >> 2) * 16384 + (ks & 3) * 32, 16, 1024);
-            const uint64_t db = umma_smem_desc_sw128(pd_k + ks * 2048 + hoff, 8192, 1024);
-            umma_f16(tmem_base + COL_DQ + (pd_n & 1) * DH, da, db, idesc_q, ks > 0 ? 1u : 0u);
+          for (int kk = 0; kk < 8; ++kk)           // dK += dS^T Q_i
+            umma_f16_lh(tm_dk, ds_lo_mn + kk * 128, HI, q_lo + kk * 128, HI, idesc_g, kk > 0 ? 1u : acc0);
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks) {         // dQ_i (partial) = dS K   (reduction over the keys of the block)
+            if (ks < ksteps)
+              umma_f16_lh(tm_dq, ds_lo_k + (ks >> 2) * 1024 + (ks & 3) * 2, HI, k_lo + ks * 128, HI, idesc_q,
+                          ks > 0 ? 1u : 0u);
           }
           umma_commit(grads_done);
           if (pd_last_tile) umma_commit(&q_empty[pd_qs]);
           if (pd_last_item) umma_commit(&kv_empty[pd_ic & 1]);
-        };
-        for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++ic) {
-          const int kb = item % NT;
-          const int hg = (item / NT) % p.HG;
-          const int nh = min(NH, p.H - hg * NH);
-          const int bn = (kb == NT - 1) ? p.bn_last : 128;
-          const uint32_t idesc_s = umma_idesc_bf16(128, bn, 0, 0);
-          const uint32_t ks = ic & 1;
-          mbar_wait_wd(&kv_full[ks], (ic >> 1) & 1);
-          const uint32_t k_addr = smem_u32(sKV + ks * 32768), v_addr = k_addr + 16384;
-          for (int i = 0; i < NT; ++i, ++qc) {
-            const uint32_t qs = qc & 1;
-            mbar_wait_wd(&q_full[qs], (qc >> 1) & 1);
-            const uint32_t q_addr = smem_u32(sQO + qs * 32768), do_addr = q_addr + 16384;
-            for (int hh = 0; hh < nh; ++hh, ++n) {
-              if (n > 0) mbar_wait_wd(sdp_free, (n - 1) & 1);      // the previous S / dP tiles are in registers
-              tc_fence_after();
+        }
+        __syncwarp();
+        ATT_T(g2);
+        ATT_ACC(9, g2, g1);
+      };
+      for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++ic) {
+        const int kb = item % NT;
+        const int hg = (item / NT) % p.HG;
+        const int nh = min(NH, p.H - hg * NH);
+        const int bn = (kb == NT - 1) ? p.bn_last : 128;
+        const uint32_t idesc_s = umma_idesc_bf16(128, bn, 0, 0);
+        const uint32_t ks = ic & 1;
+        mbar_wait_wd(&kv_full[ks], (ic >> 1) & 1);
+        const uint32_t k_lo_k = base_lo + ks * 2048u + LBO_K, v_lo_k = k_lo_k + 1024u;
+        for (int i = 0; i < NT; ++i, ++qc) {
+          const uint32_t qs = qc & 1;
+          mbar_wait_wd(&q_full[qs], (qc >> 1) & 1);
+          const uint32_t q_lo_k = base_lo + OFF_QO + qs * 2048u + LBO_K, do_lo_k = q_lo_k + 1024u;
+          for (int hh = 0; hh < nh; ++hh, ++n) {
+            ATT_T(m0);
+            if (n > 0) mbar_wait_wd(sdp_free, (n - 1) & 1);      // the previous S / dP tiles are in registers
+            tc_fence_after();
+            ATT_T(m1);
+            ATT_ACC(10, m1, m0);
+            const uint32_t ko = hh * KS * 2;                      // 32 bytes per k-step, in 16-byte units
+            if (elect_one()) {
 #pragma unroll
-              for (int kk = 0; kk < KS; ++kk) {
-                const uint32_t ko = (hh * KS + kk) * 32;
-                umma_f16(tmem_base + COL_S, umma_smem_desc_sw128(q_addr + ko, 16, 1024),
-                         umma_smem_desc_sw128(k_addr + ko, 16, 1024), idesc_s, kk > 0 ? 1u : 0u);
-              }
+              for (int kk = 0; kk < KS; ++kk)
+                umma_f16_lh(tmem_base + COL_S, q_lo_k + ko + kk * 2, HI, k_lo_k + ko + kk * 2, HI, idesc_s,
+                            kk > 0 ? 1u : 0u);
 #pragma unroll
-              for (int kk = 0; kk < KS; ++kk) {
-                const uint32_t ko = (hh * KS + kk) * 32;
-                umma_f16(tmem_base + COL_DP, umma_smem_desc_sw128(do_addr + ko, 16, 1024),
-                         umma_smem_desc_sw128(v_addr + ko, 16, 1024), idesc_s, kk > 0 ? 1u : 0u);
-              }
+              for (int kk = 0; kk < KS; ++kk)
+                umma_f16_lh(tmem_base + COL_DP, do_lo_k + ko + kk * 2, HI, v_lo_k + ko + kk * 2, HI, idesc_s,
+                            kk > 0 ? 1u : 0u);
               umma_commit(sdp_full);
-              if (pend) grads();
-              pend = true;
-              pd_n = n; pd_ic = ic; pd_k = k_addr; pd_q = q_addr; pd_qs = qs; pd_hh = hh; pd_i = i; pd_bn = bn;
-              pd_last_tile = (hh == nh - 1);
-              pd_last_item = pd_last_tile && (i == NT - 1);
             }
+            __syncwarp();
+            ATT_T(m2);
+            ATT_ACC(11, m2, m1);
+            if (pend) grads();
+            pend = true;
+            pd_n = n; pd_ic = ic; pd_ks = ks; pd_qs = qs; pd_hh = hh; pd_i = i; pd_bn = bn;
+            pd_last_tile = (hh == nh - 1);
+            pd_last_item = pd_last_tile && (i == NT - 1);
           }
         }
-        if (pend) grads();
       }
+      if (pend) grads();
+#ifdef CSM_ATTN_TIMING
+      if (lane == 0)
+        for (int i = 8; i < 12; ++i) atomicAdd(&g_attn_phase[i], static_cast<unsigned long long>(acc_t[i]));
+#endif
     }
   } else {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
@@ -916,8 +980,12 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
       }
     };
 
+#ifdef CSM_ATTN_TIMING
+    long long acc_t[16] = {0};
+#endif
 #pragma unroll 1
     while (cur.valid(p)) {
+      ATT_T(t0);
       const int bn = (cur.kb == NT - 1) ? p.bn_last : 128;
       const int bnq = bn >> 2;                  // keys of this thread's quarter: one or two 16-key groups
       const int colbase = cq * bnq;
@@ -927,8 +995,10 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
       float Ln = INFINITY, dn = 0.f;
       if (nxt.valid(p)) load_stats(nxt, Ln, dn);
 
+      ATT_T(t1);
       mbar_wait_wd(sdp_full, n & 1);
       tc_fence_after();
+      ATT_T(t2);
       uint32_t su[32], du[32];
       const uint32_t ts = tmem_base + lane_off + COL_S + colbase;
       const uint32_t td = tmem_base + lane_off + COL_DP + colbase;
@@ -943,6 +1013,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(sdp_free);       // the next sub-block's S / dP products may overwrite the tiles
+      ATT_T(t3);
 
       // P and dS of this thread's keys, packed to bf16 pairs (in place over the scores)
 #pragma unroll
@@ -969,10 +1040,12 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
       }
       // the previous sub-block's gradient products are done: the P / dS tiles may be rewritten and its dQ partial
       // (and dK / dV) read.  The stores go first so that they drain under the read-back, before the proxy fence.
+      ATT_T(t4);
       if (have_prev) {
         mbar_wait_wd(grads_done, (n - 1) & 1);
         tc_fence_after();
       }
+      ATT_T(t5);
 #pragma unroll
       for (int q = 0; q < 2; ++q) {
         if (q * 16 < bnq) {
@@ -985,11 +1058,22 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
           sts_v4(ds_row + o1, make_uint4(du[q * 16 + 4], du[q * 16 + 5], du[q * 16 + 6], du[q * 16 + 7]));
         }
       }
+      ATT_T(t6);
       if (have_prev) read_back();
+      ATT_T(t7);
       fence_proxy_async();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(pds_full);
+      ATT_T(t8);
+      ATT_ACC(0, t1, t0);      // loop head: bookkeeping + statistics prefetch issue
+      ATT_ACC(1, t2, t1);      // wait: S / dP products
+      ATT_ACC(2, t3, t2);      // tcgen05.ld of S / dP + release
+      ATT_ACC(3, t4, t3);      // exp / dS arithmetic
+      ATT_ACC(4, t5, t4);      // wait: previous gradient products
+      ATT_ACC(5, t6, t5);      // st.shared of P / dS
+      ATT_ACC(6, t7, t6);      // read-back of dQ (dK / dV)
+      ATT_ACC(7, t8, t7);      // proxy fence + arrive
 
       have_prev = 1;
       {
@@ -1013,6 +1097,12 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
       tc_fence_after();
       read_back();
     }
+#ifdef CSM_ATTN_TIMING
+    if (warp == 4 && lane == 0) {
+      for (int i = 0; i < 8; ++i) atomicAdd(&g_attn_phase[i], static_cast<unsigned long long>(acc_t[i]));
+      atomicAdd(&g_attn_phase[15], static_cast<unsigned long long>(n));
+    }
+#endif
   }
 
   __syncwarp();
@@ -1023,6 +1113,19 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
     tmem_dealloc(tmem_base, 512);
   }
 }
+
+#ifdef CSM_ATTN_TIMING
+}  // namespace
+// development: reads and clears the phase counters
+extern "C" int csm_attn_phase_read(unsigned long long* host16) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(host16, g_attn_phase, sizeof(unsigned long long) * 16);
+  unsigned long long zero[16] = {0};
+  cudaMemcpyToSymbol(g_attn_phase, zero, sizeof(zero));
+  return CSM_OK;
+}
+namespace {
+#endif
 
 template <int DH>
 int attn_bwd_tc_launch(const void* qkv, const void* o, const void* d_out, const float* lse, float* delta, void* dqkv,

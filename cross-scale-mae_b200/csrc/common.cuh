@@ -44,6 +44,7 @@ static inline int csm_cdiv(long long a, long long b) { return (int)((a + b - 1) 
 int csm_tensor_map_2d(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld,
                       uint32_t box_inner, uint32_t box_outer, uint32_t elem_bytes, uint32_t swizzle_bytes);
 
+#include <cstdlib>
 #ifdef __CUDACC__
 // Launch with programmatic dependent launch (PDL): the grid may be scheduled while the previous kernel of the
 // stream is still draining; every kernel launched this way calls csm::pdl_wait() before it touches global
@@ -56,11 +57,16 @@ inline cudaError_t csm_launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block,
   cfg.blockDim = block;
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
+  // CSMAE_PDL=0 (development switch): plain stream-ordered launches; griddepcontrol.* are then no-ops
+  static const bool pdl = [] {
+    const char* e = getenv("CSMAE_PDL");
+    return e == nullptr || e[0] != '0';
+  }();
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 }
 #endif
@@ -230,12 +236,12 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   asm volatile(
       "{\n\t"
       ".reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t"
       "}\n"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
-      : "memory");
+      : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u)   // suspend-time hint: the warp sleeps in hardware instead
+      : "memory");                                          // of spinning through the issue slots of its scheduler
   return ok != 0;
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
@@ -321,6 +327,32 @@ __device__ __forceinline__ uint64_t umma_smem_desc_sw128(uint32_t saddr, uint32_
   d |= static_cast<uint64_t>(1) << 46;  // descriptor version (Blackwell)
   d |= static_cast<uint64_t>(2) << 61;  // SWIZZLE_128B
   return d;
+}
+
+// The same descriptor as two 32-bit halves.  The MMA issuer is ONE thread whose instruction stream sits on the critical
+// path of every short product (a 128 x 32 x 16 MMA retires in 16 cycles): stepping a descriptor through a tile must
+// be a single 32-bit add on the low word (start address, 16-byte units; it cannot carry out of its 14-bit field for
+// offsets inside the 227 KB of shared memory) instead of re-deriving the 64-bit value with shifts and masks per MMA.
+__device__ __forceinline__ uint32_t umma_desc_lo(uint32_t saddr, uint32_t lbo_bytes) {
+  return ((saddr & 0x3FFFFu) >> 4) | (((lbo_bytes >> 4) & 0x3FFFu) << 16);
+}
+__host__ __device__ constexpr uint32_t umma_desc_hi_sw128(uint32_t sbo_bytes) {
+  return ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14) | (2u << 29);   // SBO | version 1 | SWIZZLE_128B
+}
+// D[tmem] (+)= A[smem] * B[smem], descriptors passed as {lo, hi} words (cta_group::1)
+__device__ __forceinline__ void umma_f16_lh(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                            uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
 }
 
 // Instruction descriptor, kind::f16: bf16 x bf16 -> f32, dense. major: 0 = K-major, 1 = MN-major.

@@ -117,6 +117,21 @@ __device__ __forceinline__ void umma2_f16(uint32_t tmem_d, uint64_t desc_a, uint
       "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// the same with the descriptors as {lo, hi} words: stepping through a tile is one 32-bit add on the low word
+__device__ __forceinline__ void umma2_f16_lh(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                             uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %5, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // arrive (once) on the mbarrier at this shared-memory offset in BOTH CTAs of the pair when all previously
 // issued tcgen05.mma of this thread have completed
 __device__ __forceinline__ void umma2_commit_mc(uint64_t* bar) {
@@ -303,45 +318,63 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
 
   if (warp == 0) {
     // ------------------------------ TMA producer (both CTAs) ------------------------------
-    if (lane == 0) {
+    // whole warp, warp-uniform control flow; one elected lane issues the copies
+    {
+      const uint32_t rank_u = __shfl_sync(0xffffffffu, rank, 0);
       const uint32_t stage_tx = 2u * static_cast<uint32_t>(A_BYTES + half_bn * BK * 2);
-      uint32_t it = 0;
+      uint32_t stage = 0, phase = 0;
       Sched sched(p, cluster_id, num_clusters);
       WorkUnit w;
       while (sched.next(p, w)) {
-        const int m0 = w.m_tile * (2 * BM) + static_cast<int>(rank) * BM;
-        const int n0 = w.n_tile * p.bn + static_cast<int>(rank) * half_bn;
-        for (int i = 0; i < w.nkb; ++i, ++it) {
-          const int s = it % STAGES;
-          const uint32_t ph = (it / STAGES) & 1;
-          mbar_wait(&empty_bar[s], ph ^ 1);
-          uint8_t* sa = smem + s * STAGE_BYTES;
+        const int m0 = w.m_tile * (2 * BM) + static_cast<int>(rank_u) * BM;
+        const int n0 = w.n_tile * p.bn + static_cast<int>(rank_u) * half_bn;
+        for (int i = 0; i < w.nkb; ++i) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * STAGE_BYTES;
           uint8_t* sb = sa + A_BYTES;
-          const uint32_t full_leader = mapa_u32(smem_u32(&full_bar[s]), 0);
-          if (rank == 0) mbar_expect_tx(&full_bar[s], stage_tx);
+          const uint32_t full_leader = mapa_u32(smem_u32(&full_bar[stage]), 0);
           const int k = (w.kb0 + i) * BK;
-          // K-major operand : one box {64 k, rows}.
-          // MN-major operand: boxes {64 mn, 64 k}; each 64-wide MN group is its own [64 k][128 B] slab.
-          if (!A_MN) {
-            tma2_load_2d(sa, &tmap_a, full_leader, k, m0);
-          } else {
+          if (elect_one()) {
+            if (rank_u == 0) mbar_expect_tx(&full_bar[stage], stage_tx);
+            // K-major operand : one box {64 k, rows}.
+            // MN-major operand: boxes {64 mn, 64 k}; each 64-wide MN group is its own [64 k][128 B] slab.
+            if (!A_MN) {
+              tma2_load_2d(sa, &tmap_a, full_leader, k, m0);
+            } else {
 #pragma unroll
-            for (int g = 0; g < BM / 64; ++g) tma2_load_2d(sa + g * (BK * 128), &tmap_a, full_leader, m0 + g * 64, k);
+              for (int g = 0; g < BM / 64; ++g) tma2_load_2d(sa + g * (BK * 128), &tmap_a, full_leader, m0 + g * 64, k);
+            }
+            if (!B_MN) {
+              tma2_load_2d(sb, &tmap_b, full_leader, k, n0);
+            } else {
+              for (int g = 0; g < half_bn / 64; ++g)
+                tma2_load_2d(sb + g * (BK * 128), &tmap_b, full_leader, n0 + g * 64, k);
+            }
           }
-          if (!B_MN) {
-            tma2_load_2d(sb, &tmap_b, full_leader, k, n0);
-          } else {
-            for (int g = 0; g < half_bn / 64; ++g)
-              tma2_load_2d(sb + g * (BK * 128), &tmap_b, full_leader, n0 + g * 64, k);
+          __syncwarp();
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
           }
         }
       }
     }
   } else if (warp == 1) {
-    // ------------------------------ MMA issuer (leader CTA, one thread) --------------------
-    if (rank == 0 && lane == 0) {
+    // ------------------------------ MMA issuer (leader CTA) --------------------------------
+    // The whole warp walks the schedule with warp-uniform control flow (descriptors, stage and phase live in uniform
+    // registers); one elected lane issues.  A descriptor is base_lo + stage * (STAGE_BYTES / 16) + a constant: one
+    // 32-bit add per MMA on the low word instead of re-deriving the 64-bit value (see common.cuh, umma_desc_lo).
+    if (__shfl_sync(0xffffffffu, rank, 0) == 0) {
       const uint32_t idesc = umma_idesc_bf16(2 * BM, p.bn, A_MN ? 1 : 0, B_MN ? 1 : 0);
-      uint32_t it = 0, tile_it = 0;
+      constexpr uint32_t HI = umma_desc_hi_sw128(1024);
+      // K-major, 128B swizzle : 8-row groups are 1024 B apart (SBO); a K step of 16 is 32 B inside the row.
+      // MN-major, 128B swizzle: 64-wide MN groups are BK*128 B apart (LBO), 8-deep K groups 1024 B (SBO);
+      //                         a K step of 16 is 16 rows = 2048 B.
+      constexpr uint32_t LBO_A = ((A_MN ? BK * 128u : 16u) >> 4) << 16, LBO_B = ((B_MN ? BK * 128u : 16u) >> 4) << 16;
+      constexpr uint32_t KSTEP_A = (A_MN ? UMMA_K * 128u : UMMA_K * 2u) >> 4;
+      constexpr uint32_t KSTEP_B = (B_MN ? UMMA_K * 128u : UMMA_K * 2u) >> 4;
+      const uint32_t base_lo = __shfl_sync(0xffffffffu, (smem_u32(smem) & 0x3FFFFu) >> 4, 0);
+      uint32_t stage = 0, phase = 0, tile_it = 0;
       Sched sched(p, cluster_id, num_clusters);
       WorkUnit w;
       for (; sched.next(p, w); ++tile_it) {
@@ -350,27 +383,25 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         mbar_wait(&tmem_empty[acc], acc_ph ^ 1);      // both CTAs' epilogues have drained this buffer
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * ACC_COLS;
-        for (int i = 0; i < w.nkb; ++i, ++it) {
-          const int s = it % STAGES;
-          const uint32_t ph = (it / STAGES) & 1;
-          mbar_wait(&full_bar[s], ph);
+        for (int i = 0; i < w.nkb; ++i) {
+          mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
-          const uint32_t sb = sa + A_BYTES;
+          const uint32_t a_lo = base_lo + stage * (STAGE_BYTES >> 4) + LBO_A;
+          const uint32_t b_lo = base_lo + stage * (STAGE_BYTES >> 4) + (A_BYTES >> 4) + LBO_B;
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k) {
-            // K-major, 128B swizzle : 8-row groups are 1024 B apart (SBO); a K step of 16 is 32 B inside the row.
-            // MN-major, 128B swizzle: 64-wide MN groups are BK*128 B apart (LBO), 8-deep K groups 1024 B (SBO);
-            //                         a K step of 16 is 16 rows = 2048 B.
-            const uint64_t da = A_MN ? umma_smem_desc_sw128(sa + k * (UMMA_K * 128), BK * 128, 1024)
-                                     : umma_smem_desc_sw128(sa + k * (UMMA_K * 2), 16, 1024);
-            const uint64_t db = B_MN ? umma_smem_desc_sw128(sb + k * (UMMA_K * 128), BK * 128, 1024)
-                                     : umma_smem_desc_sw128(sb + k * (UMMA_K * 2), 16, 1024);
-            umma2_f16(tmem_d, da, db, idesc, (i > 0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < BK / UMMA_K; ++k)
+              umma2_f16_lh(tmem_d, a_lo + k * KSTEP_A, HI, b_lo + k * KSTEP_B, HI, idesc, (i > 0 || k > 0) ? 1u : 0u);
+            umma2_commit_mc(&empty_bar[stage]);   // frees this smem slot in both CTAs once the MMAs have read it
           }
-          umma2_commit_mc(&empty_bar[s]);   // frees this smem slot in both CTAs once the MMAs have read it
+          __syncwarp();
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
         }
-        umma2_commit_mc(&tmem_full[acc]);   // accumulator complete: wakes the epilogue warps of both CTAs
+        if (elect_one()) umma2_commit_mc(&tmem_full[acc]);   // accumulator complete: wakes the epilogue warps of both CTAs
+        __syncwarp();
       }
     }
   } else {

@@ -251,6 +251,44 @@ def test_cuda_graph_replay_matches_eager():
     assert rel_l2(dict(m.named_parameters())[k].grad, 2 * eager[0][3][k]) < 1e-4
 
 
+@pytest.mark.parametrize("bs", [8, 9])
+def test_row_chains_match_single_chain(bs):
+    """engine.py `_parts`: the images of a step are split into two row chains that run the Block stacks on two
+    streams (forward and backward; the weight gradients reduce over all rows on the side stream).  Same weights, inputs
+    and noise must give the single-chain result (identical kernels on row ranges; only fp32 atomic accumulation order
+    of the LayerNorm / bias / mask-token gradients may differ) -- eager and replayed from CUDA graphs; bs=9 splits the
+    18 images 9 / 9 with two-images-per-tile attention packing inside an odd half."""
+    import csmae_b200
+    cfg = dict(dim_model=128, encoder_num_layers=2, encoder_num_heads=2, decoder_embed_dim=64, decoder_num_layers=2,
+               decoder_num_heads=2, input_size=96, patch_size=16, predictor_hidden_size=128)
+    g = torch.Generator(device="cuda").manual_seed(11)
+    x1, x2 = (torch.randn(bs, 3, 96, 96, device="cuda", generator=g) for _ in range(2))
+    n1, n2 = (torch.rand(bs, 36, device="cuda", generator=g) for _ in range(2))
+    res = {}
+    for chains in (1, 2):
+        torch.manual_seed(0)
+        m = csmae_b200.MAE_ViT_MsLdCeCd(**cfg, device="cuda").cuda().train()
+        m._engine.num_chains = chains
+        runs = []
+        for _ in range(4):                       # 2 eager warm-up steps, capture, replay
+            for p in m.parameters():
+                p.grad = None
+            loss, pred, mask = m(x1, x2, 0.75, noise=[n1, n2])
+            loss.backward()
+            runs.append((loss.detach().clone(), pred.clone(), mask.clone(),
+                         {k: p.grad.clone() for k, p in m.named_parameters() if p.grad is not None}))
+        assert m._engine._active_graph is not None
+        assert len(m._engine._parts(2 * bs, torch.device("cuda", 0))) == chains
+        res[chains] = runs
+    for a, b in zip(res[2], res[1]):
+        assert torch.equal(a[2], b[2])
+        assert abs(a[0].item() - b[0].item()) <= 1e-6 * abs(b[0].item()) + 1e-7
+        assert rel_l2(a[1], b[1]) < 1e-6
+        assert a[3].keys() == b[3].keys()
+        for k in b[3]:
+            assert rel_l2(a[3][k], b[3][k]) < 1e-4, k
+
+
 EDGE_CASES = {
     "batch1": dict(bs=1, size=96, ratio=0.75),
     "keep1_of_16": dict(bs=3, size=64, ratio=0.9),            # int(16 * 0.1) = 1 kept patch -> encoder S = 2
