@@ -111,19 +111,7 @@ __device__ __forceinline__ void tmem_st_32x8(uint32_t taddr, const uint32_t* r) 
                : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-// D[tmem] (+)= A[tmem, bf16 pairs packed along K] * B[smem desc]
-__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
-                                            uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
-      "}\n" ::"r"(tmem_d),
-      "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-
+// D[tmem] (+)= A[tmem, bf16 pairs packed along K] * B[smem descriptor as {lo, hi} words]
 __device__ __forceinline__ void umma_f16_ts_lh(uint32_t tmem_d, uint32_t tmem_a, uint32_t b_lo, uint32_t b_hi,
                                                uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -356,9 +344,15 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
     // Fold the P.V result of iteration prev_it into the running output.  The two key halves were exponentiated
     // against their OWN row maximum (no exchange before the exp): their partial outputs O_h and partial sums l_h are
     // combined here with the factors exp2((m_h - m) * c).
+#ifdef CSM_ATTN_TIMING
+    long long acc_t[16] = {0};
+#endif
     auto drain = [&]() {
+      ATT_T(d0);
       mbar_wait_wd(o_full, prev_it & 1);
       tc_fence_after();
+      ATT_T(d1);
+      ATT_ACC(4, d1, d0);      // wait: P.V product of the previous iteration
       uint32_t o0[OC], o1[OC];
       const uint32_t oaddr = tmem_base + lane_off + COL_O + half * OC;
       tmem_ld_32x16(oaddr, o0);
@@ -396,6 +390,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
         }
         if (half == 0) *prev_lse = m_run * c + log2f(l_run);
       }
+      ATT_T(d2);
+      ATT_ACC(5, d2, d1);      // read-back of O, rescale, store
     };
 
     for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
@@ -426,8 +422,10 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
           const int nfull = kvalid >> 4;
           const int rem = kvalid & 15;
           const uint32_t buf = it & 1;
+          ATT_T(t0);
           mbar_wait_wd(&s_full[buf], (it >> 1) & 1);
           tc_fence_after();
+          ATT_T(t1);
           uint32_t su[NG * 16], tu[16];
           const uint32_t taddr = tmem_base + lane_off + buf * BN + colbase;
 #pragma unroll
@@ -452,7 +450,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
           }
           const float m_h = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
           const float mc = m_h * c;
+          ATT_T(t2);
           if (!PTMEM && have_prev) drain();              // also: the P tile in shared memory is free again
+          ATT_T(t3);
           float ls[4] = {0.f, 0.f, 0.f, 0.f};
           auto store_p = [&](int g, const uint32_t* pk) {
             if (PTMEM) {
@@ -496,15 +496,24 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
           const uint32_t xo = buf * 256 + half * 128 + row;
           xm[xo] = m_h;
           xl[xo] = (ls[0] + ls[1]) + (ls[2] + ls[3]);
+          ATT_T(t4);
           if (PTMEM) {
             if (have_prev) drain();
+            ATT_T(t5);
             tmem_st_wait();
+            ATT_T(t6);
+            ATT_ACC(6, t6, t5);
           } else {
             fence_proxy_async();
           }
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(p_full);
+          ATT_T(t7);
+          ATT_ACC(0, t1, t0);      // wait: S = Q K^T
+          ATT_ACC(1, t2, t1);      // tcgen05.ld of the scores + row maximum
+          ATT_ACC(2, t4, t3);      // exp2, row sum, pack, tcgen05.st / st.shared of P
+          ATT_ACC(3, t7, t0);      // whole iteration
           have_prev = 1;
           prev_it = it;
           prev_first = (j == 0);
@@ -516,6 +525,12 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
       }
     }
     if (have_prev) drain();
+#ifdef CSM_ATTN_TIMING
+    if (warp == 4 && lane == 0) {
+      for (int i = 0; i < 8; ++i) atomicAdd(&g_attn_phase[i], static_cast<unsigned long long>(acc_t[i]));
+      atomicAdd(&g_attn_phase[15], static_cast<unsigned long long>(it));
+    }
+#endif
   }
 
   __syncwarp();
@@ -598,7 +613,9 @@ int attn_fwd_tc_launch(const void* qkv, void* out, float* lse, int B, int S, int
 // and stored directly when the sequence is a single key block, else reduced into the (zeroed) dQ columns with
 // red.global.add.bf16x2.  The softmax warps release the S / dP tiles as soon as they hold them in registers, so the
 // next sub-block's first two products run under the exp / dS arithmetic of the current one.
-// delta = rowsum(dO * O) comes from attn_delta_kernel.
+// The per-row statistics of a sub-block (L2 = the forward's log-sum-exp, delta = rowsum(dO * O) from attn_delta_kernel)
+// are staged by the two otherwise idle warps of warp group 0 into a two-deep shared-memory ring, one sub-block ahead:
+// the softmax threads read them with one ld.shared each instead of carrying prefetched global loads across iterations.
 // ---------------------------------------------------------------------------------------------
 struct BwdParams {
   int B, S, H, Dm, HG;
@@ -649,33 +666,6 @@ __device__ __forceinline__ void red_add_bf16x2_v4(void* gptr, uint4 v) {
                : "memory");
 }
 
-// the sub-block sequence of one CTA: items (stride gridDim.x) x query tiles x heads of the group
-struct BwdIter {
-  int item, i, hh, nh, hg, bi, kb;
-  __device__ __forceinline__ void set_item(const BwdParams& p, int NH) {
-    kb = item % p.NT;
-    const int r = item / p.NT;
-    hg = r % p.HG;
-    bi = r / p.HG;
-    nh = min(NH, p.H - hg * NH);
-  }
-  __device__ __forceinline__ void init(const BwdParams& p, int NH) {
-    item = blockIdx.x;
-    i = hh = 0;
-    if (item < p.items) set_item(p, NH);
-  }
-  __device__ __forceinline__ bool valid(const BwdParams& p) const { return item < p.items; }
-  __device__ __forceinline__ bool last_of_item(const BwdParams& p) const { return hh == nh - 1 && i == p.NT - 1; }
-  __device__ __forceinline__ void next(const BwdParams& p, int NH) {
-    if (++hh < nh) return;
-    hh = 0;
-    if (++i < p.NT) return;
-    i = 0;
-    item += gridDim.x;
-    if (item < p.items) set_item(p, NH);
-  }
-};
-
 constexpr int ATB_SM_WARPS = 16;
 constexpr int ATB_THREADS = 32 * (4 + ATB_SM_WARPS);   // 640
 
@@ -685,7 +675,6 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
                    const BwdParams p) {
   constexpr int NH = 64 / DH;
   constexpr int KS = DH / 16;
-  constexpr int OC = DH / 2;           // gradient columns owned by one softmax thread
   constexpr uint32_t COL_S = 0, COL_DP = 128, COL_DK = 256, COL_DV = 256 + NH * DH, COL_DQ = 256 + 2 * NH * DH;
   static_assert(COL_DQ + 2 * DH <= 512, "TMEM budget");
   extern __shared__ uint8_t smem_raw[];
@@ -705,7 +694,11 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
   uint64_t* grads_done = bars + 11;    // dV / dK / dQ products of a sub-block complete
   uint64_t* dq_free = bars + 12;       // [2] dQ partial buffer read out
   uint64_t* dkv_free = bars + 14;      // dK / dV of an item read out
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
+  uint64_t* st_full = bars + 15;       // [2] row statistics of a sub-block staged (warps 2 and 3)
+  uint64_t* st_empty = bars + 17;      // [2] ... and read by the 16 softmax warps
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 19);
+  float* sL = reinterpret_cast<float*>(bars + 20);   // [2][128] L2 = log-sum-exp (base 2) of the row; +inf = padded row
+  float* sD = sL + 256;                              // [2][128] delta = rowsum(dO * O)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -719,6 +712,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
       mbar_init(&q_full[i], 1);
       mbar_init(&q_empty[i], 1);
       mbar_init(&dq_free[i], ATB_SM_WARPS);
+      mbar_init(&st_full[i], 2);
+      mbar_init(&st_empty[i], ATB_SM_WARPS);
     }
     mbar_init(sdp_full, 1);
     mbar_init(sdp_free, ATB_SM_WARPS);
@@ -740,8 +735,46 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
   const int NT = p.NT;
 
   if (warp < 4) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
-    if (warp == 0) {
+    // The register pool setmaxnreg.inc draws from holds only what this CTA's own warps released: the CTA was
+    // launched with 640 x 96 registers, so 4 x 32 x 64 + 16 x 32 x 104 = 61440 is the most that can be redistributed.
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
+    if (warp >= 2) {
+      // ------------------------------ row statistics (warps 2 and 3) ------------------------------
+      // Same sub-block sequence as the other roles.  Warp 2 stages L2[row] (the forward's log-sum-exp, +inf for padded
+      // rows), warp 3 delta[row] = rowsum(dO * O) (attn_delta_kernel), four rows per lane, one sub-block ahead of the
+      // softmax warps.  (Forming delta here from the dO tile in shared memory and the O rows was built and measured:
+      // the two warps then issue as much as a softmax warp on two of the four schedulers, 181 -> 241 us.)
+      const float* src = warp == 2 ? p.lse : p.delta;
+      float* dst = warp == 2 ? sL : sD;
+      const float pad = warp == 2 ? INFINITY : 0.f;      // padded query row: p = exp2(s - inf) = 0
+      uint32_t n = 0;
+      for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
+        const int r_ = item / NT;
+        const int hg = r_ % p.HG;
+        const int bi = r_ / p.HG;
+        const int nh = min(NH, p.H - hg * NH);
+        for (int i = 0; i < NT; ++i) {
+          for (int hh = 0; hh < nh; ++hh, ++n) {
+            const uint32_t sb = n & 1;
+            const int h = hg * NH + hh;
+            float v[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const int r = lane + 32 * k;
+              const int b_img = p.pack ? 2 * bi + (r >> 6) : bi;
+              const int tok = p.pack ? (r & 63) : i * 128 + r;
+              v[k] = pad;
+              if (tok < p.S && b_img < p.B) v[k] = __ldg(src + (static_cast<size_t>(b_img) * p.H + h) * p.S + tok);
+            }
+            mbar_wait_wd(&st_empty[sb], ((n >> 1) & 1) ^ 1);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) dst[sb * 128 + lane + 32 * k] = v[k];
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&st_full[sb]);
+          }
+        }
+      }
+    } else if (warp == 0) {
       // ------------------------------ TMA producer ------------------------------
       if (lane == 0) {
         uint32_t ic = 0, qc = 0;
@@ -912,27 +945,6 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
       else tmem_ld_32x8(addr, v);
     };
 
-    BwdIter cur, nxt;
-    cur.init(p, NH);
-    nxt = cur;
-    // per-item token bookkeeping of this thread's TMEM lane (32-bit: B * H * S < 2^31)
-    auto img_of = [&](const BwdIter& it) { return p.pack ? 2 * it.bi + (row >> 6) : it.bi; };
-    auto tok_of = [&](int t) { return p.pack ? (row & 63) : t * 128 + row; };
-    auto load_stats = [&](const BwdIter& it, float& L, float& d) {
-      const int b_img = img_of(it), tok = tok_of(it.i);
-      L = INFINITY;      // padded query row: p = exp2(-inf) = 0
-      d = 0.f;
-      if (tok < p.S && b_img < p.B) {
-        const uint32_t o = (static_cast<uint32_t>(b_img) * p.H + it.hg * NH + it.hh) * p.S + tok;
-        L = __ldg(p.lse + o);
-        d = __ldg(p.delta + o);
-      }
-    };
-    float Lc = INFINITY, dc = 0.f;
-    if (cur.valid(p)) {
-      load_stats(cur, Lc, dc);
-      nxt.next(p, NH);
-    }
     uint32_t n = 0;
     // deferred read-backs of the previous sub-block
     uint32_t have_prev;
@@ -984,113 +996,126 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
     long long acc_t[16] = {0};
 #endif
 #pragma unroll 1
-    while (cur.valid(p)) {
-      ATT_T(t0);
-      const int bn = (cur.kb == NT - 1) ? p.bn_last : 128;
+    for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
+      // ---- per item: key block, head group, image(s); this thread's keys and its token rows ----
+      const int kb = item % NT;
+      const int r_ = item / NT;
+      const int hg = r_ % p.HG;
+      const int bi = r_ / p.HG;
+      const int nh = min(NH, p.H - hg * NH);
+      const int bn = (kb == NT - 1) ? p.bn_last : 128;
       const int bnq = bn >> 2;                  // keys of this thread's quarter: one or two 16-key groups
       const int colbase = cq * bnq;
-      int kvalid = p.pack ? (((row >> 6) == (cq >> 1)) ? p.S - (cq & 1) * 32 : 0) : (p.S - cur.kb * 128 - colbase);
+      int kvalid = p.pack ? (((row >> 6) == (cq >> 1)) ? p.S - (cq & 1) * 32 : 0) : (p.S - kb * 128 - colbase);
       kvalid = max(0, min(kvalid, bnq));
-      // statistics of the next sub-block's row: in flight during this sub-block
-      float Ln = INFINITY, dn = 0.f;
-      if (nxt.valid(p)) load_stats(nxt, Ln, dn);
-
-      ATT_T(t1);
-      mbar_wait_wd(sdp_full, n & 1);
-      tc_fence_after();
-      ATT_T(t2);
-      uint32_t su[32], du[32];
+      const int b_img = p.pack ? 2 * bi + (row >> 6) : bi;
+      const bool img_ok = b_img < p.B;
+      const int tk = p.pack ? (row & 63) : kb * 128 + row;
+      const int krow = (tk < p.S && img_ok) ? b_img * p.S + tk : -1;
+      const int col0 = hg * NH * DH;
       const uint32_t ts = tmem_base + lane_off + COL_S + colbase;
       const uint32_t td = tmem_base + lane_off + COL_DP + colbase;
+      const uint32_t gc = static_cast<uint32_t>(colbase >> 3);
+#pragma unroll 1
+      for (int i = 0; i < NT; ++i) {
+        const int tq = p.pack ? (row & 63) : i * 128 + row;
+        const int qrow = (tq < p.S && img_ok) ? b_img * p.S + tq : -1;
+#pragma unroll 1
+        for (int hh = 0; hh < nh; ++hh, ++n) {
+          ATT_T(t0);
+          const uint32_t sb = n & 1;
+          mbar_wait_wd(&st_full[sb], (n >> 1) & 1);
+          const float Lc = sL[sb * 128 + row], dc = sD[sb * 128 + row];
+          ATT_T(t1);
+          mbar_wait_wd(sdp_full, n & 1);
+          tc_fence_after();
+          ATT_T(t2);
+          uint32_t su[32], du[32];
 #pragma unroll
-      for (int q = 0; q < 2; ++q) {
-        if (q * 16 < kvalid) {
-          tmem_ld_32x16(ts + q * 16, su + q * 16);
-          tmem_ld_32x16(td + q * 16, du + q * 16);
-        }
-      }
-      tmem_ld_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(sdp_free);       // the next sub-block's S / dP products may overwrite the tiles
-      ATT_T(t3);
-
-      // P and dS of this thread's keys, packed to bf16 pairs (in place over the scores)
-#pragma unroll
-      for (int q = 0; q < 2; ++q) {
-        const int lim = kvalid - q * 16;          // valid keys of the group (warp-uniform)
-        if (lim > 0) {
-          if (lim < 16) {
-#pragma unroll
-            for (int e = 1; e < 16; ++e)
-              if (e >= lim) su[q * 16 + e] = 0xff800000u;          // masked key: p = 0, dS = 0
+          for (int q = 0; q < 2; ++q) {
+            if (q * 16 < kvalid) {
+              tmem_ld_32x16(ts + q * 16, su + q * 16);
+              tmem_ld_32x16(td + q * 16, du + q * 16);
+            }
           }
-#pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const float p0 = ex2f(fmaf(__uint_as_float(su[q * 16 + 2 * e]), c, -Lc));
-            const float p1 = ex2f(fmaf(__uint_as_float(su[q * 16 + 2 * e + 1]), c, -Lc));
-            su[q * 16 + e] = pack_bf16x2(p0, p1);
-            du[q * 16 + e] = pack_bf16x2(p0 * (__uint_as_float(du[q * 16 + 2 * e]) - dc),
-                                         p1 * (__uint_as_float(du[q * 16 + 2 * e + 1]) - dc));
-          }
-        } else {
-#pragma unroll
-          for (int e = 0; e < 8; ++e) su[q * 16 + e] = du[q * 16 + e] = 0u;
-        }
-      }
-      // the previous sub-block's gradient products are done: the P / dS tiles may be rewritten and its dQ partial
-      // (and dK / dV) read.  The stores go first so that they drain under the read-back, before the proxy fence.
-      ATT_T(t4);
-      if (have_prev) {
-        mbar_wait_wd(grads_done, (n - 1) & 1);
-        tc_fence_after();
-      }
-      ATT_T(t5);
-#pragma unroll
-      for (int q = 0; q < 2; ++q) {
-        if (q * 16 < bnq) {
-          const uint32_t gc = static_cast<uint32_t>((colbase >> 3) + 2 * q);
-          const uint32_t o0 = (gc >> 3) * 16384 + (((gc & 7) ^ sw7) << 4);
-          const uint32_t o1 = ((gc + 1) >> 3) * 16384 + ((((gc + 1) & 7) ^ sw7) << 4);
-          sts_v4(p_row + o0, make_uint4(su[q * 16 + 0], su[q * 16 + 1], su[q * 16 + 2], su[q * 16 + 3]));
-          sts_v4(p_row + o1, make_uint4(su[q * 16 + 4], su[q * 16 + 5], su[q * 16 + 6], su[q * 16 + 7]));
-          sts_v4(ds_row + o0, make_uint4(du[q * 16 + 0], du[q * 16 + 1], du[q * 16 + 2], du[q * 16 + 3]));
-          sts_v4(ds_row + o1, make_uint4(du[q * 16 + 4], du[q * 16 + 5], du[q * 16 + 6], du[q * 16 + 7]));
-        }
-      }
-      ATT_T(t6);
-      if (have_prev) read_back();
-      ATT_T(t7);
-      fence_proxy_async();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(pds_full);
-      ATT_T(t8);
-      ATT_ACC(0, t1, t0);      // loop head: bookkeeping + statistics prefetch issue
-      ATT_ACC(1, t2, t1);      // wait: S / dP products
-      ATT_ACC(2, t3, t2);      // tcgen05.ld of S / dP + release
-      ATT_ACC(3, t4, t3);      // exp / dS arithmetic
-      ATT_ACC(4, t5, t4);      // wait: previous gradient products
-      ATT_ACC(5, t6, t5);      // st.shared of P / dS
-      ATT_ACC(6, t7, t6);      // read-back of dQ (dK / dV)
-      ATT_ACC(7, t8, t7);      // proxy fence + arrive
+          tmem_ld_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(sdp_free);       // the next sub-block's S / dP products may overwrite the tiles
+          ATT_T(t3);
 
-      have_prev = 1;
-      {
-        const int b_img = img_of(cur);
-        const int tq = tok_of(cur.i), tk = tok_of(cur.kb);
-        prev_qrow = (tq < p.S && b_img < p.B) ? b_img * p.S + tq : -1;
-        prev_col0 = cur.hg * NH * DH;
-        prev_col = prev_col0 + cur.hh * DH;
-        prev_nh = cur.nh;
-        prev_last_item = cur.last_of_item(p);
-        if (prev_last_item) prev_krow = (tk < p.S && b_img < p.B) ? b_img * p.S + tk : -1;
+          // P and dS of this thread's keys, packed to bf16 pairs (in place over the scores)
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            const int lim = kvalid - q * 16;          // valid keys of the group (warp-uniform)
+            if (lim > 0) {
+              if (lim < 16) {
+#pragma unroll
+                for (int e = 1; e < 16; ++e)
+                  if (e >= lim) su[q * 16 + e] = 0xff800000u;          // masked key: p = 0, dS = 0
+              }
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                const float p0 = ex2f(fmaf(__uint_as_float(su[q * 16 + 2 * e]), c, -Lc));
+                const float p1 = ex2f(fmaf(__uint_as_float(su[q * 16 + 2 * e + 1]), c, -Lc));
+                su[q * 16 + e] = pack_bf16x2(p0, p1);
+                du[q * 16 + e] = pack_bf16x2(p0 * (__uint_as_float(du[q * 16 + 2 * e]) - dc),
+                                             p1 * (__uint_as_float(du[q * 16 + 2 * e + 1]) - dc));
+              }
+            } else {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) su[q * 16 + e] = du[q * 16 + e] = 0u;
+            }
+          }
+          // the previous sub-block's gradient products are done: the P / dS tiles may be rewritten
+          ATT_T(t4);
+          if (have_prev) {
+            mbar_wait_wd(grads_done, (n - 1) & 1);
+            tc_fence_after();
+          }
+          ATT_T(t5);
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            if (q * 16 < bnq) {
+              const uint32_t g0 = gc + 2 * q;
+              const uint32_t o0 = (g0 >> 3) * 16384 + (((g0 & 7) ^ sw7) << 4);
+              const uint32_t o1 = ((g0 + 1) >> 3) * 16384 + ((((g0 + 1) & 7) ^ sw7) << 4);
+              sts_v4(p_row + o0, make_uint4(su[q * 16 + 0], su[q * 16 + 1], su[q * 16 + 2], su[q * 16 + 3]));
+              sts_v4(p_row + o1, make_uint4(su[q * 16 + 4], su[q * 16 + 5], su[q * 16 + 6], su[q * 16 + 7]));
+              sts_v4(ds_row + o0, make_uint4(du[q * 16 + 0], du[q * 16 + 1], du[q * 16 + 2], du[q * 16 + 3]));
+              sts_v4(ds_row + o1, make_uint4(du[q * 16 + 4], du[q * 16 + 5], du[q * 16 + 6], du[q * 16 + 7]));
+            }
+          }
+          ATT_T(t6);
+          fence_proxy_async();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            mbar_arrive(pds_full);
+            mbar_arrive(&st_empty[sb]);   // every lane has consumed its statistics: the ring slot may be refilled
+          }
+          ATT_T(t7);
+          // the read-back of the previous sub-block's dQ (dK / dV) runs under this sub-block's gradient products
+          if (have_prev) read_back();
+          ATT_T(t8);
+          ATT_ACC(0, t1, t0);      // wait: row statistics
+          ATT_ACC(1, t2, t1);      // wait: S / dP products
+          ATT_ACC(2, t3, t2);      // tcgen05.ld of S / dP + release
+          ATT_ACC(3, t4, t3);      // exp / dS arithmetic
+          ATT_ACC(4, t5, t4);      // wait: previous gradient products
+          ATT_ACC(5, t6, t5);      // st.shared of P / dS
+          ATT_ACC(7, t7, t6);      // proxy fence + arrive
+          ATT_ACC(6, t8, t7);      // read-back of dQ (dK / dV)
+
+          have_prev = 1;
+          prev_qrow = qrow;
+          prev_krow = krow;
+          prev_col0 = col0;
+          prev_col = col0 + hh * DH;
+          prev_nh = nh;
+          prev_last_item = (hh == nh - 1) && (i == NT - 1);
+        }
       }
-      cur = nxt;
-      Lc = Ln;
-      dc = dn;
-      if (nxt.valid(p)) nxt.next(p, NH);
-      ++n;
     }
     if (have_prev) {
       mbar_wait_wd(grads_done, (n - 1) & 1);
@@ -1168,7 +1193,7 @@ int attn_bwd_tc_launch(const void* qkv, const void* o, const void* d_out, const 
       return CSM_ERR_CUDA;
     }
   }
-  const size_t smem = 1024 + 4 * 32768 + 65536 + 256;
+  const size_t smem = 1024 + 4 * 32768 + 65536 + 256 + 2048;
   auto kern = attn_bwd_tc_kernel<DH>;
   static bool configured = false;
   if (!configured) {

@@ -22,7 +22,19 @@ delta = torch.empty(B * H * S, device="cuda")
 lib = nat.load()
 lib.csm_attn_phase_read.argtypes = [ctypes.c_void_p]
 buf = (ctypes.c_ulonglong * 16)()
+for _ in range(3):
+    nat.call("csm_attention_fwd", qkv, out, lse, B, S, H, d)
+lib.csm_attn_phase_read(buf)
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
 nat.call("csm_attention_fwd", qkv, out, lse, B, S, H, d)
+e1.record()
+lib.csm_attn_phase_read(buf)
+n = max(buf[15], 1)
+print(f"forward B={B} S={S} H={H} d={d}: {e0.elapsed_time(e1) * 1e3:.1f} us (instrumented), {n} iterations over the sampled warps")
+for i, nm in enumerate(["wait S", "tcgen05.ld + row max", "exp2 / sum / pack / store P", "whole iteration", "drain: wait P.V",
+                        "drain: O read-back", "tcgen05.st wait"]):
+    print(f"  {nm:28s} {buf[i] / n:8.0f} clk/iteration")
 for _ in range(3):
     nat.call("csm_attention_bwd", qkv, out, d_out, lse, delta, dqkv, None, B, S, H, d)
 lib.csm_attn_phase_read(buf)
@@ -32,7 +44,7 @@ nat.call("csm_attention_bwd", qkv, out, d_out, lse, delta, dqkv, None, B, S, H, 
 e1.record()
 lib.csm_attn_phase_read(buf)
 n = max(buf[15], 1)
-names = ["head/bookkeeping", "wait S,dP", "tcgen05.ld+release", "exp/dS math", "wait grads(n-1)", "st.shared P,dS",
+names = ["wait row statistics", "wait S,dP", "tcgen05.ld+release", "exp/dS math", "wait grads(n-1)", "st.shared P,dS",
          "read-back dQ/dK/dV", "fence+arrive", "MMA: wait P,dS", "MMA: issue grads", "MMA: wait sdp_free", "MMA: issue S,dP"]
 print(f"B={B} S={S} H={H} d={d}: {e0.elapsed_time(e1) * 1e3:.1f} us (instrumented), {n} sub-blocks over the sampled warps")
 tot = sum(buf[i] for i in range(8))
