@@ -621,6 +621,8 @@ struct BwdParams {
   int B, S, H, Dm, HG;
   int pack;          // two images per 128-row tile (S <= 64)
   int NT;            // 128-row query tiles == 128-key blocks per image
+  int acc;           // NT == 2: a CTA takes both key blocks of a (image, head group) back to back and dQ accumulates in
+                     // TMEM across them (no partial-dQ reduction in global memory)
   int bn_last;       // keys in the last key block (multiple of 64)
   int items;
   float c, scale;
@@ -666,6 +668,14 @@ __device__ __forceinline__ void red_add_bf16x2_v4(void* gptr, uint4 v) {
                : "memory");
 }
 
+// k-th work item of this CTA.  An item is (image or image pair, head group, key block), id = (.. * HG + hg) * NT + kb.
+// Plain mode: items are dealt round-robin.  acc mode: units (image, head group) are dealt round-robin and a CTA walks
+// the NT key blocks of its unit consecutively.
+__device__ __forceinline__ int bwd_item(const BwdParams& p, int k) {
+  if (!p.acc) return blockIdx.x + k * gridDim.x;
+  return (blockIdx.x + (k / p.NT) * gridDim.x) * p.NT + k % p.NT;
+}
+
 constexpr int ATB_SM_WARPS = 16;
 constexpr int ATB_THREADS = 32 * (4 + ATB_SM_WARPS);   // 640
 
@@ -676,7 +686,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
   constexpr int NH = 64 / DH;
   constexpr int KS = DH / 16;
   constexpr uint32_t COL_S = 0, COL_DP = 128, COL_DK = 256, COL_DV = 256 + NH * DH, COL_DQ = 256 + 2 * NH * DH;
-  static_assert(COL_DQ + 2 * DH <= 512, "TMEM budget");
+  static_assert(COL_DQ + 2 * NH * DH <= 512, "TMEM budget (acc mode: NT = 2 query tiles x NH heads x DH columns of dQ)");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sKV = smem;                 // [2 stages][K 16 KB | V 16 KB]
@@ -748,7 +758,9 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
       float* dst = warp == 2 ? sL : sD;
       const float pad = warp == 2 ? INFINITY : 0.f;      // padded query row: p = exp2(s - inf) = 0
       uint32_t n = 0;
-      for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
+      for (int k = 0;; ++k) {
+        const int item = bwd_item(p, k);
+        if (item >= p.items) break;
         const int r_ = item / NT;
         const int hg = r_ % p.HG;
         const int bi = r_ / p.HG;
@@ -778,7 +790,9 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
       // ------------------------------ TMA producer ------------------------------
       if (lane == 0) {
         uint32_t ic = 0, qc = 0;
-        for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++ic) {
+        for (;; ++ic) {
+          const int item = bwd_item(p, static_cast<int>(ic));
+          if (item >= p.items) break;
           const int kb = item % NT;
           const int r = item / NT;
           const int hg = r % p.HG;
@@ -825,7 +839,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
       // pending sub-block: its gradient products are issued after the NEXT sub-block's S / dP products
       bool pend = false;
       uint32_t pd_n = 0, pd_ic = 0, pd_ks = 0, pd_qs = 0;
-      int pd_hh = 0, pd_i = 0, pd_bn = 0;
+      int pd_hh = 0, pd_i = 0, pd_bn = 0, pd_kb = 0;
       bool pd_last_tile = false, pd_last_item = false;
 #ifdef CSM_ATTN_TIMING
       long long acc_t[16] = {0};
@@ -836,14 +850,20 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
         ATT_T(g1);
         ATT_ACC(8, g1, g0);
         if (pd_i == 0 && pd_hh == 0 && pd_ic > 0) mbar_wait_wd(dkv_free, (pd_ic - 1) & 1);   // previous item's dK / dV read
-        if (pd_n >= 2) mbar_wait_wd(&dq_free[pd_n & 1], ((pd_n >> 1) - 1) & 1);              // dQ buffer read out
+        if (!p.acc) {
+          if (pd_n >= 2) mbar_wait_wd(&dq_free[pd_n & 1], ((pd_n >> 1) - 1) & 1);            // dQ buffer read out
+        } else if (pd_kb == 0 && pd_i == 0 && pd_hh == 0 && pd_ic >= static_cast<uint32_t>(NT)) {
+          mbar_wait_wd(&dq_free[0], (pd_ic / NT - 1) & 1);                                   // previous unit's dQ read out
+        }
         tc_fence_after();
         const uint32_t hoff = DH == 32 ? static_cast<uint32_t>(pd_hh) * 4u : 0u;            // 64 bytes per head
         const uint32_t q_lo = base_lo + OFF_QO + pd_qs * 2048u + hoff + LBO_MN;
         const uint32_t do_lo = q_lo + 1024u;                                                // dO tile: + 16 KB
         const uint32_t k_lo = base_lo + pd_ks * 2048u + hoff + LBO_MN;
         const uint32_t tm_dv = tmem_base + COL_DV + pd_hh * DH, tm_dk = tmem_base + COL_DK + pd_hh * DH;
-        const uint32_t tm_dq = tmem_base + COL_DQ + (pd_n & 1) * DH;
+        // plain: the partial of a sub-block goes to one of two buffers; acc: one accumulator per (query tile, head)
+        const uint32_t tm_dq = tmem_base + COL_DQ + (p.acc ? (pd_i * NH + pd_hh) * DH : (pd_n & 1) * DH);
+        const uint32_t accq = (p.acc && pd_kb > 0) ? 1u : 0u;
         const uint32_t acc0 = pd_i > 0 ? 1u : 0u;
         const int ksteps = pd_bn >> 4;             // 4 or 8
         if (elect_one()) {
@@ -857,7 +877,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
           for (int ks = 0; ks < 8; ++ks) {         // dQ_i (partial) = dS K   (reduction over the keys of the block)
             if (ks < ksteps)
               umma_f16_lh(tm_dq, ds_lo_k + (ks >> 2) * 1024 + (ks & 3) * 2, HI, k_lo + ks * 128, HI, idesc_q,
-                          ks > 0 ? 1u : 0u);
+                          ks > 0 ? 1u : accq);
           }
           umma_commit(grads_done);
           if (pd_last_tile) umma_commit(&q_empty[pd_qs]);
@@ -867,7 +887,9 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
         ATT_T(g2);
         ATT_ACC(9, g2, g1);
       };
-      for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++ic) {
+      for (;; ++ic) {
+        const int item = bwd_item(p, static_cast<int>(ic));
+        if (item >= p.items) break;
         const int kb = item % NT;
         const int hg = (item / NT) % p.HG;
         const int nh = min(NH, p.H - hg * NH);
@@ -903,7 +925,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
             ATT_ACC(11, m2, m1);
             if (pend) grads();
             pend = true;
-            pd_n = n; pd_ic = ic; pd_ks = ks; pd_qs = qs; pd_hh = hh; pd_i = i; pd_bn = bn;
+            pd_n = n; pd_ic = ic; pd_ks = ks; pd_qs = qs; pd_hh = hh; pd_i = i; pd_bn = bn; pd_kb = kb;
             pd_last_tile = (hh == nh - 1);
             pd_last_item = pd_last_tile && (i == NT - 1);
           }
@@ -929,7 +951,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
     const uint32_t ds_row = smem_u32(sdS) + row * 128;
     const uint32_t sw7 = static_cast<uint32_t>(row & 7);
     const uint32_t ld3 = 3u * p.Dm;
-    const bool reduce_dq = NT > 1;
+    const bool reduce_dq = NT > 1 && !p.acc;
     constexpr int OQ = DH / 4;                // gradient columns read back by one thread (8 or 16)
 
     auto pack8 = [&](const uint32_t* v, float mul) -> uint4 {
@@ -949,26 +971,48 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
     // deferred read-backs of the previous sub-block
     uint32_t have_prev;
     asm volatile("mov.u32 %0, 0;" : "=r"(have_prev));
-    bool prev_last_item = false;
+    bool prev_last_item = false, prev_last_kb = false;
     int prev_qrow = -1, prev_krow = -1;       // global token rows (or -1: padded)
-    int prev_col = 0, prev_col0 = 0, prev_nh = 0;
+    int prev_col = 0, prev_col0 = 0, prev_nh = 0, prev_img = 0;
 
     // dQ partial of sub-block n - 1 and, after the last sub-block of an item, its dK / dV
     auto read_back = [&]() {
-      uint32_t vq[OQ];
-      tmem_ld_oq(tmem_base + lane_off + COL_DQ + ((n - 1) & 1) * DH + cq * OQ, vq);
-      tmem_ld_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&dq_free[(n - 1) & 1]);
-      if (prev_qrow >= 0) {
-        __nv_bfloat16* dst = p.dqkv + static_cast<size_t>(prev_qrow) * ld3 + prev_col + cq * OQ;
+      if (!p.acc) {
+        uint32_t vq[OQ];
+        tmem_ld_oq(tmem_base + lane_off + COL_DQ + ((n - 1) & 1) * DH + cq * OQ, vq);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&dq_free[(n - 1) & 1]);
+        if (prev_qrow >= 0) {
+          __nv_bfloat16* dst = p.dqkv + static_cast<size_t>(prev_qrow) * ld3 + prev_col + cq * OQ;
 #pragma unroll
-        for (int q8 = 0; q8 < OQ / 8; ++q8) {
-          const uint4 pk = pack8(vq + q8 * 8, p.scale);
-          if (reduce_dq) red_add_bf16x2_v4(dst + q8 * 8, pk);
-          else *reinterpret_cast<uint4*>(dst + q8 * 8) = pk;
+          for (int q8 = 0; q8 < OQ / 8; ++q8) {
+            const uint4 pk = pack8(vq + q8 * 8, p.scale);
+            if (reduce_dq) red_add_bf16x2_v4(dst + q8 * 8, pk);
+            else *reinterpret_cast<uint4*>(dst + q8 * 8) = pk;
+          }
         }
+      } else if (prev_last_item && prev_last_kb) {
+        // acc mode, end of a unit: the dQ accumulators of all its (query tile, head) pairs, summed over the key blocks
+        // (bringing all accumulators into registers first and releasing TMEM before the stores was measured slower:
+        //  160 -> 170 us on the decoder shape, the wider live range costs more than the earlier release returns)
+#pragma unroll 1
+        for (int t = 0; t < NT * prev_nh; ++t) {
+          const int i = t / prev_nh, hh = t - i * prev_nh;
+          uint32_t vq[OQ];
+          tmem_ld_oq(tmem_base + lane_off + COL_DQ + (i * NH + hh) * DH + cq * OQ, vq);
+          tmem_ld_wait();
+          const int tq = i * 128 + row;
+          if (tq < p.S) {
+            __nv_bfloat16* dst = p.dqkv + (static_cast<size_t>(prev_img) * p.S + tq) * ld3 + prev_col0 + hh * DH + cq * OQ;
+#pragma unroll
+            for (int q8 = 0; q8 < OQ / 8; ++q8) *reinterpret_cast<uint4*>(dst + q8 * 8) = pack8(vq + q8 * 8, p.scale);
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&dq_free[0]);
       }
       if (prev_last_item) {
 #pragma unroll 1
@@ -996,7 +1040,9 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
     long long acc_t[16] = {0};
 #endif
 #pragma unroll 1
-    for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
+    for (int k = 0;; ++k) {
+      const int item = bwd_item(p, k);
+      if (item >= p.items) break;
       // ---- per item: key block, head group, image(s); this thread's keys and its token rows ----
       const int kb = item % NT;
       const int r_ = item / NT;
@@ -1114,6 +1160,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
           prev_col = col0 + hh * DH;
           prev_nh = nh;
           prev_last_item = (hh == nh - 1) && (i == NT - 1);
+          prev_last_kb = (kb == NT - 1);
+          prev_img = b_img;
         }
       }
     }
@@ -1167,6 +1215,7 @@ int attn_bwd_tc_launch(const void* qkv, const void* o, const void* d_out, const 
     p.NT = (S + 127) / 128;
     p.bn_last = ((S - (p.NT - 1) * 128) + 63) & ~63;
     p.items = B * p.HG * p.NT;
+    p.acc = p.NT == 2 ? 1 : 0;      // NT * (64 / DH) * DH = 128 dQ accumulator columns fit beside S, dP, dK, dV
   }
   p.scale = 1.0f / sqrtf(static_cast<float>(DH));
   p.c = 1.4426950408889634f * p.scale;
@@ -1184,7 +1233,7 @@ int attn_bwd_tc_launch(const void* qkv, const void* o, const void* d_out, const 
       return CSM_ERR_CUDA;
     }
   }
-  if (p.NT > 1) {
+  if (p.NT > 1 && !p.acc) {
     // several key blocks reduce their dQ partials into the dQ columns of dqkv: start from zero
     cudaError_t me = cudaMemset2DAsync(dqkv, static_cast<size_t>(3) * Dm * 2, 0, static_cast<size_t>(Dm) * 2,
                                        static_cast<size_t>(B) * S, stream);
@@ -1210,7 +1259,8 @@ int attn_bwd_tc_launch(const void* qkv, const void* o, const void* d_out, const 
   if (rc) return rc;
   rc = csm_tensor_map_2d(&tdo, d_out, Dm, static_cast<uint64_t>(B) * S, Dm, 64, box_rows, 2, 128);
   if (rc) return rc;
-  const int grid = p.items < device_sms() ? p.items : device_sms();
+  const int units = p.acc ? p.items / p.NT : p.items;
+  const int grid = units < device_sms() ? units : device_sms();
   cudaError_t le = csm_launch_pdl(kern, dim3(grid), dim3(ATB_THREADS), smem, stream, tq, tdo, p);
   if (le != cudaSuccess) {
     csm_set_error("attention_bwd: launch failed: %s", cudaGetErrorString(le));
