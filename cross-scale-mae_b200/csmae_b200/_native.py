@@ -56,6 +56,8 @@ SIGNATURES = {
     "csm_adamw_multi": [_P, _P, _I, _P, _I, _P],
     "csm_grad_stats_f32": [_P, _L, _P, _P, _I, _P],
     "csm_sincos_pos_embed": [_P, _I, _I, _I, _P],
+    "csm_loss_finalize": [_P, _P, _P, _I, _P],
+    "csm_zero_async": [_P, _L, _P],
     "csm_amp_update": [_P, _P, _P, _P, _F, _F, _F, _I, _P],
     "csm_sumsq_f32": [_P, _L, _P, _I, _P],
 }
@@ -72,7 +74,7 @@ _lib = None
 _lock = threading.Lock()
 _sm_count = {}
 launch_count = 0   # kernels launched through the C-ABI so far (bench.py reports the delta)
-KERNELS_PER_CALL = {"csm_ntxent_fwd": 2, "csm_decoder_assemble_bwd": 2, "csm_attention_bwd": 2}
+KERNELS_PER_CALL = {"csm_ntxent_fwd": 2, "csm_decoder_assemble_bwd": 2, "csm_attention_bwd": 2, "csm_zero_async": 0}
 
 
 class NativeError(RuntimeError):

@@ -464,7 +464,7 @@ class HotPathEngine:
 
         # ---- losses ----------------------------------------------------------------------------
         loss_acc = buf("loss_acc", (8,), f32)
-        loss_acc.zero_()
+        call("csm_zero_async", loss_acc, 32)
         norm_pix = 1 if m.norm_pix_loss else 0
         for s, im in enumerate(imgs_list):
             call("csm_recon_loss_fwd", pred_full[s * N * Sd:], im, mask[s * N:], loss_acc[s:], N, C, H, p, L, norm_pix)
@@ -492,7 +492,9 @@ class HotPathEngine:
             fnorm = buf("ntx.fnorm", (NB,), f32)
             neg = buf("ntx.neg", (NB,), f32)
             call("csm_ntxent_fwd", x, zhat, fnorm, neg, loss_acc[3:], N, Se, D, NTXENT_TAU, NTXENT_EPS)
-        loss = (loss_acc * self._coefs_tensor(coefs, dev)).sum()
+        loss = buf("loss", (1,), f32)
+        call("csm_loss_finalize", loss_acc, self._coefs_tensor(coefs, dev), loss, 8)
+        loss = loss.view(())
         st["coefs"] = coefs
         st["red"] = red
         self._state = st
@@ -682,7 +684,23 @@ class HotPathEngine:
             offs.append(total)
             total += (s_ + 3) // 4 * 4                         # keep every gradient 16-byte aligned
         if flat is None:
-            flat = torch.zeros(total, dtype=f32, device=dev)
+            flat = torch.empty(total, dtype=f32, device=dev)
+        # The weight-gradient GEMMs reduce-add their split-K partials and the bias / LayerNorm / token gradients are
+        # atomic column sums, so the buffer starts from zero: a memset on the side stream, hidden under the first
+        # kernels of the chain (loss gradients, decoder_pred dgrad), which do not touch it.
+        main = torch.cuda.current_stream(dev) if flat.is_cuda else None
+        zeroed = None
+        if flat.is_cuda:
+            if self.use_side_stream:
+                side = self._side_stream(dev)
+                self._wait(side, main)
+                with torch.cuda.stream(side):
+                    call("csm_zero_async", flat, total * 4)
+                zeroed = torch.cuda.Event()
+                zeroed.record(side)
+                self._side_dirty = True
+            else:
+                call("csm_zero_async", flat, total * 4)
         else:
             flat.zero_()
         G = {n: flat[o:o + s_].view(params[n].shape) for n, o, s_ in zip(names, offs, sizes)}
@@ -705,10 +723,14 @@ class HotPathEngine:
         for s, im in enumerate(st["imgs"]):
             call("csm_recon_loss_bwd", B["pred_full"][s * N * Sd:], im, B["mask"][s * N:], dpred[s * N * Sd:], g, coef,
                  N, C, H, p, L, norm_pix)
-        call("csm_linear_wgrad", dpred, B["dec_bf16"], G["decoder_pred.weight"], rows_d, P, Dd, nsm)
-        call("csm_colsum_bf16", dpred, G["decoder_pred.bias"], rows_d, P, 0, nsm)
+        def side_pred():
+            call("csm_linear_wgrad", dpred, B["dec_bf16"], G["decoder_pred.weight"], rows_d, P, Dd, nsm)
+            call("csm_colsum_bf16", dpred, G["decoder_pred.bias"], rows_d, P, 0, nsm)
+        self._on_side(dev, side_pred)
         d_dec = buf("b.dec.dln", (rows_d, Dd), bf16)
         call("csm_linear_dgrad", dpred, w16["decoder_pred.weight"], d_dec, None, rows_d, P, Dd, EPI_BF16)
+        if zeroed is not None:
+            main.wait_event(zeroed)              # from here on the chain itself adds into the gradient buffer
 
         # ---- cross-scale decoder loss through the predictor (MsLdCeCd.py:57-59) ------------------
         dy2 = None
@@ -718,15 +740,19 @@ class HotPathEngine:
             dy2 = buf("b.dy2", (rows_d, Dd), f32)
             d_cp = buf("b.d_cp", (N * Sd, Dd), bf16)
             call("csm_cross_mse_bwd", B["pred.cp"], B["dec_f32"], d_cp, dy2, g, st["coefs"][2], N * Sd, Sd, Dd)
-            call("csm_linear_wgrad", d_cp, B["pred.a1"], G["predictor.3.weight"], N * Sd, Dd, Hp, nsm)
-            call("csm_colsum_bf16", d_cp, G["predictor.3.bias"], N * Sd, Dd, 0, nsm)
+            def side_p3():
+                call("csm_linear_wgrad", d_cp, B["pred.a1"], G["predictor.3.weight"], N * Sd, Dd, Hp, nsm)
+                call("csm_colsum_bf16", d_cp, G["predictor.3.bias"], N * Sd, Dd, 0, nsm)
+            self._on_side(dev, side_p3)
             d_a1 = buf("b.d_a1", (N * Sd, Hp), bf16)
             call("csm_linear_dgrad", d_cp, w16["predictor.3.weight"], d_a1, None, N * Sd, Dd, Hp, EPI_BF16)
             dh1 = buf("b.dh1", (N * Sd, Hp), bf16)
             call("csm_bn_patch_bwd", B["pred.h1"], B["pred.a1"], d_a1, bn.weight, B["pred.bn_mean"], B["pred.bn_rstd"],
                  dh1, G["predictor.1.weight"], G["predictor.1.bias"], N, L, Hp, 1 if st["training"] else 0)
-            call("csm_linear_wgrad", dh1, B["dec_bf16"][N * Sd:], G["predictor.0.weight"], N * Sd, Hp, Dd, nsm)
-            call("csm_colsum_bf16", dh1, G["predictor.0.bias"], N * Sd, Hp, 0, nsm)
+            def side_p0():
+                call("csm_linear_wgrad", dh1, B["dec_bf16"][N * Sd:], G["predictor.0.weight"], N * Sd, Hp, Dd, nsm)
+                call("csm_colsum_bf16", dh1, G["predictor.0.bias"], N * Sd, Hp, 0, nsm)
+            self._on_side(dev, side_p0)
             call("csm_linear_dgrad", dh1, w16["predictor.0.weight"], dy2[N * Sd:], None, N * Sd, Hp, Dd, EPI_F32)
 
         # ---- decoder_norm, decoder blocks (row chains, as in the forward) ---------------------------

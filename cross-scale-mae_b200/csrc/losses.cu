@@ -706,6 +706,29 @@ extern "C" int csm_recon_loss_bwd(const void* pred_full_bf16, const float* imgs,
   return CSM_OK;
 }
 
+// loss = sum_i acc[i] * coef[i]: the scalar the step returns, from the accumulator array every loss kernel adds into
+// (n <= 32 terms; one warp)
+__global__ void loss_finalize_kernel(const float* __restrict__ acc, const float* __restrict__ coef,
+                                     float* __restrict__ loss, int n) {
+  pdl_wait();
+  pdl_trigger();
+  const int lane = threadIdx.x;
+  float v = lane < n ? acc[lane] * coef[lane] : 0.f;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if (lane == 0) *loss = v;
+}
+
+extern "C" int csm_loss_finalize(const float* loss_terms, const float* coefs, float* loss, int n, cudaStream_t stream) {
+  CSM_CHECK_ARG(n > 0 && n <= 32, "csm_loss_finalize: 1..32 terms (n=%d)", n);
+  cudaError_t e = csm_launch_pdl(loss_finalize_kernel, dim3(1), dim3(32), 0, stream, loss_terms, coefs, loss, n);
+  if (e != cudaSuccess) {
+    csm_set_error("csm_loss_finalize: launch failed: %s", cudaGetErrorString(e));
+    return CSM_ERR_CUDA;
+  }
+  return CSM_OK;
+}
+
 extern "C" int csm_cross_mse_fwd(const void* cp_bf16, const float* tgt, float* loss_sum, int rows, int Sd, int Dd,
                                  cudaStream_t stream) {
   CSM_CHECK_ARG(rows > 0 && Dd % 4 == 0, "csm_cross_mse_fwd: bad sizes rows=%d Dd=%d", rows, Dd);

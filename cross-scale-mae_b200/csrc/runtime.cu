@@ -35,3 +35,14 @@ extern "C" int csm_device_check(int device) {
   }
   return prop.multiProcessorCount;
 }
+
+// Zeroes device memory with a memset node (no kernel): loss accumulators, the flat gradient buffer.
+extern "C" int csm_zero_async(void* ptr, long long nbytes, cudaStream_t stream) {
+  CSM_CHECK_ARG(ptr != nullptr && nbytes >= 0, "csm_zero_async: bad arguments");
+  cudaError_t e = cudaMemsetAsync(ptr, 0, static_cast<size_t>(nbytes), stream);
+  if (e != cudaSuccess) {
+    csm_set_error("csm_zero_async: cudaMemsetAsync failed: %s", cudaGetErrorString(e));
+    return CSM_ERR_CUDA;
+  }
+  return CSM_OK;
+}

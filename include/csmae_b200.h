@@ -76,6 +76,8 @@ int csm_resized_crop(const float* imgs, float* out, int planes, int H, int W, in
                      csm_stream_t stream);
 /* fixed 2-D sin-cos position table [cls_token + G*G, embed_dim] f32 (util/pos_embed.py:16-63; w-coordinate first, cls
  * row zero), evaluated in fp64 and rounded once -- init-time (MAE_ViT_Baseline.py:203-218) */
+/* zeroes nbytes of device memory asynchronously (a memset node when captured into a CUDA graph) */
+int csm_zero_async(void* ptr, long long nbytes, csm_stream_t stream);
 int csm_sincos_pos_embed(float* out, int embed_dim, int grid_size, int cls_token, csm_stream_t stream);
 /* kept patches -> GEMM operand rows [(nimg*(keep+1)), C*p*p] in Conv2d (c,py,px) order; cls slot rows zero
  * (timm PatchEmbed conv, MAE_ViT_Baseline.py:75-77,245, fused with the masking gather :251) */
@@ -120,6 +122,9 @@ int csm_recon_loss_fwd(const void* pred_full_bf16, const float* imgs, const floa
 int csm_recon_loss_bwd(const void* pred_full_bf16, const float* imgs, const float* mask, void* dpred_bf16,
                        const float* grad_scalar, float coef, int nimg, int C, int H, int p, int L, int norm_pix,
                        csm_stream_t stream);
+/* loss = sum_i loss_terms[i] * coefs[i], i < n <= 32: the scalar of MAE_ViT_MsLdCeCd.py:62-69 from the accumulator array
+ * every loss kernel adds its raw sum into */
+int csm_loss_finalize(const float* loss_terms, const float* coefs, float* loss, int n, csm_stream_t stream);
 /* cross-scale decoder MSE, target not detached (MAE_ViT_MsLdCeCd.py:57-59) */
 int csm_cross_mse_fwd(const void* cp_bf16, const float* tgt, float* loss_sum, int rows, int Sd, int Dd,
                       csm_stream_t stream);
