@@ -80,7 +80,11 @@ class _GraphSequence:
         kw = {} if self._pool is None else {"pool": self._pool}
         if self._stream is not None:
             kw["stream"] = self._stream
-        self._ctx = torch.cuda.graph(g, capture_error_mode="thread_local", **kw)
+        # "relaxed": with an NCCL process group in the process, the capturing thread itself can end up in a call CUDA
+        # classes as potentially unsafe (an event query or free from a collected Work / Event object, an allocator
+        # call) and a stricter mode then invalidates the whole capture (seen on 2-GPU boxes, tests/test_ddp_gpu.py);
+        # none of those calls is part of the captured work
+        self._ctx = torch.cuda.graph(g, capture_error_mode="relaxed", **kw)
         self._ctx.__enter__()
         self.graphs.append(g)
 
@@ -373,7 +377,7 @@ class HotPathEngine:
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
         c0 = nat.launch_count
-        with torch.cuda.graph(g, capture_error_mode="thread_local"):
+        with torch.cuda.graph(g, capture_error_mode="relaxed"):
             out = self._forward_eager(entry["imgs"], entry["noise"], mask_ratio, training)
         entry["fwd_launches"] = nat.launch_count - c0      # kernels recorded, not run: counted at each replay
         nat.launch_count = c0

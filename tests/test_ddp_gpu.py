@@ -76,7 +76,7 @@ def _worker(rank, world, port, q):
         dist.broadcast(flat, 0)
         dist.all_gather(allm, bn.running_mean.detach().clone())
         assert torch.equal(allm[0], allm[1]) and torch.equal(allm[0], allm[rank])
-        assert int(bn.num_batches_tracked.item()) == 5
+        assert int(bn.num_batches_tracked.item()) == 6       # the local step above + the five wrapped steps
         # torch's own wrapper, exactly as main_pretrain.py:417-421 builds it
         model._engine.enable_grad_sync(None, 1)
         tddp = torch.nn.parallel.DistributedDataParallel(model, device_ids=[rank], find_unused_parameters=True)
