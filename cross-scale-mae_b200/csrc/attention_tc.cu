@@ -48,17 +48,7 @@ struct FwdParams {
 };
 
 // bounded wait: a protocol error traps (the launch fails with an error) instead of hanging the device
-__device__ __forceinline__ void mbar_wait_wd(uint64_t* bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
-  long long t0 = 0;
-  for (uint32_t tries = 1; !mbar_try_wait(bar, parity); ++tries) {
-    if ((tries & 1023u) == 0) {            // the clock is read once per 1024 failed tries: the wait loop itself
-      const long long t = clock64();      // stays two instructions long
-      if (t0 == 0) t0 = t;
-      else if (t - t0 > 4000000000ll) __trap();
-    }
-  }
-}
+__device__ __forceinline__ void mbar_wait_wd(uint64_t* bar, uint32_t parity) { mbar_wait_bounded(bar, parity); }
 
 __device__ __forceinline__ void tmem_ld_32x8(uint32_t taddr, uint32_t* r) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"

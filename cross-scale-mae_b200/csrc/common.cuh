@@ -244,9 +244,44 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");                                          // of spinning through the issue slots of its scheduler
   return ok != 0;
 }
+// The wait loop as ONE asm block (scoped labels): try_wait (which suspends the warp up to the hint), branch -- nothing
+// else per wake-up.  A third of all instructions the attention backward issued were the compiler's version of this
+// loop (select, compare, counter, watchdog clock) run by warps that are waiting anyway, in the issue slots of the
+// warps that are not.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  while (!mbar_try_wait(bar, parity)) {
-  }
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n"
+      "MBAR_WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n\t"
+      "@P1 bra MBAR_WAIT_DONE;\n\t"
+      "bra MBAR_WAIT_LOOP;\n"
+      "MBAR_WAIT_DONE:\n\t"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity), "r"(0x989680u)
+      : "memory");
+}
+// the same with a bound on the number of wake-ups: a protocol error traps (the launch fails) instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait_bounded(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1, P2;\n\t"
+      ".reg .u32 cnt;\n\t"
+      "mov.u32 cnt, 0;\n"
+      "MBAR_WAITB_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2, %3;\n\t"
+      "@P1 bra MBAR_WAITB_DONE;\n\t"
+      "add.u32 cnt, cnt, 1;\n\t"
+      "setp.lt.u32 P2, cnt, 0x4000000;\n\t"
+      "@P2 bra MBAR_WAITB_LOOP;\n"
+      "MBAR_WAITB_DONE:\n\t"
+      "selp.u32 %0, 1, 0, P1;\n\t"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u)
+      : "memory");
+  if (!ok) __trap();
 }
 
 // ---------------------------------------------------------------------------------------------
