@@ -454,6 +454,22 @@ def test_cross_mse(nat):
     close(d_cp.view(N, Sd, Dd), ref, 1e-2, 1e-7, "cross mse d_cp")
 
 
+def test_loss_finalize_and_zero(nat):
+    """csm_zero_async + csm_loss_finalize: the accumulator array every loss kernel adds into is cleared by a memset
+    node and dotted with the coefficients of MAE_ViT_MsLdCeCd.py:62-69 / MAE_ViT_MsLd.py:61-66 by one warp."""
+    acc = rnd(8, seed=3).abs() * 100
+    coefs = torch.tensor([1 / 3.0, 0.25, 1e-3, 1.0, 0.0, 0.0, 0.0, 0.0], device="cuda")
+    loss = torch.full((1,), float("nan"), device="cuda")
+    nat.call("csm_loss_finalize", acc, coefs, loss, 8)
+    close(loss, (acc.double() * coefs.double()).sum().float().reshape(1), 1e-6, 1e-6, "loss finalize")
+    big = torch.ones(1 << 20, device="cuda")
+    nat.call("csm_zero_async", big[16:], (big.numel() - 32) * 4)
+    torch.cuda.synchronize()
+    assert big[:16].eq(1).all() and big[-16:].eq(1).all() and big[16:-16].eq(0).all()
+    with pytest.raises(nat.NativeError):
+        nat.call("csm_loss_finalize", acc, coefs, loss, 33)
+
+
 # N >= 8 with N/8 rows x Hp x 2 B <= 96 KB (48 KB for the backward): the channel is spread over a cluster of 8 CTAs
 # (rows staged in shared memory, sums through DSMEM); (11, ...) leaves two CTAs of the cluster without rows;
 # N = 4 and the eval-mode call take the one-CTA-per-channel kernels

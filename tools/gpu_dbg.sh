@@ -1,5 +1,5 @@
 #!/bin/bash
-timeout 900 python -m pytest tests/test_kernels_gpu.py -m gpu -q -x --timeout 600 2>&1 | grep -v "^$" | tail -3
-timeout 300 python tools/opbench.py --only attn 2>&1 | tail -4
-timeout 300 python tools/opbench.py --only gemm 2>&1 | grep "enc.fc1\|dec.fc1\|dec.proj" 
-timeout 300 python bench.py --quick --steps 30 --warmup 5 2>gpurun_out/err.log || tail -5 gpurun_out/err.log
+for rep in 1 2; do
+for cfg in "CSMAE_PDL=1" "CSMAE_PDL=0" "CSMAE_SIDE_STREAM=0"; do
+  env $cfg timeout 300 python bench.py --quick --steps 40 --warmup 5 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('$cfg', round(d['ms_step'],3), d['clocks']['sm_mhz'])"
+done; done
