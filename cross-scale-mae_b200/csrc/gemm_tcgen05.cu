@@ -811,8 +811,11 @@ int choose_bn(int M, int N, int num_clusters, bool b_mn) {
   const int tiles_m = csm_cdiv(M, 2 * BM);
   int best_bn = 256;
   long long best_cost = -1;
-  const int cands_k[4] = {256, 192, 128, 64};
-  for (int i = 0; i < 4; ++i) {
+  // any multiple of 32 is a legal width (UMMA N % 16 == 0, 8-row swizzle atoms per CTA half, 32-column epilogue chunks);
+  // 224 and 160 are what the M = 6400 encoder shapes want: N = 2304 -> 275 units of 256 x 224 in 4 rounds instead of
+  // 225 of 256 x 256 in 4, N = 768 -> 125 units of 256 x 160 in 2 rounds instead of 100 of 256 x 192 in 2
+  const int cands_k[7] = {256, 224, 192, 160, 128, 96, 64};
+  for (int i = 0; i < 7; ++i) {
     const int bn = cands_k[i];
     if (b_mn && (bn % 128) != 0) continue;     // MN-major B is loaded in 64-wide groups per CTA
     const long long tiles = static_cast<long long>(tiles_m) * csm_cdiv(N, bn);

@@ -36,8 +36,9 @@ def close(a, b, rtol, atol, what=""):
 
 
 # ------------------------------------------------------------------------------------------------ GEMM
+# (6400, 768) / (6400, 2304) / (2560, 672): the tile-width chooser takes 160- / 224- / 96-column cluster tiles
 GEMM_SHAPES = [(128, 128, 64), (256, 384, 128), (200, 136, 72), (3200, 768, 768), (1000, 2304, 768),
-               (394, 64, 64), (64, 192, 64), (12608, 512, 2048)]
+               (394, 64, 64), (64, 192, 64), (12608, 512, 2048), (6400, 768, 256), (6400, 2304, 128), (2560, 672, 128)]
 
 
 @pytest.mark.parametrize("M,N,K", GEMM_SHAPES)
@@ -49,7 +50,8 @@ def test_linear_fwd_bf16(nat, M, N, K):
     close(out, ref, 1e-2, 1e-2, "linear_fwd bf16")      # bf16 output rounding (2^-8 relative)
 
 
-@pytest.mark.parametrize("M,N,K", [(256, 256, 128), (1000, 3072, 768), (200, 136, 72)])
+@pytest.mark.parametrize("M,N,K", [(256, 256, 128), (1000, 3072, 768), (200, 136, 72), (6400, 768, 128),
+                                   (6400, 2304, 64), (2560, 672, 128)])
 def test_linear_fwd_gelu_resid_f32(nat, M, N, K):
     x, w, b = rnd(M, K, dtype=bf16), rnd(N, K, scale=K ** -0.5, dtype=bf16), rnd(N)
     ref = x.float() @ w.float().t() + b
