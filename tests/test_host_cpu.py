@@ -374,3 +374,19 @@ def test_checkpoint_round_trip_and_finetune_key_remap(tmp_path):
     assert remapped["pos_embed"].shape == (1, L + 1, D)          # what interpolate_pos_embed expects
     assert remapped["blocks.0.attn.qkv.weight"].shape == (3 * D, D)
     assert remapped["patch_embed.proj.weight"].shape == (D, 3, 16, 16)
+
+
+def test_setmaxnreg_regions_fit_their_registers():
+    """ptxas does not bound the code after `setmaxnreg.dec N` by itself in every case and `setmaxnreg.inc` can only
+    draw from what the CTA released: tools/check_setmaxnreg.py scans the SASS of the attention kernels (the only users)
+    for the highest register used by the warps that released registers."""
+    import shutil
+    import subprocess
+    from csmae_b200 import build
+    obj = os.path.join(build.LIB_DIR, "obj", "attention_tc.o")
+    if not os.path.exists(obj) or shutil.which("cuobjdump") is None:
+        pytest.skip("object file or cuobjdump not available")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "check_setmaxnreg.py"), obj], capture_output=True,
+                       text=True)
+    assert r.returncode == 0, r.stdout
+    assert r.stdout.count("ok ") >= 4, r.stdout

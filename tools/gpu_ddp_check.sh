@@ -1,5 +1,5 @@
 #!/bin/bash
-# N-GPU check: the 2-rank gradient-equivalence test and a short bench line at N GPUs.  Usage: tools/gpu_r2e_ddp.sh N
+# N-GPU check: the 2-rank gradient-equivalence test and a short bench line at N GPUs.  Usage: tools/gpu_ddp_check.sh N
 N=${1:-2}
 mkdir -p gpurun_out
 timeout 600 python -m pytest tests/test_ddp_gpu.py tests/test_kernels_gpu.py -m gpu -q -k "two_rank or loss_finalize" --timeout 500 2>&1 | tail -3
