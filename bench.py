@@ -314,10 +314,12 @@ def measure(env, args, arch, B, S, steps, warmup, full):
     torch.manual_seed(1 + rank)      # masking noise: per-rank stream (main_pretrain.py:368-369)
 
     def step(x1, x2):
-        opt.zero_grad(set_to_none=True)
+        # order of engine_pretrain.py:41-75: forward, backward + optimizer step, THEN zero_grad -- the host drops the
+        # 258 gradient references while the GPU runs the optimizer kernel, not before the next step's first kernel
         loss, _, _ = step_model(x1, x2, MASK_RATIO)
         loss.backward()
         opt.step()
+        opt.zero_grad(set_to_none=True)
         return loss
 
     for _ in range(max(warmup, 3)):
