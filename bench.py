@@ -390,6 +390,7 @@ def measure(env, args, arch, B, S, steps, warmup, full):
         l_, _, _ = step_model(imgs1, imgs2, MASK_RATIO)
         l_.backward()
     out["ms_fwd_bwd"] = env.timed(fwd_bwd, max(3, steps // 2))
+    opt.zero_grad(set_to_none=True)
 
     # host-side cost of enqueueing one step (no synchronisation inside): if this approaches ms_per_step the
     # path is launch-bound on the CPU
