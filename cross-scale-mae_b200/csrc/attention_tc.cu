@@ -937,11 +937,19 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
     const int row = quarter * 32 + lane;
     const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
     const float c = p.c;
-    const uint32_t p_row = smem_u32(sP) + row * 128;
-    const uint32_t ds_row = smem_u32(sdS) + row * 128;
+    // pinned bases (csm::pin): under the 96-register cap of this 640-thread CTA the compiler otherwise re-derives the
+    // shared-memory window address (~8 instructions) and this thread's TMEM lane offset (~6) at every barrier
+    // operation, statistics read and tcgen05.ld of the loop
+    const uint32_t sbar = pin(smem_u32(bars));                           // + 8 * index of a barrier
+    const uint32_t s_stat = pin(smem_u32(sL) + row * 4);                 // L2 of this row; delta 1024 B further
+    const uint32_t tlane = pin(tmem_base + lane_off);
+    const uint32_t p_row = pin(smem_u32(sP) + row * 128);
+    const uint32_t ds_row = p_row + 32768;
     const uint32_t sw7 = static_cast<uint32_t>(row & 7);
     const uint32_t ld3 = 3u * p.Dm;
     const bool reduce_dq = NT > 1 && !p.acc;
+    constexpr uint32_t B_SDP_FULL = 8 * 8, B_SDP_FREE = 9 * 8, B_PDS_FULL = 10 * 8, B_GRADS = 11 * 8, B_DQ_FREE = 12 * 8,
+                       B_DKV_FREE = 14 * 8, B_ST_FULL = 15 * 8, B_ST_EMPTY = 17 * 8;
     constexpr int OQ = DH / 4;                // gradient columns read back by one thread (8 or 16)
 
     auto pack8 = [&](const uint32_t* v, float mul) -> uint4 {
@@ -969,11 +977,11 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
     auto read_back = [&]() {
       if (!p.acc) {
         uint32_t vq[OQ];
-        tmem_ld_oq(tmem_base + lane_off + COL_DQ + ((n - 1) & 1) * DH + cq * OQ, vq);
+        tmem_ld_oq(tlane + COL_DQ + ((n - 1) & 1) * DH + cq * OQ, vq);
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&dq_free[(n - 1) & 1]);
+        if (lane == 0) mbar_arrive_a(sbar + B_DQ_FREE + ((n - 1) & 1) * 8);
         if (prev_qrow >= 0) {
           __nv_bfloat16* dst = p.dqkv + static_cast<size_t>(prev_qrow) * ld3 + prev_col + cq * OQ;
 #pragma unroll
@@ -991,7 +999,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
         for (int t = 0; t < NT * prev_nh; ++t) {
           const int i = t / prev_nh, hh = t - i * prev_nh;
           uint32_t vq[OQ];
-          tmem_ld_oq(tmem_base + lane_off + COL_DQ + (i * NH + hh) * DH + cq * OQ, vq);
+          tmem_ld_oq(tlane + COL_DQ + (i * NH + hh) * DH + cq * OQ, vq);
           tmem_ld_wait();
           const int tq = i * 128 + row;
           if (tq < p.S) {
@@ -1002,14 +1010,14 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&dq_free[0]);
+        if (lane == 0) mbar_arrive_a(sbar + B_DQ_FREE);
       }
       if (prev_last_item) {
 #pragma unroll 1
         for (int hh = 0; hh < prev_nh; ++hh) {
           uint32_t vk[OQ], vv[OQ];
-          tmem_ld_oq(tmem_base + lane_off + COL_DK + hh * DH + cq * OQ, vk);
-          tmem_ld_oq(tmem_base + lane_off + COL_DV + hh * DH + cq * OQ, vv);
+          tmem_ld_oq(tlane + COL_DK + hh * DH + cq * OQ, vk);
+          tmem_ld_oq(tlane + COL_DV + hh * DH + cq * OQ, vv);
           tmem_ld_wait();
           if (prev_krow >= 0) {
             __nv_bfloat16* dst = p.dqkv + static_cast<size_t>(prev_krow) * ld3 + prev_col0 + hh * DH + cq * OQ;
@@ -1022,7 +1030,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(dkv_free);
+        if (lane == 0) mbar_arrive_a(sbar + B_DKV_FREE);
       }
     };
 
@@ -1049,8 +1057,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
       const int tk = p.pack ? (row & 63) : kb * 128 + row;
       const int krow = (tk < p.S && img_ok) ? b_img * p.S + tk : -1;
       const int col0 = hg * NH * DH;
-      const uint32_t ts = tmem_base + lane_off + COL_S + colbase;
-      const uint32_t td = tmem_base + lane_off + COL_DP + colbase;
+      const uint32_t ts = tlane + COL_S + colbase;
+      const uint32_t td = tlane + COL_DP + colbase;
       const uint32_t gc = static_cast<uint32_t>(colbase >> 3);
 #pragma unroll 1
       for (int i = 0; i < NT; ++i) {
@@ -1060,10 +1068,10 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
         for (int hh = 0; hh < nh; ++hh, ++n) {
           ATT_T(t0);
           const uint32_t sb = n & 1;
-          mbar_wait_wd(&st_full[sb], (n >> 1) & 1);
-          const float Lc = sL[sb * 128 + row], dc = sD[sb * 128 + row];
+          mbar_wait_bounded_a(sbar + B_ST_FULL + sb * 8, (n >> 1) & 1);
+          const float Lc = lds_f32(s_stat + sb * 512), dc = lds_f32(s_stat + 1024 + sb * 512);
           ATT_T(t1);
-          mbar_wait_wd(sdp_full, n & 1);
+          mbar_wait_bounded_a(sbar + B_SDP_FULL, n & 1);
           tc_fence_after();
           ATT_T(t2);
           uint32_t su[32], du[32];
@@ -1077,7 +1085,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
           tmem_ld_wait();
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(sdp_free);       // the next sub-block's S / dP products may overwrite the tiles
+          if (lane == 0) mbar_arrive_a(sbar + B_SDP_FREE);       // the next sub-block's S / dP products may overwrite the tiles
           ATT_T(t3);
 
           // P and dS of this thread's keys, packed to bf16 pairs (in place over the scores)
@@ -1106,7 +1114,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
           // the previous sub-block's gradient products are done: the P / dS tiles may be rewritten
           ATT_T(t4);
           if (have_prev) {
-            mbar_wait_wd(grads_done, (n - 1) & 1);
+            mbar_wait_bounded_a(sbar + B_GRADS, (n - 1) & 1);
             tc_fence_after();
           }
           ATT_T(t5);
@@ -1127,8 +1135,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
           tc_fence_before();
           __syncwarp();
           if (lane == 0) {
-            mbar_arrive(pds_full);
-            mbar_arrive(&st_empty[sb]);   // every lane has consumed its statistics: the ring slot may be refilled
+            mbar_arrive_a(sbar + B_PDS_FULL);
+            mbar_arrive_a(sbar + B_ST_EMPTY + sb * 8);   // every lane has consumed its statistics: the ring slot may be refilled
           }
           ATT_T(t7);
           // the read-back of the previous sub-block's dQ (dK / dV) runs under this sub-block's gradient products
@@ -1156,7 +1164,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
       }
     }
     if (have_prev) {
-      mbar_wait_wd(grads_done, (n - 1) & 1);
+      mbar_wait_bounded_a(sbar + B_GRADS, (n - 1) & 1);
       tc_fence_after();
       read_back();
     }

@@ -261,6 +261,43 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "r"(parity), "r"(0x989680u)
       : "memory");
 }
+// Variants over a 32-bit shared-window address.  In a register-starved loop the compiler re-derives a generic pointer's
+// shared address at every use (cvta of the dynamic shared-memory base, the 1024-byte alignment: ~8 instructions);
+// a base the compiler cannot see through (csm::pin) plus immediate offsets costs none.
+__device__ __forceinline__ uint32_t pin(uint32_t v) {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %1;" : "=r"(r) : "r"(v));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_a(uint32_t bar_addr) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_addr) : "memory");
+}
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void mbar_wait_bounded_a(uint32_t bar_addr, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1, P2;\n\t"
+      ".reg .u32 cnt;\n\t"
+      "mov.u32 cnt, 0;\n"
+      "MBAR_WAITA_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2, %3;\n\t"
+      "@P1 bra MBAR_WAITA_DONE;\n\t"
+      "add.u32 cnt, cnt, 1;\n\t"
+      "setp.lt.u32 P2, cnt, 0x4000000;\n\t"
+      "@P2 bra MBAR_WAITA_LOOP;\n"
+      "MBAR_WAITA_DONE:\n\t"
+      "selp.u32 %0, 1, 0, P1;\n\t"
+      "}\n"
+      : "=r"(ok)
+      : "r"(bar_addr), "r"(parity), "r"(0x989680u)
+      : "memory");
+  if (!ok) __trap();
+}
 // the same with a bound on the number of wake-ups: a protocol error traps (the launch fails) instead of hanging the GPU
 __device__ __forceinline__ void mbar_wait_bounded(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
