@@ -943,8 +943,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
     const uint32_t sbar = pin(smem_u32(bars));                           // + 8 * index of a barrier
     const uint32_t s_stat = pin(smem_u32(sL) + row * 4);                 // L2 of this row; delta 1024 B further
     const uint32_t tlane = pin(tmem_base + lane_off);
-    const uint32_t p_row = pin(smem_u32(sP) + row * 128);
-    const uint32_t ds_row = p_row + 32768;
+    const uint32_t p_row = pin(smem_u32(sP) + row * 128);         // the dS tile is 32 KB further
     const uint32_t sw7 = static_cast<uint32_t>(row & 7);
     const uint32_t ld3 = 3u * p.Dm;
     const bool reduce_dq = NT > 1 && !p.acc;
@@ -1059,7 +1058,16 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
       const int col0 = hg * NH * DH;
       const uint32_t ts = tlane + COL_S + colbase;
       const uint32_t td = tlane + COL_DP + colbase;
+      // shared-memory offsets of this thread's two 16-byte chunks per 16-key group in the 128B-swizzled [query][key]
+      // tiles: fixed for the item, kept in registers (pin_hard) instead of ~20 instructions per group and sub-block
       const uint32_t gc = static_cast<uint32_t>(colbase >> 3);
+      uint32_t st_o0[2], st_o1[2];
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const uint32_t g0 = gc + 2 * q;
+        st_o0[q] = pin_hard(p_row + (g0 >> 3) * 16384 + (((g0 & 7) ^ sw7) << 4));
+        st_o1[q] = pin_hard(p_row + ((g0 + 1) >> 3) * 16384 + ((((g0 + 1) & 7) ^ sw7) << 4));
+      }
 #pragma unroll 1
       for (int i = 0; i < NT; ++i) {
         const int tq = p.pack ? (row & 63) : i * 128 + row;
@@ -1121,13 +1129,10 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
 #pragma unroll
           for (int q = 0; q < 2; ++q) {
             if (q * 16 < bnq) {
-              const uint32_t g0 = gc + 2 * q;
-              const uint32_t o0 = (g0 >> 3) * 16384 + (((g0 & 7) ^ sw7) << 4);
-              const uint32_t o1 = ((g0 + 1) >> 3) * 16384 + ((((g0 + 1) & 7) ^ sw7) << 4);
-              sts_v4(p_row + o0, make_uint4(su[q * 16 + 0], su[q * 16 + 1], su[q * 16 + 2], su[q * 16 + 3]));
-              sts_v4(p_row + o1, make_uint4(su[q * 16 + 4], su[q * 16 + 5], su[q * 16 + 6], su[q * 16 + 7]));
-              sts_v4(ds_row + o0, make_uint4(du[q * 16 + 0], du[q * 16 + 1], du[q * 16 + 2], du[q * 16 + 3]));
-              sts_v4(ds_row + o1, make_uint4(du[q * 16 + 4], du[q * 16 + 5], du[q * 16 + 6], du[q * 16 + 7]));
+              sts_v4(st_o0[q], make_uint4(su[q * 16 + 0], su[q * 16 + 1], su[q * 16 + 2], su[q * 16 + 3]));
+              sts_v4(st_o1[q], make_uint4(su[q * 16 + 4], su[q * 16 + 5], su[q * 16 + 6], su[q * 16 + 7]));
+              sts_v4(st_o0[q] + 32768, make_uint4(du[q * 16 + 0], du[q * 16 + 1], du[q * 16 + 2], du[q * 16 + 3]));
+              sts_v4(st_o1[q] + 32768, make_uint4(du[q * 16 + 4], du[q * 16 + 5], du[q * 16 + 6], du[q * 16 + 7]));
             }
           }
           ATT_T(t6);

@@ -269,6 +269,14 @@ __device__ __forceinline__ uint32_t pin(uint32_t v) {
   asm volatile("mov.u32 %0, %1;" : "=r"(r) : "r"(v));
   return r;
 }
+// pin() is transparent to ptxas (a PTX mov); a value read back through a warp shuffle of the own lane is not: what it
+// produces stays in its register instead of being re-derived (one SHFL, for values computed once per work item)
+__device__ __forceinline__ uint32_t pin_hard(uint32_t v) {
+  uint32_t r, lane;
+  asm volatile("mov.u32 %0, %%laneid;" : "=r"(lane));
+  asm volatile("shfl.sync.idx.b32 %0, %1, %2, 0x1f, 0xffffffff;" : "=r"(r) : "r"(v), "r"(lane));
+  return r;
+}
 __device__ __forceinline__ void mbar_arrive_a(uint32_t bar_addr) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_addr) : "memory");
 }
