@@ -621,24 +621,21 @@ struct BwdParams {
   __nv_bfloat16* dqkv;
 };
 
-// delta[(b*H + h)*S + s] = sum_j dO[b*S + s, h*DH + j] * O[b*S + s, h*DH + j]: one thread per (token, head),
-// consecutive threads read consecutive 2*DH-byte pieces of a row
+// delta[(b*H + h)*S + s] = sum_j dO[b*S + s, h*DH + j] * O[b*S + s, h*DH + j].  A thread takes one 16-byte chunk of a
+// (token, head) row piece, so a warp's loads are 512 contiguous bytes; the DH / 8 lanes of a piece combine with shuffles
+// and the first of them writes.
 template <int DH>
 __global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ d_out,
                                   float* __restrict__ delta, int B, int S, int H) {
+  constexpr int CPR = DH / 8;                                   // 16-byte chunks per (token, head)
   pdl_wait();
   pdl_trigger();
-  const long long total = static_cast<long long>(B) * S * H;
-  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
-       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int h = static_cast<int>(idx % H);
-    const long long r = idx / H;                         // b * S + s
-    const uint4* op = reinterpret_cast<const uint4*>(o + idx * DH);
-    const uint4* dp = reinterpret_cast<const uint4*>(d_out + idx * DH);
+  const long long total = static_cast<long long>(B) * S * H * CPR;      // a multiple of 4, the grid stride of 32
+  for (long long t = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; t - (threadIdx.x & 31) < total;
+       t += static_cast<long long>(gridDim.x) * blockDim.x) {
     float acc = 0.f;
-#pragma unroll
-    for (int c8 = 0; c8 < DH / 8; ++c8) {
-      const uint4 a = __ldg(dp + c8), bb = __ldg(op + c8);
+    if (t < total) {
+      const uint4 a = __ldg(reinterpret_cast<const uint4*>(d_out) + t), bb = __ldg(reinterpret_cast<const uint4*>(o) + t);
       const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {bb.x, bb.y, bb.z, bb.w};
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
@@ -647,8 +644,15 @@ __global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ o, const __n
         acc = fmaf(x.y, y.y, acc);
       }
     }
-    const long long b = r / S, s_ = r % S;
-    delta[(b * H + h) * S + s_] = acc;
+#pragma unroll
+    for (int o_ = 1; o_ < CPR; o_ <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o_);
+    if (t < total && (t % CPR) == 0) {
+      const long long idx = t / CPR;                           // (b * S + s) * H + h
+      const int h = static_cast<int>(idx % H);
+      const long long r = idx / H;
+      const long long b = r / S, s_ = r % S;
+      delta[(b * H + h) * S + s_] = acc;
+    }
   }
 }
 
@@ -1226,8 +1230,8 @@ int attn_bwd_tc_launch(const void* qkv, const void* o, const void* d_out, const 
   p.delta = delta;
   p.dqkv = reinterpret_cast<__nv_bfloat16*>(dqkv);
   {
-    const long long total = static_cast<long long>(B) * S * H;
-    const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, 8LL * device_sms()));
+    const long long total = static_cast<long long>(B) * S * H * (DH / 8);
+    const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, 32LL * device_sms()));
     cudaError_t de = csm_launch_pdl(attn_delta_kernel<DH>, dim3(blocks), dim3(256), 0, stream,
                                     reinterpret_cast<const __nv_bfloat16*>(o),
                                     reinterpret_cast<const __nv_bfloat16*>(d_out), delta, B, S, H);
